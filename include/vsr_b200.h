@@ -1,0 +1,205 @@
+/*
+ * vsr_b200.h -- C ABI of libvsr_b200.so, the B200 (sm_100a) implementation of the
+ * per-frame warp-and-fuse hot path of PlanNoa/video_super_resolution.
+ *
+ * This header is the drop-in boundary.  Every entry point
+ *   - takes raw DEVICE pointers, plain sizes and an explicit CUDA stream (passed as void*,
+ *     i.e. a cudaStream_t / CUstream); no ATen / torch types cross it;
+ *   - never allocates, frees or synchronises: outputs and workspaces are caller-allocated
+ *     (the reference convention, resample2d.py:17-19, channelnorm.py:12);
+ *   - returns 0 on success, VSR_ERR_* (<1000) for argument errors and 1000+cudaError_t
+ *     for CUDA failures (the reference returns a constant 1 and drops CUDA errors,
+ *     resample2d_cuda.cc:12,23 -- see INTEGRATION.md for the binding a maintainer adds).
+ *
+ * "ref:" comments cite the interface of /root/reference that each function replaces.
+ * Layout names: NCHW = reference layout (resample2d.py:10-11), NHWC = channels-last pixels
+ * as produced by the reference's video loader (utils/video_utils.py:23).
+ */
+#ifndef VSR_B200_H_
+#define VSR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VSR_OK 0
+#define VSR_ERR_INVALID_ARG 1   /* null pointer, non-positive size, unsupported option   */
+#define VSR_ERR_UNSUPPORTED 2   /* shape/geometry outside what the kernels implement      */
+#define VSR_ERR_WORKSPACE 3     /* caller workspace too small                             */
+#define VSR_ERR_STATE 4         /* plan used before weights were loaded, etc.             */
+#define VSR_ERR_CUDA_BASE 1000  /* 1000 + cudaError_t                                      */
+
+typedef void* vsr_stream_t; /* cudaStream_t */
+
+/* Library identification / launch accounting (bench.py's gpu_launches). */
+const char* vsr_version(void);
+/* number of kernels this library launched in the calling process since load/reset */
+uint64_t vsr_launch_count(void);
+void vsr_launch_count_reset(void);
+/* human readable text for a VSR error code (static storage) */
+const char* vsr_error_string(int code);
+
+/* ------------------------------------------------------------------------------------------
+ * a3 / a4: the pinned warp.  ref: resample2d_cuda.cc:6-13 `resample2d_cuda_forward(input1,
+ * input2, output, kernel_size, bilinear)` -> resample2d_kernel.cu:15-72,200-242.
+ * input1 (B,C,H,W) f32, flow (B,2,H,W) f32 (channel 0 horizontal), output (B,C,H,W) f32, all
+ * NCHW contiguous.  Arithmetic is the reference's, bit for bit: fp32 coordinates, border-clamped
+ * taps, tap weights formed in double, per-tap products rounded to fp32 and summed TL,TR,BL,BR.
+ * kernel_size must be 1 (the only value the reference uses, resample2d.py:44).
+ * ---------------------------------------------------------------------------------------- */
+int vsr_resample2d_forward(const float* input1, const float* flow, float* output,
+                           int B, int C, int H, int W, int kernel_size, int bilinear,
+                           vsr_stream_t stream);
+
+/* Channels-last variant used by the pipeline (frames C=3, features C=32).  src/dst (B,H,W,C)
+ * f32, flow (B,H,W,2) f32.  If norm_out != NULL it additionally receives, per pixel,
+ * sqrt(sum_c (ref[b,y,x,c] - dst[b,y,x,c])^2) with fp32 accumulation, i.e. the reference's
+ * `channelnorm(img - resampled)` (models.py:86-88) fused into the warp; `ref` may be NULL iff
+ * norm_out is NULL.  Same arithmetic as vsr_resample2d_forward. */
+int vsr_warp_nhwc_f32(const float* src, const float* flow, float* dst,
+                      const float* ref, float* norm_out,
+                      int B, int H, int W, int C, int bilinear, vsr_stream_t stream);
+
+/* Nearest-neighbour label/mask warp on u8 (north star "VOSProjection: mask/label warping"),
+ * ref arithmetic: resample2d_kernel.cu:65-70 (floor(xf + 0.5) in double, border clamp).
+ * labels/dst (B,H,W) u8, flow (B,H,W,2) f32.  Bit-exact. */
+int vsr_warp_labels_u8(const uint8_t* labels, const float* flow, uint8_t* dst,
+                       int B, int H, int W, vsr_stream_t stream);
+
+/* ref: channelnorm_cuda.cc `channelnorm_cuda_forward(input1, output, norm_deg)` ->
+ * channelnorm_kernel.cu:19-60.  input (B,C,H,W) f32 NCHW, output (B,1,H,W).  norm_deg is accepted
+ * and ignored exactly as the reference does (channelnorm_kernel.cu:53-59). */
+int vsr_channelnorm_forward(const float* input, float* output, int B, int C, int H, int W,
+                            int norm_deg, vsr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a1 / a2: flow projection (forward splat + count + normalise + hole fill), SURVEY.md App. B.
+ * ref surface: FlowProjectionModule.forward (FlowProjectionModule.py:18-33) and
+ * DepthProjectionModule.forward (DepthProjectionModule.py:12-18); the splat body itself has no
+ * reference implementation (parity unpinned, oracle/oracle.c is the contract).
+ * flow (B,h,w,2) f32; inv_depth (B,h,w) f32 > 0 or NULL (NULL = unweighted FlowProjection);
+ * outputs: proj (B,h,w,2) f32, wsum (B,h,w) f32 or NULL, count (B,h,w) i32, hole (B,h,w) u8.
+ * workspace: vsr_flow_projection_workspace_bytes(B,h,w) bytes of device memory (any contents).
+ * count / hole are bit-exact; proj / wsum are fp32 sums in nondeterministic order.
+ * ---------------------------------------------------------------------------------------- */
+size_t vsr_flow_projection_workspace_bytes(int B, int h, int w);
+int vsr_flow_projection_forward(const float* flow, const float* inv_depth,
+                                float* proj, float* wsum, int32_t* count, uint8_t* hole,
+                                void* workspace, size_t workspace_bytes,
+                                int B, int h, int w, vsr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a5: VOS mask arithmetic.  ref: VOSProjectionModule.py:22-25 (sigmoid(a)+sigmoid(b) > 0.7),
+ * utils/tools.py:76-77 (maskprocess) and network/video_super_resolution.py:58-60
+ * (MaskedArray(img, mask, fill_value=0).filled()).
+ * logits_a/logits_b (h,w) f32 -> mask (h,w) u8 in {0,1}.
+ * image (C,h,w) f32 -> masked (C,h,w) f32 = image where mask==0 else 0.
+ * ---------------------------------------------------------------------------------------- */
+int vsr_vos_threshold(const float* logits_a, const float* logits_b, uint8_t* mask,
+                      int h, int w, vsr_stream_t stream);
+int vsr_mask_fill(const float* image, const uint8_t* mask, float* masked,
+                  int C, int h, int w, vsr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a6 / a7: the fusion / upsampling convolutions (SRFBN + per-pixel fc over the map axis).
+ * ref: SRProjectionModule.forward (SRProjectionModule.py:133-147), FeedbackBlock (:7-93),
+ * blocks.py:7-74, with the INTENDED dense-concat dataflow.
+ *
+ * A plan owns nothing on the device: weights live in a caller buffer that
+ * vsr_srfbn_pack_weights fills, activations in a caller workspace.
+ * Geometry: x4 only (k=8,s=4,p=2, SRProjectionModule.py:101-103), num_features=32,
+ * num_groups=6, num_steps>=1, M stacked maps (reference: 8).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct vsr_srfbn_plan vsr_srfbn_plan;
+
+typedef struct vsr_srfbn_config {
+  int32_t num_maps;      /* M: maps stacked along dim 0 (video_super_resolution.py:40), fc in-features */
+  int32_t h, w;          /* LR size; output is (4h, 4w)                                          */
+  int32_t num_steps;     /* SRProjectionModule num_steps (default 3)                             */
+  int32_t num_groups;    /* must be 6                                                            */
+  int32_t num_features;  /* must be 32                                                           */
+  int32_t upscale;       /* must be 4                                                            */
+} vsr_srfbn_config;
+
+/* Host-side weights in the reference's state-dict layout, fp32, host
+ * memory.  Arrays indexed by group.  PReLU slopes are single floats (blocks.py:70-71). */
+typedef struct vsr_srfbn_weights {
+  const float* sub_mean_bias;      /* (3)   MeanShift bias, weight is identity (blocks.py:46-55)  */
+  const float* add_mean_bias;      /* (3)                                                         */
+  const float* conv_in_w;          /* (128,3,3,3)  */
+  const float* conv_in_b;          /* (128)        */
+  float conv_in_slope;
+  const float* feat_in_w;          /* (32,128,1,1) */
+  const float* feat_in_b;
+  float feat_in_slope;
+  const float* compress_in_w;      /* (32,64,1,1)  */
+  const float* compress_in_b;
+  float compress_in_slope;
+  const float* up_w[6];            /* ConvTranspose (32 in,32 out,8,8) */
+  const float* up_b[6];
+  float up_slope[6];
+  const float* down_w[6];          /* Conv (32 out,32 in,8,8) */
+  const float* down_b[6];
+  float down_slope[6];
+  const float* uptran_w[5];        /* (32,32*(i+2),1,1), i=0..4 */
+  const float* uptran_b[5];
+  float uptran_slope[5];
+  const float* downtran_w[5];
+  const float* downtran_b[5];
+  float downtran_slope[5];
+  const float* compress_out_w;     /* (32,192,1,1) */
+  const float* compress_out_b;
+  float compress_out_slope;
+  const float* out_w;              /* ConvTranspose (32,32,8,8) */
+  const float* out_b;
+  float out_slope;
+  const float* conv_out_w;         /* (3,32,3,3), no activation */
+  const float* conv_out_b;
+  const float* fc0_w;              /* (32,M) */
+  const float* fc0_b;              /* (32)   */
+  const float* fc2_w;              /* (1,32) */
+  const float* fc2_b;              /* (1)    */
+} vsr_srfbn_weights;
+
+int vsr_srfbn_plan_create(const vsr_srfbn_config* cfg, vsr_srfbn_plan** out_plan);
+void vsr_srfbn_plan_destroy(vsr_srfbn_plan* plan);
+/* bytes of device memory the caller must provide */
+size_t vsr_srfbn_weight_bytes(const vsr_srfbn_plan* plan);
+size_t vsr_srfbn_workspace_bytes(const vsr_srfbn_plan* plan);
+/* Converts the fp32 state-dict weights to the packed BF16 GEMM operands in host memory
+ * (`host_packed`, vsr_srfbn_weight_bytes bytes); the caller copies them to the device. */
+int vsr_srfbn_pack_weights(const vsr_srfbn_plan* plan, const vsr_srfbn_weights* w, void* host_packed);
+/* Binds device buffers (packed weights + workspace) and builds the TMA descriptors. */
+int vsr_srfbn_bind(vsr_srfbn_plan* plan, const void* dev_weights, void* dev_workspace,
+                   size_t workspace_bytes);
+/* x: (M,3,h,w) f32 NCHW, 0..255 (video_super_resolution.py:40,62); y: (1,3,4h,4w) f32. */
+int vsr_srfbn_forward(vsr_srfbn_plan* plan, const float* x, float* y, vsr_stream_t stream);
+/* Test hook: per-map network output before the fc fuse, (M,3,4h,4w) f32 (SRProjectionModule.py:143);
+ * valid after vsr_srfbn_forward on the same stream. */
+int vsr_srfbn_debug_premix(const vsr_srfbn_plan* plan, float* out_maps, vsr_stream_t stream);
+
+/* Single-layer test hooks: run ONE layer of the stack through the same tcgen05 kernels the plan
+ * uses, on BF16 channels-last operands, so tests can compare layer by layer with torch.nn fp32
+ * (SURVEY.md Appendix C).  All pointers device.  `act`: 1 = PReLU(slope), 0 = none.
+ *   pointwise: y[r, 0:32] = act(sum_k x[r, k] * w[n, k] + b[n]),  x (rows, K) bf16, K%32==0, K<=224
+ *   deconv   : ConvTranspose2d(32,32,8,4,2): x (B,h,w,32) bf16 -> y (B,4h,4w,32) bf16
+ *   downconv : Conv2d(32,32,8,4,2):          x (B,4h,4w,32) bf16 -> y (B,h,w,32) bf16
+ * w/b in the reference (torch) layouts, fp32, HOST memory. */
+int vsr_test_pointwise(const void* x_bf16, int64_t rows, int K, const float* w_host,
+                       const float* b_host, float slope, int act, void* y_bf16,
+                       void* workspace, size_t workspace_bytes, vsr_stream_t stream);
+int vsr_test_deconv(const void* x_bf16, int B, int h, int w, const float* w_host,
+                    const float* b_host, float slope, void* y_bf16,
+                    void* workspace, size_t workspace_bytes, vsr_stream_t stream);
+int vsr_test_downconv(const void* x_bf16, int B, int h, int w, const float* w_host,
+                      const float* b_host, float slope, void* y_bf16,
+                      void* workspace, size_t workspace_bytes, vsr_stream_t stream);
+size_t vsr_test_workspace_bytes(int B, int h, int w);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSR_B200_H_ */

@@ -1,0 +1,187 @@
+"""ctypes front-end of the CPU oracle (oracle/oracle.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package never imports this module.
+
+All functions take and return numpy arrays; layouts are stated per function.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+_lib = None
+
+_f32p = ctypes.POINTER(ctypes.c_float)
+_u8p = ctypes.POINTER(ctypes.c_uint8)
+_i32p = ctypes.POINTER(ctypes.c_int32)
+
+
+def build(force: bool = False) -> str:
+    """Compile oracle.c with gcc (recipe: oracle/Makefile)."""
+    src = os.path.join(_HERE, "oracle.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "all"])
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(_LIB_PATH)
+        L = ctypes.c_long
+        I = ctypes.c_int
+        _lib.or_resample2d.argtypes = [_f32p, _f32p, _f32p, I, I, I, I] + [L] * 12 + [I, I, I, I]
+        _lib.or_resample2d.restype = None
+        _lib.or_warp_labels.argtypes = [_u8p, _f32p, _u8p, I, I, I]
+        _lib.or_warp_labels.restype = None
+        _lib.or_channelnorm.argtypes = [_f32p, _f32p, I, I, I, I, L, L, L, L]
+        _lib.or_channelnorm.restype = None
+        _lib.or_flow_projection.argtypes = [_f32p, _f32p, _f32p, _f32p, _i32p, _u8p, I, I, I]
+        _lib.or_flow_projection.restype = None
+        _lib.or_vos_threshold.argtypes = [_f32p, _f32p, _u8p, L]
+        _lib.or_vos_threshold.restype = None
+        _lib.or_mask_fill.argtypes = [_f32p, _u8p, _f32p, I, L]
+        _lib.or_mask_fill.restype = None
+    return _lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+def _c(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def _fan_rows(fn, H, threads):
+    """Run fn(y0, y1) over `threads` row ranges (ctypes drops the GIL during the C call)."""
+    threads = max(1, min(int(threads), H))
+    if threads == 1:
+        fn(0, H)
+        return
+    edges = np.linspace(0, H, threads + 1).astype(int)
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(lambda i: fn(int(edges[i]), int(edges[i + 1])), range(threads)))
+
+
+def resample2d_nchw(input1, flow, kernel_size=1, bilinear=True, threads=1):
+    """Reference layout: input1 (B,C,H,W), flow (B,2,H,W) -> (B,C,H,W).
+    ref: resample2d.py:8-23, resample2d_kernel.cu:15-72."""
+    input1 = _c(input1, np.float32)
+    flow = _c(flow, np.float32)
+    B, C, H, W = input1.shape
+    assert flow.shape == (B, 2, H, W)
+    out = np.zeros((B, C, H, W), np.float32)
+    L = lib()
+
+    def run(y0, y1):
+        L.or_resample2d(_p(input1, _f32p), _p(flow, _f32p), _p(out, _f32p), B, C, H, W,
+                        C * H * W, H * W, W, 1, 2 * H * W, H * W, W, 1, C * H * W, H * W, W, 1,
+                        int(kernel_size), int(bool(bilinear)), y0, y1)
+
+    _fan_rows(run, H, threads)
+    return out
+
+
+def warp_nhwc(src, flow, bilinear=True, threads=1):
+    """Pipeline layout: src (B,H,W,C), flow (B,H,W,2) -> (B,H,W,C); same arithmetic."""
+    src = _c(src, np.float32)
+    flow = _c(flow, np.float32)
+    B, H, W, C = src.shape
+    assert flow.shape == (B, H, W, 2)
+    out = np.zeros((B, H, W, C), np.float32)
+    L = lib()
+
+    def run(y0, y1):
+        L.or_resample2d(_p(src, _f32p), _p(flow, _f32p), _p(out, _f32p), B, C, H, W,
+                        H * W * C, 1, W * C, C, H * W * 2, 1, W * 2, 2, H * W * C, 1, W * C, C,
+                        1, int(bool(bilinear)), y0, y1)
+
+    _fan_rows(run, H, threads)
+    return out
+
+
+def warp_labels(labels, flow):
+    """labels (B,H,W) u8, flow (B,H,W,2) -> (B,H,W) u8.  ref: resample2d_kernel.cu:65-70."""
+    labels = _c(labels, np.uint8)
+    flow = _c(flow, np.float32)
+    B, H, W = labels.shape
+    out = np.zeros((B, H, W), np.uint8)
+    lib().or_warp_labels(_p(labels, _u8p), _p(flow, _f32p), _p(out, _u8p), B, H, W)
+    return out
+
+
+def channelnorm_nchw(x):
+    """x (B,C,H,W) -> (B,1,H,W).  ref: channelnorm_kernel.cu:19-60."""
+    x = _c(x, np.float32)
+    B, C, H, W = x.shape
+    out = np.zeros((B, 1, H, W), np.float32)
+    lib().or_channelnorm(_p(x, _f32p), _p(out, _f32p), B, C, H, W, C * H * W, H * W, W, 1)
+    return out
+
+
+def channelnorm_nhwc(x):
+    """x (B,H,W,C) -> (B,H,W)."""
+    x = _c(x, np.float32)
+    B, H, W, C = x.shape
+    out = np.zeros((B, H, W), np.float32)
+    lib().or_channelnorm(_p(x, _f32p), _p(out, _f32p), B, C, H, W, H * W * C, 1, W * C, C)
+    return out
+
+
+def flow_projection(flow, inv_depth=None, threads=1):
+    """flow (B,h,w,2), inv_depth (B,h,w)|None -> proj (B,h,w,2), wsum (B,h,w), count i32, hole u8.
+    SURVEY.md Appendix B (PARITY UNPINNED: no reference implementation exists)."""
+    flow = _c(flow, np.float32)
+    B, h, w, two = flow.shape
+    assert two == 2
+    if inv_depth is not None:
+        inv_depth = _c(inv_depth, np.float32)
+        assert inv_depth.shape == (B, h, w)
+    proj = np.zeros((B, h, w, 2), np.float32)
+    wsum = np.zeros((B, h, w), np.float32)
+    count = np.zeros((B, h, w), np.int32)
+    hole = np.zeros((B, h, w), np.uint8)
+    L = lib()
+
+    def one(b):
+        L.or_flow_projection(_p(flow[b:b + 1], _f32p),
+                             _p(inv_depth[b:b + 1], _f32p) if inv_depth is not None else None,
+                             _p(proj[b:b + 1], _f32p), _p(wsum[b:b + 1], _f32p),
+                             _p(count[b:b + 1], _i32p), _p(hole[b:b + 1], _u8p), 1, h, w)
+
+    threads = max(1, min(int(threads), B))
+    if threads == 1:
+        for b in range(B):
+            one(b)
+    else:
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(one, range(B)))
+    return proj, wsum, count, hole
+
+
+def vos_threshold(logits_a, logits_b):
+    """(h,w) f32 x2 -> (h,w) u8.  ref: VOSProjectionModule.py:22-25."""
+    a = _c(logits_a, np.float32)
+    b = _c(logits_b, np.float32)
+    out = np.zeros(a.shape, np.uint8)
+    lib().or_vos_threshold(_p(a, _f32p), _p(b, _f32p), _p(out, _u8p), a.size)
+    return out
+
+
+def mask_fill(image, mask):
+    """image (C,h,w) f32, mask (h,w) u8 -> (C,h,w).  ref: video_super_resolution.py:58-60."""
+    image = _c(image, np.float32)
+    mask = _c(mask, np.uint8)
+    C = image.shape[0]
+    out = np.zeros_like(image)
+    lib().or_mask_fill(_p(image, _f32p), _p(mask, _u8p), _p(out, _f32p), C, mask.size)
+    return out

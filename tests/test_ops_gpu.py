@@ -1,0 +1,182 @@
+"""GPU parity: the CUDA warp / projection / mask kernels (through the C ABI) against the CPU oracle
+on the same seeded inputs.  Bit-exact where the arithmetic is a gather or integer; max-abs <= 1e-3
+where fp32 atomics reorder sums (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+from video_super_resolution_b200 import ops, synthetic
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = 1e-3  # north star: max-abs <= 1e-3 fp32 for projection / warp
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize("shape", [(1, 3, 64, 64), (2, 3, 37, 53), (1, 2, 16, 130), (3, 5, 9, 7)])
+@pytest.mark.parametrize("bilinear", [True, False])
+def test_resample2d_nchw_bit_exact(shape, bilinear):
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(B * 1000 + W)
+    img = torch.rand(shape, generator=g) * 255
+    flow = (torch.rand((B, 2, H, W), generator=g) - 0.5) * 24   # reaches beyond the borders
+    flow[:, :, 0, 0] = 0.5                                        # exact half-pixel tie
+    flow[:, :, -1, -1] = 1000.0                                   # far out of range -> clamp
+    got = _np(ops.resample2d(img.to(DEV), flow.to(DEV), 1, bilinear))
+    want = orc.resample2d_nchw(img.numpy(), flow.numpy(), 1, bilinear)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("C", [3, 32, 4, 5, 1])
+@pytest.mark.parametrize("bilinear", [True, False])
+def test_warp_nhwc_bit_exact(C, bilinear):
+    B, H, W = 2, 45, 71
+    g = torch.Generator().manual_seed(C)
+    src = torch.rand((B, H, W, C), generator=g) * 255
+    flow = synthetic.smooth_flow(B, H, W, 8.0, seed=C) + (torch.rand((B, H, W, 2), generator=g) - 0.5)
+    got = _np(ops.warp(src.to(DEV), flow.to(DEV), bilinear))
+    want = orc.warp_nhwc(src.numpy(), flow.numpy(), bilinear)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("C", [3, 8])
+def test_warp_fused_residual_norm(C):
+    B, H, W = 2, 33, 65
+    g = torch.Generator().manual_seed(10 + C)
+    src = torch.rand((B, H, W, C), generator=g) * 255
+    ref = torch.rand((B, H, W, C), generator=g) * 255
+    flow = synthetic.smooth_flow(B, H, W, 6.0, seed=3)
+    warped, norm = ops.warp(src.to(DEV), flow.to(DEV), True, ref=ref.to(DEV))
+    want_w = orc.warp_nhwc(src.numpy(), flow.numpy(), True)
+    want_n = orc.channelnorm_nhwc(ref.numpy() - want_w)
+    assert np.array_equal(_np(warped), want_w)
+    assert np.array_equal(_np(norm), want_n)
+
+
+def test_warp_unaligned_views_and_ragged_tail():
+    # 1 pixel short of a vector multiple, and an output carved at a non-16-byte offset
+    B, H, W = 1, 17, 19
+    g = torch.Generator().manual_seed(5)
+    src = torch.rand((B, H, W, 3), generator=g)
+    flow = (torch.rand((B, H, W, 2), generator=g) - 0.5) * 5
+    got = _np(ops.warp(src.to(DEV), flow.to(DEV)))
+    assert np.array_equal(got, orc.warp_nhwc(src.numpy(), flow.numpy()))
+
+
+@pytest.mark.parametrize("shape", [(1, 64, 64), (3, 31, 45), (2, 8, 1023)])
+def test_label_warp_bit_exact(shape):
+    B, H, W = shape
+    lab = synthetic.labels(B, H, W, seed=W)
+    flow = synthetic.smooth_flow(B, H, W, 8.0, seed=H)
+    flow[:, 0, 0, :] = 0.5
+    got = _np(ops.warp_labels(lab.to(DEV), flow.to(DEV)))
+    assert got.dtype == np.uint8
+    assert np.array_equal(got, orc.warp_labels(lab.numpy(), flow.numpy()))
+
+
+@pytest.mark.parametrize("shape", [(1, 3, 64, 64), (2, 2, 19, 33), (1, 7, 5, 5)])
+def test_channelnorm_bit_exact(shape):
+    x = torch.randn(shape, generator=torch.Generator().manual_seed(shape[1])) * 30
+    got = _np(ops.channelnorm(x.to(DEV)))
+    assert np.array_equal(got, orc.channelnorm_nchw(x.numpy()))
+
+
+def _check_projection(flow, inv):
+    proj, wsum, count, hole = ops.project_flow(flow.to(DEV), inv.to(DEV) if inv is not None else None)
+    o_proj, o_wsum, o_count, o_hole = orc.flow_projection(flow.numpy(), inv.numpy() if inv is not None else None)
+    assert np.array_equal(_np(count), o_count)            # bit-exact (north star)
+    assert np.array_equal(_np(hole), o_hole)              # bit-exact
+    assert np.abs(_np(proj) - o_proj).max() <= TOL
+    assert np.abs(_np(wsum) - o_wsum).max() <= TOL * max(1.0, float(o_wsum.max()))
+    return o_count, o_hole
+
+
+@pytest.mark.parametrize("shape", [(1, 64, 64), (2, 37, 70), (1, 5, 3), (3, 130, 33)])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_projection_smooth_flow(shape, weighted):
+    B, h, w = shape
+    flow = synthetic.smooth_flow(B, h, w, 8.0, seed=h)
+    inv = synthetic.inv_depth(B, h, w, seed=w) if weighted else None
+    _check_projection(flow, inv)
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+def test_projection_collision_stress_random_flow(weighted):
+    B, h, w = 2, 96, 160
+    flow = synthetic.random_flow(B, h, w, 64.0, seed=1)
+    inv = synthetic.inv_depth(B, h, w, seed=2) if weighted else None
+    count, hole = _check_projection(flow, inv)
+    assert hole.any() and count.max() >= 4
+
+
+def test_projection_dense_occlusion_fill_band():
+    B, h, w = 2, 72, 200
+    flow, inv = synthetic.occlusion_scene(B, h, w, shift=64.0, seed=4)
+    count, hole = _check_projection(flow, inv)
+    assert hole.sum() > 0.05 * hole.size                   # the 64-px trailing band
+
+
+def test_projection_edge_cases():
+    # zero flow (duplicate clamped targets at the borders), all out of range, NaN flow, integer flow
+    z = torch.zeros((1, 9, 11, 2))
+    _check_projection(z, None)
+    _check_projection(torch.full((1, 6, 6, 2), 500.0), None)
+    n = torch.zeros((1, 6, 7, 2))
+    n[0, 2, 3, 0] = float("nan")
+    _check_projection(n, None)
+    i = torch.zeros((1, 12, 40, 2))
+    i[..., 0] = 3.0
+    i[..., 1] = -2.0
+    _check_projection(i, synthetic.inv_depth(1, 12, 40, seed=9))
+
+
+def test_projection_full_size_properties():
+    # C3 size (1080p): size-independent properties instead of the slow CPU oracle
+    B, h, w = 1, 1080, 1920
+    flow = synthetic.smooth_flow(B, h, w, 8.0, seed=0).to(DEV)
+    inv = synthetic.inv_depth(B, h, w, seed=1).to(DEV)
+    proj, wsum, count, hole = ops.project_flow(flow, inv)
+    x2 = torch.arange(w, device=DEV).view(1, 1, w) + flow[..., 0]
+    y2 = torch.arange(h, device=DEV).view(1, h, 1) + flow[..., 1]
+    valid = (x2 >= 0) & (x2 <= w - 1) & (y2 >= 0) & (y2 <= h - 1)
+    assert int(count.sum()) == 4 * int(valid.sum())          # every valid source hits 4 targets
+    assert torch.equal(hole.bool(), count == 0)
+    wtot = (inv * valid).sum().item() * 4
+    assert abs(wsum.sum().item() - wtot) <= 1e-4 * wtot      # linearity: total weight conserved
+    assert proj.abs().max().item() <= 8.0 + 1e-3             # a weighted mean of |flow| <= 8
+    # idempotent / deterministic integers
+    _, _, count2, hole2 = ops.project_flow(flow, inv)
+    assert torch.equal(count, count2) and torch.equal(hole, hole2)
+
+
+def test_vos_threshold_and_mask_fill_bit_exact():
+    la, lb = synthetic.logits(67, 129, seed=3)
+    mask = ops.vos_threshold(la.to(DEV), lb.to(DEV))
+    want = orc.vos_threshold(la.numpy(), lb.numpy())
+    assert np.array_equal(_np(mask), want)
+    assert 0 < want.mean() < 1
+    img = torch.rand((3, 67, 129), generator=torch.Generator().manual_seed(1)) * 255
+    got = _np(ops.mask_fill(img.to(DEV), mask))
+    assert np.array_equal(got, orc.mask_fill(img.numpy(), want))
+
+
+def test_golden_vos_fixture_on_gpu(golden_dir):
+    import os
+    z = np.load(os.path.join(golden_dir, "vos_mask.npz"))
+    la = torch.from_numpy(z["logits"])
+    mask = ops.vos_threshold(la[0, 0].contiguous().to(DEV), la[1, 0].contiguous().to(DEV))
+    assert np.array_equal(_np(mask).astype(np.float32), z["mask"])
+    filled = ops.mask_fill(torch.from_numpy(z["image"]).to(DEV), mask)
+    assert np.array_equal(_np(filled), z["filled"])
+
+
+def test_launches_are_counted():
+    from video_super_resolution_b200 import _lib
+    _lib.launch_count_reset()
+    x = torch.zeros((1, 3, 8, 8), device=DEV)
+    ops.channelnorm(x)
+    assert _lib.launch_count() == 1

@@ -1,0 +1,112 @@
+"""CPU: properties of the C oracle itself (hand-checkable cases)."""
+import numpy as np
+
+from oracle import oracle as orc
+
+
+def test_resample_identity_and_integer_shift():
+    rng = np.random.default_rng(0)
+    img = rng.random((2, 3, 7, 9)).astype(np.float32)
+    zero = np.zeros((2, 2, 7, 9), np.float32)
+    assert np.array_equal(orc.resample2d_nchw(img, zero), img)
+    flow = zero.copy()
+    flow[:, 0] = 2.0   # channel 0 is horizontal (resample2d_kernel.cu:40)
+    flow[:, 1] = -1.0
+    out = orc.resample2d_nchw(img, flow)
+    xs = np.clip(np.arange(9) + 2, 0, 8)
+    ys = np.clip(np.arange(7) - 1, 0, 6)
+    assert np.array_equal(out, img[:, :, ys][:, :, :, xs])   # border replicate, no zero padding
+
+
+def test_resample_half_pixel_is_mean_and_nearest_ties_round_up():
+    img = np.arange(12, dtype=np.float32).reshape(1, 1, 3, 4)
+    flow = np.zeros((1, 2, 3, 4), np.float32)
+    flow[:, 0] = 0.5
+    out = orc.resample2d_nchw(img, flow)
+    assert np.allclose(out[0, 0, :, :3], img[0, 0, :, :3] + 0.5)
+    assert np.array_equal(out[0, 0, :, 3], img[0, 0, :, 3])  # xL = xR = W-1 at the border
+    near = orc.resample2d_nchw(img, flow, bilinear=False)
+    assert np.array_equal(near[0, 0, :, :3], img[0, 0, :, 1:])  # floor(x + 0.5 + 0.5) = x + 1
+
+
+def test_nhwc_and_nchw_agree_bitwise():
+    rng = np.random.default_rng(1)
+    img = (rng.random((2, 11, 13, 3)) * 255).astype(np.float32)
+    flow = ((rng.random((2, 11, 13, 2)) - 0.5) * 9).astype(np.float32)
+    a = orc.warp_nhwc(img, flow)
+    b = orc.resample2d_nchw(img.transpose(0, 3, 1, 2), flow.transpose(0, 3, 1, 2))
+    assert np.array_equal(a, b.transpose(0, 2, 3, 1))
+    assert np.array_equal(orc.warp_nhwc(img, flow, threads=3), a)
+
+
+def test_label_warp_matches_nearest_resample():
+    rng = np.random.default_rng(2)
+    lab = (rng.random((2, 9, 10)) > 0.6).astype(np.uint8)
+    flow = ((rng.random((2, 9, 10, 2)) - 0.5) * 7).astype(np.float32)
+    a = orc.warp_labels(lab, flow)
+    b = orc.warp_nhwc(lab[..., None].astype(np.float32), flow, bilinear=False)[..., 0]
+    assert np.array_equal(a, b.astype(np.uint8))
+
+
+def test_channelnorm():
+    x = np.array([3.0, 4.0], np.float32).reshape(1, 2, 1, 1)
+    assert orc.channelnorm_nchw(x)[0, 0, 0, 0] == 5.0
+    rng = np.random.default_rng(3)
+    y = rng.random((2, 5, 4, 6)).astype(np.float32)
+    assert np.allclose(orc.channelnorm_nchw(y)[:, 0], np.sqrt((y.astype(np.float64) ** 2).sum(1)), rtol=1e-6)
+    assert np.array_equal(orc.channelnorm_nhwc(y.transpose(0, 2, 3, 1)), orc.channelnorm_nchw(y)[:, 0])
+
+
+def test_flow_projection_zero_flow():
+    h, w = 5, 6
+    flow = np.zeros((1, h, w, 2), np.float32)
+    proj, wsum, count, hole = orc.flow_projection(flow)
+    # each pixel splats to itself, right, below, below-right (clamped duplicates at the borders)
+    expect = np.zeros((h, w), np.int32)
+    for y in range(h):
+        for x in range(w):
+            for yy in (y, min(y + 1, h - 1)):
+                for xx in (x, min(x + 1, w - 1)):
+                    expect[yy, xx] += 1
+    assert np.array_equal(count[0], expect)
+    assert count.sum() == 4 * h * w
+    assert not hole.any() and not proj.any()
+    assert np.array_equal(wsum[0], expect.astype(np.float32))
+
+
+def test_flow_projection_constant_shift_holes_and_fill():
+    h, w = 6, 8
+    flow = np.zeros((1, h, w, 2), np.float32)
+    flow[..., 0] = 3.0
+    proj, wsum, count, hole = orc.flow_projection(flow)
+    assert hole[0, :, :3].all() and not hole[0, :, 3:].any()      # trailing band is all holes
+    assert np.allclose(proj[0, :, 3:, 0], -3.0) and np.allclose(proj[0, :, 3:, 1], 0.0)
+    assert np.allclose(proj[0, :, :3, 0], -3.0)                    # filled from the right neighbour
+    assert (count[0][hole[0] == 1] == 0).all()
+
+
+def test_flow_projection_all_out_of_range_stays_zero():
+    flow = np.full((1, 4, 4, 2), 100.0, np.float32)
+    proj, wsum, count, hole = orc.flow_projection(flow)
+    assert hole.all() and not count.any() and not proj.any() and not wsum.any()
+
+
+def test_depth_projection_nearer_surface_dominates():
+    h, w = 1, 6
+    flow = np.zeros((1, h, w, 2), np.float32)
+    inv = np.full((1, h, w), 0.1, np.float32)
+    flow[0, 0, 0, 0] = 3.0     # pixel 0 (near, inv depth 1) lands on pixel 3 (far, static)
+    inv[0, 0, 0] = 1.0
+    proj, wsum, count, hole = orc.flow_projection(flow, inv)
+    plain, _, _, _ = orc.flow_projection(flow)
+    assert proj[0, 0, 3, 0] < plain[0, 0, 3, 0] < 0    # the weighted estimate sits nearer to -3
+    # h == 1: yB == yT, so every contribution lands twice (clamped duplicate target, App. B step 2)
+    assert np.isclose(wsum[0, 0, 3], 2 * (1.0 + 0.1 + 0.1))
+    assert np.array_equal(count, orc.flow_projection(flow)[2])   # counts do not depend on depth
+
+
+def test_flow_projection_nan_flow_is_skipped():
+    flow = np.zeros((1, 3, 3, 2), np.float32)
+    flow[0, 1, 1, 0] = np.nan
+    _, _, count, _ = orc.flow_projection(flow)
+    assert count.sum() == 4 * 8

@@ -1,0 +1,52 @@
+// common.cuh -- shared helpers for libvsr_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+
+#include "../../include/vsr_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libvsr_b200 is written for sm_100a (Blackwell B200) only"
+#endif
+
+namespace vsr {
+
+extern std::atomic<uint64_t> g_launch_count;
+
+inline int cuda_status(cudaError_t e) { return e == cudaSuccess ? VSR_OK : VSR_ERR_CUDA_BASE + (int)e; }
+
+// Call right after a <<<>>> launch: counts it and converts a launch error into a VSR code.
+inline int after_launch() {
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return cuda_status(cudaGetLastError());
+}
+
+inline cudaStream_t as_stream(vsr_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+constexpr int kNumSMs = 148;  // B200
+
+__host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// streaming (read-once) loads / write-once stores: keep them out of L1
+__device__ __forceinline__ float2 ldg_stream_f2(const float2* p) {
+  float2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_stream_f4(float4* p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+}  // namespace vsr

@@ -1,0 +1,372 @@
+// warp.cu -- backward warps of the hot path: bilinear / nearest resampling by a pixel-unit flow,
+// the fused warp-residual channel norm, the u8 label warp and the stand-alone channel norm.
+//
+// Arithmetic contract (bit for bit, so the result equals the reference kernel's output):
+//   ref: my_packages/FlowProjection/networks/resample2d_package/resample2d_kernel.cu:15-72
+//        my_packages/FlowProjection/networks/channelnorm_package/channelnorm_kernel.cu:19-60
+// What is different is everything around the arithmetic: the flow is read once per pixel instead
+// of once per (pixel, channel); tap indices and weights are computed once per pixel; the
+// channels-last kernels move 16-byte vectors and stage the C=3 output through shared memory so
+// that every global store is a full 128-bit coalesced transaction.
+#include "common.cuh"
+
+namespace vsr {
+namespace {
+
+constexpr int kThreads = 256;
+
+struct Taps {
+  int xL, xR, yT, yB;
+  double wTL, wTR, wBL, wBR;
+};
+
+// resample2d_kernel.cu:40-52: fp32 coordinates, floor, border clamp with the output dims;
+// :56-59: the `1.` literals make the four weights doubles.
+__device__ __forceinline__ Taps bilinear_taps(int x, int y, float dx, float dy, int W, int H) {
+  Taps t;
+  float xf = __fadd_rn((float)x, dx);
+  float yf = __fadd_rn((float)y, dy);
+  float fx0 = floorf(xf), fy0 = floorf(yf);
+  double alpha = (double)__fsub_rn(xf, fx0);
+  double beta = (double)__fsub_rn(yf, fy0);
+  t.xL = max(min((int)fx0, W - 1), 0);
+  t.xR = max(min((int)__fadd_rn(fx0, 1.0f), W - 1), 0);
+  t.yT = max(min((int)fy0, H - 1), 0);
+  t.yB = max(min((int)__fadd_rn(fy0, 1.0f), H - 1), 0);
+  double ia = __dsub_rn(1.0, alpha), ib = __dsub_rn(1.0, beta);
+  t.wTL = __dmul_rn(ia, ib);
+  t.wTR = __dmul_rn(alpha, ib);
+  t.wBL = __dmul_rn(ia, beta);
+  t.wBR = __dmul_rn(alpha, beta);
+  return t;
+}
+
+// :56-59 each product is formed in double, rounded to fp32, then accumulated in fp32 (TL,TR,BL,BR)
+__device__ __forceinline__ float blend(const Taps& t, float tl, float tr, float bl, float br) {
+  float v = 0.0f;
+  v = __fadd_rn(v, __double2float_rn(__dmul_rn(t.wTL, (double)tl)));
+  v = __fadd_rn(v, __double2float_rn(__dmul_rn(t.wTR, (double)tr)));
+  v = __fadd_rn(v, __double2float_rn(__dmul_rn(t.wBL, (double)bl)));
+  v = __fadd_rn(v, __double2float_rn(__dmul_rn(t.wBR, (double)br)));
+  return v;
+}
+
+// :65-70 `floor(xf + 0.5)`: the literal promotes to double; ties go up.
+__device__ __forceinline__ void nearest_tap(int x, int y, float dx, float dy, int W, int H, int& xN, int& yN) {
+  float xf = __fadd_rn((float)x, dx);
+  float yf = __fadd_rn((float)y, dy);
+  xN = max(min((int)floor(__dadd_rn((double)xf, 0.5)), W - 1), 0);
+  yN = max(min((int)floor(__dadd_rn((double)yf, 0.5)), H - 1), 0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Reference layout (NCHW).  One thread per (b, y, x); the channel loop re-uses taps and weights.
+// Loads/stores are coalesced along x for every channel plane.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+resample2d_nchw_kernel(const float* __restrict__ in1, const float* __restrict__ flow, float* __restrict__ out,
+                       int B, int C, int H, int W, int bilinear) {
+  const int64_t HW = (int64_t)H * W;
+  const int64_t n = (int64_t)B * HW;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int x = (int)(i % W);
+    int y = (int)((i / W) % H);
+    int b = (int)(i / HW);
+    const float* fl = flow + (int64_t)b * 2 * HW + (int64_t)y * W + x;
+    float dx = __ldg(fl), dy = __ldg(fl + HW);
+    const float* src = in1 + (int64_t)b * C * HW;
+    float* dst = out + (int64_t)b * C * HW + (int64_t)y * W + x;
+    if (bilinear) {
+      Taps t = bilinear_taps(x, y, dx, dy, W, H);
+      int64_t oTL = (int64_t)t.yT * W + t.xL, oTR = (int64_t)t.yT * W + t.xR;
+      int64_t oBL = (int64_t)t.yB * W + t.xL, oBR = (int64_t)t.yB * W + t.xR;
+#pragma unroll 3
+      for (int c = 0; c < C; ++c) {
+        const float* p = src + (int64_t)c * HW;
+        dst[(int64_t)c * HW] = blend(t, __ldg(p + oTL), __ldg(p + oTR), __ldg(p + oBL), __ldg(p + oBR));
+      }
+    } else {
+      int xN, yN;
+      nearest_tap(x, y, dx, dy, W, H, xN, yN);
+      int64_t o = (int64_t)yN * W + xN;
+      for (int c = 0; c < C; ++c) dst[(int64_t)c * HW] = __ldg(src + (int64_t)c * HW + o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Channels-last, C == 3 (frames).  A block owns 256 consecutive pixels; results are staged in
+// shared memory and leave as 192 coalesced float4 stores.  Optional fused residual norm
+// sqrt(sum_c (ref - warped)^2) (models.py:86-88 = resample -> subtract -> channelnorm).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+warp_nhwc3_kernel(const float* __restrict__ src, const float* __restrict__ flow, float* __restrict__ dst,
+                  const float* __restrict__ ref, float* __restrict__ norm_out,
+                  int64_t n_pix, int H, int W, int bilinear, int vec_store) {
+  __shared__ __align__(16) float stage[kThreads * 3];
+  const int64_t HW = (int64_t)H * W;
+  for (int64_t base = (int64_t)blockIdx.x * kThreads; base < n_pix; base += (int64_t)gridDim.x * kThreads) {
+    int64_t i = base + threadIdx.x;
+    float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+    if (i < n_pix) {
+      int x = (int)(i % W);
+      int y = (int)((i / W) % H);
+      int64_t b = i / HW;
+      float2 f = ldg_stream_f2(reinterpret_cast<const float2*>(flow) + i);
+      const float* s = src + b * HW * 3;
+      if (bilinear) {
+        Taps t = bilinear_taps(x, y, f.x, f.y, W, H);
+        const float* pTL = s + ((int64_t)t.yT * W + t.xL) * 3;
+        const float* pTR = s + ((int64_t)t.yT * W + t.xR) * 3;
+        const float* pBL = s + ((int64_t)t.yB * W + t.xL) * 3;
+        const float* pBR = s + ((int64_t)t.yB * W + t.xR) * 3;
+        v0 = blend(t, __ldg(pTL + 0), __ldg(pTR + 0), __ldg(pBL + 0), __ldg(pBR + 0));
+        v1 = blend(t, __ldg(pTL + 1), __ldg(pTR + 1), __ldg(pBL + 1), __ldg(pBR + 1));
+        v2 = blend(t, __ldg(pTL + 2), __ldg(pTR + 2), __ldg(pBL + 2), __ldg(pBR + 2));
+      } else {
+        int xN, yN;
+        nearest_tap(x, y, f.x, f.y, W, H, xN, yN);
+        const float* p = s + ((int64_t)yN * W + xN) * 3;
+        v0 = __ldg(p);
+        v1 = __ldg(p + 1);
+        v2 = __ldg(p + 2);
+      }
+      if (norm_out != nullptr) {
+        // channelnorm_kernel.cu:53-59: fp32 `result += val*val` (an FMA under nvcc's default
+        // contraction) in channel order, then sqrt.
+        const float* r = ref + i * 3;
+        float d0 = __fsub_rn(__ldg(r), v0), d1 = __fsub_rn(__ldg(r + 1), v1), d2 = __fsub_rn(__ldg(r + 2), v2);
+        float acc = fmaf(d0, d0, 0.0f);
+        acc = fmaf(d1, d1, acc);
+        acc = fmaf(d2, d2, acc);
+        norm_out[i] = sqrtf(acc);
+      }
+    }
+    stage[threadIdx.x * 3 + 0] = v0;
+    stage[threadIdx.x * 3 + 1] = v1;
+    stage[threadIdx.x * 3 + 2] = v2;
+    __syncthreads();
+    int64_t n_here = min((int64_t)kThreads, n_pix - base) * 3;  // floats owned by this block
+    float* out = dst + base * 3;
+    if (vec_store) {
+      int n4 = (int)(n_here / 4);
+      for (int k = threadIdx.x; k < n4; k += kThreads)
+        stg_stream_f4(reinterpret_cast<float4*>(out) + k, reinterpret_cast<const float4*>(stage)[k]);
+      for (int k = n4 * 4 + threadIdx.x; k < n_here; k += kThreads) out[k] = stage[k];
+    } else {
+      for (int k = threadIdx.x; k < n_here; k += kThreads) out[k] = stage[k];
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Channels-last, C % 4 == 0 (features).  One thread per (pixel, 4-channel group): four 16-byte
+// gathers and one 16-byte coalesced store; the C/4 lanes of a pixel share taps through the
+// broadcast of the flow load.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+warp_nhwc_vec4_kernel(const float* __restrict__ src, const float* __restrict__ flow, float* __restrict__ dst,
+                      int64_t n_pix, int H, int W, int C, int bilinear) {
+  const int G = C >> 2;
+  const int64_t HW = (int64_t)H * W;
+  const int64_t n = n_pix * G;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+    int64_t i = j / G;
+    int g = (int)(j - i * G);
+    int x = (int)(i % W);
+    int y = (int)((i / W) % H);
+    int64_t b = i / HW;
+    float2 f = __ldg(reinterpret_cast<const float2*>(flow) + i);
+    const float4* s = reinterpret_cast<const float4*>(src + b * HW * C) + g;
+    float4 o;
+    if (bilinear) {
+      Taps t = bilinear_taps(x, y, f.x, f.y, W, H);
+      float4 tl = __ldg(s + ((int64_t)t.yT * W + t.xL) * G);
+      float4 tr = __ldg(s + ((int64_t)t.yT * W + t.xR) * G);
+      float4 bl = __ldg(s + ((int64_t)t.yB * W + t.xL) * G);
+      float4 br = __ldg(s + ((int64_t)t.yB * W + t.xR) * G);
+      o.x = blend(t, tl.x, tr.x, bl.x, br.x);
+      o.y = blend(t, tl.y, tr.y, bl.y, br.y);
+      o.z = blend(t, tl.z, tr.z, bl.z, br.z);
+      o.w = blend(t, tl.w, tr.w, bl.w, br.w);
+    } else {
+      int xN, yN;
+      nearest_tap(x, y, f.x, f.y, W, H, xN, yN);
+      o = __ldg(s + ((int64_t)yN * W + xN) * G);
+    }
+    stg_stream_f4(reinterpret_cast<float4*>(dst) + j, o);
+  }
+}
+
+// Channels-last, any C: one thread per pixel, channel loop (also serves the fused norm for C != 3,
+// keeping the reference's channel-order fp32 accumulation).
+__global__ void __launch_bounds__(kThreads)
+warp_nhwc_generic_kernel(const float* __restrict__ src, const float* __restrict__ flow, float* __restrict__ dst,
+                         const float* __restrict__ ref, float* __restrict__ norm_out,
+                         int64_t n_pix, int H, int W, int C, int bilinear) {
+  const int64_t HW = (int64_t)H * W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pix; i += (int64_t)gridDim.x * blockDim.x) {
+    int x = (int)(i % W);
+    int y = (int)((i / W) % H);
+    int64_t b = i / HW;
+    float2 f = __ldg(reinterpret_cast<const float2*>(flow) + i);
+    const float* s = src + b * HW * C;
+    float* o = dst + i * C;
+    float acc = 0.0f;
+    if (bilinear) {
+      Taps t = bilinear_taps(x, y, f.x, f.y, W, H);
+      const float* pTL = s + ((int64_t)t.yT * W + t.xL) * C;
+      const float* pTR = s + ((int64_t)t.yT * W + t.xR) * C;
+      const float* pBL = s + ((int64_t)t.yB * W + t.xL) * C;
+      const float* pBR = s + ((int64_t)t.yB * W + t.xR) * C;
+      for (int c = 0; c < C; ++c) {
+        float v = blend(t, __ldg(pTL + c), __ldg(pTR + c), __ldg(pBL + c), __ldg(pBR + c));
+        o[c] = v;
+        if (norm_out != nullptr) {
+          float d = __fsub_rn(__ldg(ref + i * C + c), v);
+          acc = fmaf(d, d, acc);
+        }
+      }
+    } else {
+      int xN, yN;
+      nearest_tap(x, y, f.x, f.y, W, H, xN, yN);
+      const float* p = s + ((int64_t)yN * W + xN) * C;
+      for (int c = 0; c < C; ++c) {
+        float v = __ldg(p + c);
+        o[c] = v;
+        if (norm_out != nullptr) {
+          float d = __fsub_rn(__ldg(ref + i * C + c), v);
+          acc = fmaf(d, d, acc);
+        }
+      }
+    }
+    if (norm_out != nullptr) norm_out[i] = sqrtf(acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// u8 label warp (nearest).  Four consecutive pixels per thread: two 16-byte flow loads, four
+// byte gathers, one 32-bit store.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+warp_labels_kernel(const uint8_t* __restrict__ labels, const float* __restrict__ flow, uint8_t* __restrict__ dst,
+                   int64_t n_pix, int H, int W, int vec) {
+  const int64_t HW = (int64_t)H * W;
+  const int64_t n4 = vec ? n_pix / 4 : 0;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (int64_t)gridDim.x * blockDim.x) {
+    float4 fa = ldg_stream_f4(reinterpret_cast<const float4*>(flow) + q * 2);
+    float4 fb = ldg_stream_f4(reinterpret_cast<const float4*>(flow) + q * 2 + 1);
+    float fxs[4] = {fa.x, fa.z, fb.x, fb.z};
+    float fys[4] = {fa.y, fa.w, fb.y, fb.w};
+    uint32_t packed = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int64_t i = q * 4 + k;
+      int x = (int)(i % W);
+      int y = (int)((i / W) % H);
+      int64_t b = i / HW;
+      int xN, yN;
+      nearest_tap(x, y, fxs[k], fys[k], W, H, xN, yN);
+      packed |= (uint32_t)__ldg(labels + b * HW + (int64_t)yN * W + xN) << (8 * k);
+    }
+    reinterpret_cast<uint32_t*>(dst)[q] = packed;
+  }
+  // scalar tail (and the whole range when the buffers are not 16/4-byte aligned)
+  for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pix;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int x = (int)(i % W);
+    int y = (int)((i / W) % H);
+    int64_t b = i / HW;
+    float2 f = __ldg(reinterpret_cast<const float2*>(flow) + i);
+    int xN, yN;
+    nearest_tap(x, y, f.x, f.y, W, H, xN, yN);
+    dst[i] = __ldg(labels + b * HW + (int64_t)yN * W + xN);
+  }
+}
+
+// channelnorm_kernel.cu:19-60, NCHW: one thread per (b, y, x), coalesced plane reads.
+__global__ void __launch_bounds__(kThreads)
+channelnorm_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int C, int H, int W) {
+  const int64_t HW = (int64_t)H * W;
+  const int64_t n = (int64_t)B * HW;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t b = i / HW;
+    int64_t p = i - b * HW;
+    const float* s = in + b * C * HW + p;
+    float acc = 0.0f;
+    for (int c = 0; c < C; ++c) {
+      float v = __ldg(s + (int64_t)c * HW);
+      acc = fmaf(v, v, acc);
+    }
+    out[i] = sqrtf(acc);
+  }
+}
+
+inline int grid_for(int64_t work_items, int per_block) {
+  int64_t blocks = ceil_div64(work_items, per_block);
+  // enough CTAs for every SM to hold its full complement of 256-thread blocks (8/SM), a whole
+  // number of waves; grid-stride loops absorb the rest.
+  int64_t cap = (int64_t)kNumSMs * 8 * 4;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+}  // namespace
+}  // namespace vsr
+
+using namespace vsr;
+
+extern "C" int vsr_resample2d_forward(const float* input1, const float* flow, float* output, int B, int C, int H,
+                                      int W, int kernel_size, int bilinear, vsr_stream_t stream) {
+  if (!input1 || !flow || !output || B <= 0 || C <= 0 || H <= 0 || W <= 0) return VSR_ERR_INVALID_ARG;
+  if (kernel_size != 1) return VSR_ERR_UNSUPPORTED;  // resample2d.py:44: the only value ever used
+  int64_t n = (int64_t)B * H * W;
+  resample2d_nchw_kernel<<<grid_for(n, kThreads), kThreads, 0, as_stream(stream)>>>(input1, flow, output, B, C, H, W,
+                                                                                   bilinear ? 1 : 0);
+  return after_launch();
+}
+
+extern "C" int vsr_warp_nhwc_f32(const float* src, const float* flow, float* dst, const float* ref, float* norm_out,
+                                 int B, int H, int W, int C, int bilinear, vsr_stream_t stream) {
+  if (!src || !flow || !dst || B <= 0 || C <= 0 || H <= 0 || W <= 0) return VSR_ERR_INVALID_ARG;
+  if ((norm_out != nullptr) != (ref != nullptr)) return VSR_ERR_INVALID_ARG;
+  if (!aligned(flow, 8)) return VSR_ERR_INVALID_ARG;
+  int64_t n_pix = (int64_t)B * H * W;
+  cudaStream_t st = as_stream(stream);
+  if (C == 3) {
+    int vec = aligned(dst, 16) ? 1 : 0;
+    warp_nhwc3_kernel<<<grid_for(n_pix, kThreads), kThreads, 0, st>>>(src, flow, dst, ref, norm_out, n_pix, H, W,
+                                                                      bilinear ? 1 : 0, vec);
+  } else if ((C % 4) == 0 && norm_out == nullptr && aligned(src, 16) && aligned(dst, 16)) {
+    warp_nhwc_vec4_kernel<<<grid_for(n_pix * (C / 4), kThreads), kThreads, 0, st>>>(src, flow, dst, n_pix, H, W, C,
+                                                                                    bilinear ? 1 : 0);
+  } else {
+    warp_nhwc_generic_kernel<<<grid_for(n_pix, kThreads), kThreads, 0, st>>>(src, flow, dst, ref, norm_out, n_pix, H,
+                                                                             W, C, bilinear ? 1 : 0);
+  }
+  return after_launch();
+}
+
+extern "C" int vsr_warp_labels_u8(const uint8_t* labels, const float* flow, uint8_t* dst, int B, int H, int W,
+                                  vsr_stream_t stream) {
+  if (!labels || !flow || !dst || B <= 0 || H <= 0 || W <= 0) return VSR_ERR_INVALID_ARG;
+  if (!aligned(flow, 8)) return VSR_ERR_INVALID_ARG;
+  int64_t n_pix = (int64_t)B * H * W;
+  int vec = (aligned(flow, 16) && aligned(dst, 4)) ? 1 : 0;
+  warp_labels_kernel<<<grid_for(ceil_div64(n_pix, 4), kThreads), kThreads, 0, as_stream(stream)>>>(labels, flow, dst,
+                                                                                                  n_pix, H, W, vec);
+  return after_launch();
+}
+
+extern "C" int vsr_channelnorm_forward(const float* input, float* output, int B, int C, int H, int W, int norm_deg,
+                                       vsr_stream_t stream) {
+  (void)norm_deg;  // accepted and ignored, as channelnorm_kernel.cu:53-59 does
+  if (!input || !output || B <= 0 || C <= 0 || H <= 0 || W <= 0) return VSR_ERR_INVALID_ARG;
+  int64_t n = (int64_t)B * H * W;
+  channelnorm_nchw_kernel<<<grid_for(n, kThreads), kThreads, 0, as_stream(stream)>>>(input, output, B, C, H, W);
+  return after_launch();
+}

@@ -1,0 +1,166 @@
+"""Operator-level Python API over the C ABI (include/vsr_b200.h).
+
+Every function takes CUDA tensors, allocates the outputs (the reference's caller-allocates
+convention, resample2d.py:17-19) and enqueues the kernels on torch's current stream.  There is no
+CPU path: a non-CUDA tensor raises.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+_WORKSPACES: dict = {}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: video_super_resolution_b200 ops run on CUDA tensors only (no CPU fallback)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    # same contract as the reference (`assert input.is_contiguous()`, resample2d.py:10-11)
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: tensor must be contiguous")
+    return t
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    """Caller-side workspace cache (the library itself owns no memory)."""
+    key = (device.index, torch.cuda.current_stream().cuda_stream)
+    buf = _WORKSPACES.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+        _WORKSPACES[key] = buf
+    return buf
+
+
+def resample2d(input1: torch.Tensor, flow: torch.Tensor, kernel_size: int = 1, bilinear: bool = True) -> torch.Tensor:
+    """Reference layout: input1 (B,C,H,W), flow (B,2,H,W) -> (B,C,H,W).
+    ref: Resample2dFunction.forward (resample2d.py:8-23), resample2d_kernel.cu:15-72."""
+    _req(input1, torch.float32, "input1")
+    _req(flow, torch.float32, "input2")
+    _, C, _, _ = input1.shape
+    B, two, H, W = flow.shape
+    if two != 2 or input1.shape[0] != B or tuple(input1.shape[2:]) != (H, W):
+        raise ValueError("resample2d: input1 (B,C,H,W) and flow (B,2,H,W) must agree (the reference's only use)")
+    out = torch.empty((B, C, H, W), dtype=torch.float32, device=input1.device)
+    with torch.cuda.device(input1.device):
+        _lib.check(_lib.lib().vsr_resample2d_forward(input1.data_ptr(), flow.data_ptr(), out.data_ptr(), B, C, H, W,
+                                                     int(kernel_size), int(bool(bilinear)), _stream()), "resample2d")
+    return out
+
+
+def warp(src: torch.Tensor, flow: torch.Tensor, bilinear: bool = True, ref: torch.Tensor | None = None):
+    """Channels-last warp: src (B,H,W,C), flow (B,H,W,2) -> (B,H,W,C).  With `ref` (B,H,W,C) also
+    returns the per-pixel L2 norm of (ref - warped), (B,H,W) (models.py:86-88 fused)."""
+    _req(src, torch.float32, "src")
+    _req(flow, torch.float32, "flow")
+    B, H, W, C = src.shape
+    if tuple(flow.shape) != (B, H, W, 2):
+        raise ValueError("warp: flow must be (B,H,W,2)")
+    dst = torch.empty_like(src)
+    norm = None
+    if ref is not None:
+        _req(ref, torch.float32, "ref")
+        if ref.shape != src.shape:
+            raise ValueError("warp: ref must have the shape of src")
+        norm = torch.empty((B, H, W), dtype=torch.float32, device=src.device)
+    with torch.cuda.device(src.device):
+        _lib.check(_lib.lib().vsr_warp_nhwc_f32(src.data_ptr(), flow.data_ptr(), dst.data_ptr(),
+                                                ref.data_ptr() if ref is not None else None,
+                                                norm.data_ptr() if norm is not None else None,
+                                                B, H, W, C, int(bool(bilinear)), _stream()), "warp")
+    return dst if ref is None else (dst, norm)
+
+
+def warp_labels(labels: torch.Tensor, flow: torch.Tensor) -> torch.Tensor:
+    """Nearest label warp: labels (B,H,W) u8, flow (B,H,W,2) -> (B,H,W) u8, bit-exact."""
+    _req(labels, torch.uint8, "labels")
+    _req(flow, torch.float32, "flow")
+    B, H, W = labels.shape
+    if tuple(flow.shape) != (B, H, W, 2):
+        raise ValueError("warp_labels: flow must be (B,H,W,2)")
+    dst = torch.empty_like(labels)
+    with torch.cuda.device(labels.device):
+        _lib.check(_lib.lib().vsr_warp_labels_u8(labels.data_ptr(), flow.data_ptr(), dst.data_ptr(), B, H, W,
+                                                 _stream()), "warp_labels")
+    return dst
+
+
+def channelnorm(x: torch.Tensor, norm_deg: int = 2) -> torch.Tensor:
+    """x (B,C,H,W) -> (B,1,H,W).  ref: ChannelNormFunction.forward (channelnorm.py:8-18)."""
+    _req(x, torch.float32, "input1")
+    B, C, H, W = x.shape
+    out = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().vsr_channelnorm_forward(x.data_ptr(), out.data_ptr(), B, C, H, W, int(norm_deg),
+                                                      _stream()), "channelnorm")
+    return out
+
+
+def project_flow(flow: torch.Tensor, inv_depth: torch.Tensor | None = None):
+    """Forward flow projection.  flow (B,h,w,2); inv_depth (B,h,w) or None.
+    Returns proj (B,h,w,2) f32, wsum (B,h,w) f32, count (B,h,w) i32, hole (B,h,w) u8."""
+    _req(flow, torch.float32, "flow")
+    B, h, w, two = flow.shape
+    if two != 2:
+        raise ValueError("project_flow: flow must be (B,h,w,2)")
+    if inv_depth is not None:
+        _req(inv_depth, torch.float32, "inv_depth")
+        if tuple(inv_depth.shape) != (B, h, w):
+            raise ValueError("project_flow: inv_depth must be (B,h,w)")
+    dev = flow.device
+    proj = torch.empty((B, h, w, 2), dtype=torch.float32, device=dev)
+    wsum = torch.empty((B, h, w), dtype=torch.float32, device=dev)
+    count = torch.empty((B, h, w), dtype=torch.int32, device=dev)
+    hole = torch.empty((B, h, w), dtype=torch.uint8, device=dev)
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        nbytes = int(L.vsr_flow_projection_workspace_bytes(B, h, w))
+        ws = _workspace(nbytes, dev)
+        _lib.check(L.vsr_flow_projection_forward(flow.data_ptr(), inv_depth.data_ptr() if inv_depth is not None else None,
+                                                 proj.data_ptr(), wsum.data_ptr(), count.data_ptr(), hole.data_ptr(),
+                                                 ws.data_ptr(), ws.numel(), B, h, w, _stream()), "project_flow")
+    return proj, wsum, count, hole
+
+
+def project_depth_flow(flow: torch.Tensor, inv_depth: torch.Tensor):
+    """Inverse-depth-weighted projection (nearer surfaces dominate contested targets)."""
+    if inv_depth is None:
+        raise ValueError("project_depth_flow: inv_depth is required")
+    return project_flow(flow, inv_depth)
+
+
+def vos_threshold(logits_a: torch.Tensor, logits_b: torch.Tensor) -> torch.Tensor:
+    """sigmoid(a)+sigmoid(b) > 0.7 -> u8 {0,1}.  ref: VOSProjectionModule.py:22-25."""
+    _req(logits_a, torch.float32, "logits_a")
+    _req(logits_b, torch.float32, "logits_b")
+    if logits_a.shape != logits_b.shape or logits_a.dim() != 2:
+        raise ValueError("vos_threshold: two (h,w) tensors expected")
+    h, w = logits_a.shape
+    mask = torch.empty((h, w), dtype=torch.uint8, device=logits_a.device)
+    with torch.cuda.device(logits_a.device):
+        _lib.check(_lib.lib().vsr_vos_threshold(logits_a.data_ptr(), logits_b.data_ptr(), mask.data_ptr(), h, w,
+                                                _stream()), "vos_threshold")
+    return mask
+
+
+def mask_fill(image: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """image (C,h,w) f32, mask (h,w) u8 -> image with masked pixels zeroed.
+    ref: video_super_resolution.py:58-60 (MaskedArray(..., fill_value=0).filled())."""
+    _req(image, torch.float32, "image")
+    _req(mask, torch.uint8, "mask")
+    C, h, w = image.shape
+    if tuple(mask.shape) != (h, w):
+        raise ValueError("mask_fill: mask must be (h,w)")
+    out = torch.empty_like(image)
+    with torch.cuda.device(image.device):
+        _lib.check(_lib.lib().vsr_mask_fill(image.data_ptr(), mask.data_ptr(), out.data_ptr(), C, h, w, _stream()),
+                   "mask_fill")
+    return out
