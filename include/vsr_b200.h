@@ -104,6 +104,24 @@ int vsr_mask_fill(const float* image, const uint8_t* mask, float* masked,
                   int C, int h, int w, vsr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * a7: assembly of the (M,3,h,w) map stack, M = 3T-1.  ref: network/video_super_resolution.py:33-40
+ * (transpose1323 + interpolate + torch.cat) and :43-44,:57-62 (nearest downsize of the first-pass
+ * output, MaskedArray fill with the VOS mask, second cat).  Stack order along dim 0
+ * (video_super_resolution.py:40 generalised to T frames): T frames (warped neighbours, the centre
+ * frame at centre_idx), T-1 flow maps (projected fx, projected fy, warp-residual norm), T-1 depth
+ * maps tiled x3 (utils/tools.py:76-77), 1 estimate.
+ * warped (T-1,h,w,3) NHWC, centre (h,w,3), proj (T-1,h,w,2), resid (T-1,h,w), depth (T-1,h,w),
+ * estimate (3,h,w) NCHW or NULL (= centre frame, video_super_resolution.py:37-38); stack (M,3,h,w).
+ * vsr_estimate_slot: slot (3,h,w) = mask ? 0 : hr[:, y*scale, x*scale] for hr (3,h*scale,w*scale);
+ * mask (h,w) u8 or NULL.
+ * ---------------------------------------------------------------------------------------- */
+int vsr_assemble_stack(const float* warped, const float* centre, const float* proj, const float* resid,
+                       const float* depth, const float* estimate, float* stack,
+                       int T, int centre_idx, int h, int w, vsr_stream_t stream);
+int vsr_estimate_slot(const float* hr, const uint8_t* mask, float* slot, int h, int w, int scale,
+                      vsr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * a6 / a7: the fusion / upsampling convolutions (SRFBN + per-pixel fc over the map axis).
  * ref: SRProjectionModule.forward (SRProjectionModule.py:133-147), FeedbackBlock (:7-93),
  * blocks.py:7-74, with the INTENDED dense-concat dataflow.
@@ -177,6 +195,16 @@ int vsr_srfbn_bind(vsr_srfbn_plan* plan, const void* dev_weights, void* dev_work
                    size_t workspace_bytes);
 /* x: (M,3,h,w) f32 NCHW, 0..255 (video_super_resolution.py:40,62); y: (1,3,4h,4w) f32. */
 int vsr_srfbn_forward(vsr_srfbn_plan* plan, const float* x, float* y, vsr_stream_t stream);
+/* Per-launch accounting for bench.py: with profiling enabled, vsr_srfbn_forward brackets every
+ * kernel launch with CUDA events on the caller's stream; vsr_srfbn_profile_read waits for the last
+ * forward and returns, per kernel class, the summed device time (ms), the number of launches, and
+ * the layers' specified 2*MAC FLOPs and compulsory bytes (inputs + outputs of each launch, once).
+ * Arrays have VSR_SRFBN_KERNEL_CLASSES entries, in the order of vsr_srfbn_kernel_class_name(). */
+#define VSR_SRFBN_KERNEL_CLASSES 8
+const char* vsr_srfbn_kernel_class_name(int k);
+int vsr_srfbn_profile_enable(vsr_srfbn_plan* plan, int enable);
+int vsr_srfbn_profile_read(vsr_srfbn_plan* plan, double* ms, int32_t* launches, double* flops, double* bytes);
+
 /* Test hook: per-map network output before the fc fuse, (M,3,4h,4w) f32 (SRProjectionModule.py:143);
  * valid after vsr_srfbn_forward on the same stream. */
 int vsr_srfbn_debug_premix(const vsr_srfbn_plan* plan, float* out_maps, vsr_stream_t stream);
@@ -185,14 +213,16 @@ int vsr_srfbn_debug_premix(const vsr_srfbn_plan* plan, float* out_maps, vsr_stre
  * uses, on BF16 channels-last operands, so tests can compare layer by layer with torch.nn fp32
  * (SURVEY.md Appendix C).  All pointers device.  `act`: 1 = PReLU(slope), 0 = none.
  *   pointwise: y[r, 0:32] = act(sum_k x[r, k] * w[n, k] + b[n]),  x (rows, K) bf16, K%32==0, K<=224
- *   deconv   : ConvTranspose2d(32,32,8,4,2): x (B,h,w,32) bf16 -> y (B,4h,4w,32) bf16
- *   downconv : Conv2d(32,32,8,4,2):          x (B,4h,4w,32) bf16 -> y (B,h,w,32) bf16
+ *   deconv   : ConvTranspose2d(32,32,8,4,2): x (B,h,w,32) bf16 -> y (B,4h,4w,32) bf16 (block_layout=0)
+ *              or the HR block layout (B,h+1,w+1,16,32) (block_layout=1)
+ *   downconv : Conv2d(32,32,8,4,2):          x in the HR block layout (B,h+1,w+1,16,32) bf16
+ *              -> y (B,h,w,32) bf16
  * w/b in the reference (torch) layouts, fp32, HOST memory. */
 int vsr_test_pointwise(const void* x_bf16, int64_t rows, int K, const float* w_host,
                        const float* b_host, float slope, int act, void* y_bf16,
                        void* workspace, size_t workspace_bytes, vsr_stream_t stream);
 int vsr_test_deconv(const void* x_bf16, int B, int h, int w, const float* w_host,
-                    const float* b_host, float slope, void* y_bf16,
+                    const float* b_host, float slope, int block_layout, void* y_bf16,
                     void* workspace, size_t workspace_bytes, vsr_stream_t stream);
 int vsr_test_downconv(const void* x_bf16, int B, int h, int w, const float* w_host,
                       const float* b_host, float slope, void* y_bf16,

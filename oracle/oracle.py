@@ -185,3 +185,53 @@ def mask_fill(image, mask):
     out = np.zeros_like(image)
     lib().or_mask_fill(_p(image, _f32p), _p(mask, _u8p), _p(out, _f32p), C, mask.size)
     return out
+
+
+def assemble_stack(warped, centre, proj, resid, depth, estimate, centre_idx):
+    """numpy restatement of the stack assembly (video_super_resolution.py:33-40 generalised to T
+    frames): warped (T-1,h,w,3), centre (h,w,3), proj (T-1,h,w,2), resid/depth (T-1,h,w),
+    estimate (3,h,w)|None -> (3T-1,3,h,w)."""
+    Tm1, h, w, _ = warped.shape
+    T = Tm1 + 1
+    out = np.zeros((3 * T - 1, 3, h, w), np.float32)
+    n = 0
+    for t in range(T):
+        if t == centre_idx:
+            out[t] = centre.transpose(2, 0, 1)                       # transpose1201
+        else:
+            out[t] = warped[n].transpose(2, 0, 1)
+            n += 1
+    for n in range(Tm1):
+        out[T + n, 0] = proj[n, :, :, 0]
+        out[T + n, 1] = proj[n, :, :, 1]
+        out[T + n, 2] = resid[n]
+        out[2 * T - 1 + n] = np.stack((depth[n],) * 3)               # maskprocess
+    out[3 * T - 2] = centre.transpose(2, 0, 1) if estimate is None else estimate
+    return out
+
+
+def estimate_slot(hr, mask, scale=4):
+    """hr (3,H,W) -> (3,h,w): nearest downsize (F.interpolate default: src = dst*scale,
+    video_super_resolution.py:44) then MaskedArray(..., fill_value=0).filled() (:58-60)."""
+    lo = np.ascontiguousarray(hr[:, ::scale, ::scale], dtype=np.float32)
+    if mask is not None:
+        lo = np.ma.MaskedArray(lo, np.stack((mask,) * 3).astype(bool), fill_value=0).filled()
+    return lo.astype(np.float32)
+
+
+def warp_fuse_front(frames, flows, inv_depth, logits_a, logits_b, estimate=None, threads=1):
+    """CPU restatement of WarpFusePipeline.project_and_warp (a1-a5 + a7): returns the map stack and
+    the intermediates.  frames (T,h,w,3), flows (T-1,h,w,2), inv_depth (T-1,h,w), logits (h,w) x2."""
+    T = frames.shape[0]
+    c = T // 2
+    proj_f, _, cnt_f, hole_f = flow_projection(flows, None, threads=threads)
+    proj_d, wsum, cnt_d, hole_d = flow_projection(flows, inv_depth, threads=threads)
+    neigh = np.ascontiguousarray(frames[[t for t in range(T) if t != c]])
+    warped = warp_nhwc(neigh, proj_d, True, threads=threads)
+    resid = channelnorm_nhwc(frames[c][None] - warped)
+    mask = vos_threshold(logits_a, logits_b)
+    mask_w = warp_labels(mask[None], proj_d[min(c, T - 2)][None])[0]
+    stack = assemble_stack(warped, frames[c], proj_f, resid, wsum, estimate, c)
+    return stack, {"proj_flow": proj_f, "count_flow": cnt_f, "hole_flow": hole_f, "proj_depth": proj_d, "wsum": wsum,
+                   "count_depth": cnt_d, "hole_depth": hole_d, "warped": warped, "resid": resid, "mask": mask,
+                   "mask_warped": mask_w}

@@ -1,0 +1,71 @@
+"""Python front-ends of the single-layer test hooks of the C ABI (vsr_test_*) and the HR block
+layout helpers.  Test support only."""
+import ctypes
+
+import torch
+
+from video_super_resolution_b200 import _lib
+
+
+def _fp(t):
+    return ctypes.cast(t.data_ptr(), ctypes.c_void_p)
+
+
+def to_block(x):
+    """(B,4h,4w,C) plain NHWC -> HR block layout (B,h+1,w+1,16,C): origin shifted by (-2,-2), zero ring."""
+    B, H, W, C = x.shape
+    xp = torch.nn.functional.pad(x, (0, 0, 2, 2, 2, 2))
+    xp = xp.view(B, H // 4 + 1, 4, W // 4 + 1, 4, C).permute(0, 1, 3, 2, 4, 5)
+    return xp.reshape(B, H // 4 + 1, W // 4 + 1, 16, C).contiguous()
+
+
+def from_block(xb):
+    B, hb, wb, _, C = xb.shape
+    x = xb.view(B, hb, wb, 4, 4, C).permute(0, 1, 3, 2, 4, 5).reshape(B, hb * 4, wb * 4, C)
+    return x[:, 2:-2, 2:-2].contiguous()
+
+
+def _ws(dev):
+    n = int(_lib.lib().vsr_test_workspace_bytes(1, 1, 1))
+    return torch.empty(n, dtype=torch.uint8, device=dev)
+
+
+def pointwise(x_bf16, w, b, slope, act=True):
+    """x (rows,K) bf16 cuda; w (32,K) f32 cpu; b (32) f32 cpu -> (rows,32) bf16."""
+    rows, K = x_bf16.shape
+    y = torch.empty((rows, 32), dtype=torch.bfloat16, device=x_bf16.device)
+    ws = _ws(x_bf16.device)
+    w = w.contiguous().float()
+    b = b.contiguous().float()
+    _lib.check(_lib.lib().vsr_test_pointwise(x_bf16.data_ptr(), rows, K, _fp(w), _fp(b), float(slope), int(act),
+                                             y.data_ptr(), ws.data_ptr(), ws.numel(),
+                                             torch.cuda.current_stream().cuda_stream), "test_pointwise")
+    return y
+
+
+def deconv(x_bf16, w, b, slope, block_layout=False):
+    """x (B,h,w,32) bf16; w (32,32,8,8) ConvTranspose layout -> (B,4h,4w,32) or block layout."""
+    B, h, wd, _ = x_bf16.shape
+    shape = (B, h + 1, wd + 1, 16, 32) if block_layout else (B, 4 * h, 4 * wd, 32)
+    y = torch.full(shape, float("nan"), dtype=torch.bfloat16, device=x_bf16.device)
+    ws = _ws(x_bf16.device)
+    w = w.contiguous().float()
+    b = b.contiguous().float()
+    _lib.check(_lib.lib().vsr_test_deconv(x_bf16.data_ptr(), B, h, wd, _fp(w), _fp(b), float(slope),
+                                          int(block_layout), y.data_ptr(), ws.data_ptr(), ws.numel(),
+                                          torch.cuda.current_stream().cuda_stream), "test_deconv")
+    return y
+
+
+def downconv(xb_bf16, w, b, slope):
+    """xb (B,h+1,w+1,16,32) bf16 block layout; w (32,32,8,8) Conv2d layout -> (B,h,w,32) bf16."""
+    B, hb, wb = xb_bf16.shape[:3]
+    h, wd = hb - 1, wb - 1
+    y = torch.full((B, h, wd, 32), float("nan"), dtype=torch.bfloat16, device=xb_bf16.device)
+    ws = _ws(xb_bf16.device)
+    w = w.contiguous().float()
+    b = b.contiguous().float()
+    _lib.check(_lib.lib().vsr_test_downconv(xb_bf16.data_ptr(), B, h, wd, _fp(w), _fp(b), float(slope),
+                                            y.data_ptr(), ws.data_ptr(), ws.numel(),
+                                            torch.cuda.current_stream().cuda_stream), "test_downconv")
+    return y

@@ -1,0 +1,112 @@
+"""GPU parity of the fusion / upsampling convolutions (tcgen05 implicit GEMM, BF16 in / FP32
+accumulate) against torch.nn.functional fp32 -- the reference's own arithmetic provider for these
+layers (blocks.py:16,34; SRProjectionModule.py:126-131) -- layer by layer and end to end against
+oracle/srfbn_oracle.py (intended dense-concat dataflow).
+
+Tolerances: one layer fed BF16-rounded inputs/weights differs from fp32 math only by accumulation
+order and the BF16 rounding of the output (rel 2^-8); whole stack: PSNR delta <= 0.05 dB
+(BASELINE.json north_star), measured against a target placed ~35 dB from the fp32 output.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import srfbn_oracle as so
+from tests import srfbn_hooks as hk
+from video_super_resolution_b200.my_packages.SRProjection.SRProjectionModule import SRProjectionModule
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _bf(t):
+    return t.to(torch.bfloat16)
+
+
+def _close(got, want, what):
+    got = got.float().cpu()
+    want = want.float().cpu()
+    assert torch.isfinite(got).all(), f"{what}: non-finite output"
+    err = (got - want).abs()
+    tol = 0.02 * want.abs() + 0.02 * want.abs().mean() + 1e-3
+    bad = (err > tol).sum().item()
+    assert bad == 0, f"{what}: {bad}/{err.numel()} outside tolerance, max err {err.max():.4g} (ref max {want.abs().max():.4g})"
+
+
+@pytest.mark.parametrize("rows,K", [(128, 32), (1000, 64), (129, 96), (4096 + 77, 192), (300, 224)])
+def test_pointwise_layer(rows, K):
+    g = torch.Generator().manual_seed(rows + K)
+    x = _bf(torch.randn((rows, K), generator=g))
+    w = _bf(torch.randn((32, K), generator=g) / math.sqrt(K)).float()
+    b = torch.randn(32, generator=g) * 0.1
+    got = hk.pointwise(x.to(DEV), w, b, 0.2)
+    want = F.prelu(x.float() @ w.t() + b, torch.tensor([0.2]))
+    _close(got, want, f"pointwise rows={rows} K={K}")
+
+
+@pytest.mark.parametrize("B,h,w", [(1, 8, 16), (2, 5, 7), (1, 19, 33)])
+@pytest.mark.parametrize("block", [False, True])
+def test_deconv_layer(B, h, w, block):
+    g = torch.Generator().manual_seed(B * 100 + h * 10 + w)
+    x = _bf(torch.randn((B, h, w, 32), generator=g))
+    wt = _bf(torch.randn((32, 32, 8, 8), generator=g) / 16).float()
+    b = torch.randn(32, generator=g) * 0.1
+    got = hk.deconv(x.to(DEV), wt, b, 0.25, block_layout=block)
+    want = F.prelu(F.conv_transpose2d(x.float().permute(0, 3, 1, 2), wt, b, stride=4, padding=2),
+                   torch.tensor([0.25])).permute(0, 2, 3, 1)
+    if block:
+        raw = got.float().cpu()
+        ring = hk.to_block(torch.ones((B, 4 * h, 4 * w, 1)))       # 1 inside the image, 0 on the ring
+        assert torch.isfinite(raw).all()
+        assert (raw * (1 - ring)).abs().max() == 0, "padding ring of the block layout must be zero"
+        got = hk.from_block(got.cpu())
+    _close(got, want, f"deconv B={B} {h}x{w} block={block}")
+
+
+@pytest.mark.parametrize("B,h,w", [(1, 8, 16), (2, 5, 7), (1, 19, 33)])
+def test_downconv_layer(B, h, w):
+    g = torch.Generator().manual_seed(B * 100 + h * 10 + w + 1)
+    x = _bf(torch.randn((B, 4 * h, 4 * w, 32), generator=g))
+    wt = _bf(torch.randn((32, 32, 8, 8), generator=g) / 45).float()
+    b = torch.randn(32, generator=g) * 0.1
+    got = hk.downconv(hk.to_block(x).to(DEV), wt, b, 0.15)
+    want = F.prelu(F.conv2d(x.float().permute(0, 3, 1, 2), wt, b, stride=4, padding=2),
+                   torch.tensor([0.15])).permute(0, 2, 3, 1)
+    _close(got, want, f"downconv B={B} {h}x{w}")
+
+
+def _psnr(a, b):
+    mse = ((a - b) ** 2).mean().item()
+    return 10 * math.log10(255.0 ** 2 / max(mse, 1e-20))
+
+
+@pytest.mark.parametrize("M,h,w,steps", [(8, 16, 16, 3), (3, 9, 21, 2), (20, 24, 40, 3)])
+def test_full_stack_against_oracle(M, h, w, steps):
+    sd = so.init_state_dict(num_maps=M, seed=M + h, gain=2.3)
+    # make every slope distinct so a mixed-up layer shows
+    gs = torch.Generator().manual_seed(99)
+    for k in sd:
+        if k.endswith(".1.weight"):
+            sd[k] = torch.rand(1, generator=gs) * 0.4 + 0.05
+    mod = SRProjectionModule(num_steps=steps, num_maps=M)
+    mod.load_state_dict(sd)
+    x = torch.rand((M, 3, h, w), generator=torch.Generator().manual_seed(5)) * 255
+    with torch.no_grad():
+        want_maps = so.forward_maps(x, sd, num_steps=steps)
+        want = so.fc_fuse(want_maps, sd)
+    got_maps = mod.premix(x.to(DEV)).cpu()
+    got = mod(x.to(DEV)).cpu()
+    assert torch.isfinite(got_maps).all() and torch.isfinite(got).all()
+    # direct agreement of the per-map SR images (0..255 scale)
+    assert _psnr(got_maps, want_maps) > 50.0, f"per-map PSNR {_psnr(got_maps, want_maps):.2f} dB"
+    # north-star criterion: PSNR delta <= 0.05 dB against a common target ~35 dB away
+    noise = torch.randn(want_maps.shape, generator=torch.Generator().manual_seed(6)) * 4.5
+    target = want_maps + noise
+    delta = abs(_psnr(got_maps, target) - _psnr(want_maps, target))
+    assert delta <= 0.05, f"PSNR delta {delta:.4f} dB"
+    # fused output: the fc mixes M maps with random weights; compare relative to its scale
+    scale = want.abs().mean().item() + 1.0
+    assert (got - want).abs().max().item() <= 0.02 * scale + 0.05 * (got - want).abs().mean().item() + 0.5, \
+        f"fused max err {(got - want).abs().max():.4f} at scale {scale:.2f}"

@@ -59,6 +59,23 @@ SIGNATURES = {
     "vsr_flow_projection_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_void_p]),
     "vsr_vos_threshold": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "vsr_mask_fill": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "vsr_assemble_stack": (c_int, [c_void_p] * 7 + [c_int, c_int, c_int, c_int, c_void_p]),
+    "vsr_estimate_slot": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "vsr_srfbn_plan_create": (c_int, [ctypes.POINTER(SrfbnConfig), ctypes.POINTER(c_void_p)]),
+    "vsr_srfbn_plan_destroy": (None, [c_void_p]),
+    "vsr_srfbn_weight_bytes": (c_size_t, [c_void_p]),
+    "vsr_srfbn_workspace_bytes": (c_size_t, [c_void_p]),
+    "vsr_srfbn_pack_weights": (c_int, [c_void_p, ctypes.POINTER(SrfbnWeights), c_void_p]),
+    "vsr_srfbn_bind": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t]),
+    "vsr_srfbn_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vsr_srfbn_kernel_class_name": (ctypes.c_char_p, [c_int]),
+    "vsr_srfbn_profile_enable": (c_int, [c_void_p, c_int]),
+    "vsr_srfbn_profile_read": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vsr_srfbn_debug_premix": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "vsr_test_pointwise": (c_int, [c_void_p, c_i64, c_int, c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vsr_test_deconv": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vsr_test_downconv": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vsr_test_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
 }
 
 _lib = None

@@ -1,0 +1,460 @@
+// igemm.cuh -- one persistent, warp-specialised implicit-GEMM kernel (tcgen05 + TMEM + TMA) that
+// serves every dense layer of the fusion stack:
+//
+//     D[128 pixels, BN] = sum over K-chunks  A_chunk[128, CK] * W_chunk[BN, CK]^T      (BF16 -> FP32)
+//
+//   * an A chunk is a TMA box [CK channels, tile_w, tile_h, 1] of a channels-last activation
+//     tensor at (c0, x0+dx, y0+dy, b): 1x1 convs use one chunk per 32-channel slice of each
+//     concatenated source (torch.cat disappears), the 8x8-s4 transposed conv uses the 2x2 LR
+//     taps, the 8x8-s4 conv the 2x2 blocks of the "HR block" layout, the 3x3 conv its 9 taps;
+//     TMA's out-of-bounds zero fill IS the zero padding of the convolutions;
+//   * the weights of the layer (<=128 KB) are loaded once per CTA and stay resident in smem;
+//   * warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2-5 = epilogue
+//     (tcgen05.ld -> bias + PReLU -> BF16 -> global), accumulators double-buffered in TMEM so the
+//     epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Layout conventions are documented in DESIGN.md ("HR block layout").
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace vsr {
+
+constexpr int kTileM = 128;          // UMMA M
+constexpr int kMaxChunks = 72;       // K chunks per tile (downconv: 32 with CK=64, 64 with CK=32)
+constexpr int kMaxSources = 6;       // concatenated A sources (downtran of group 5)
+constexpr int kMaxStages = 8;
+constexpr int kIgemmThreads = 192;   // 6 warps
+
+enum EpiMode : int {
+  EPI_ROWS = 0,        // BN=32: 64-byte BF16 row per pixel at out + row*pitch + off
+  EPI_DECONV = 1,      // BN=256 (one half of the 16 sub-positions): HR block layout or plain NHWC HR
+  EPI_CONV_OUT = 2,    // BN=16 (3 real): fp32 planar output + bilinear skip + mean shifts
+};
+
+struct Chunk {
+  int8_t map;   // index into a_maps
+  int8_t dx;    // spatial offset of the box origin, in pixels of the source
+  int8_t dy;
+  int8_t pad;
+  int32_t c0;   // channel (innermost) offset
+};
+
+struct alignas(64) IgemmParams {
+  CUtensorMap a_maps[kMaxSources];
+  CUtensorMap b_map;
+  Chunk chunks[kMaxChunks];
+  int32_t num_chunks;
+  int32_t num_stages;
+  // tile grid: total tiles = n_tiles * tiles_x * tiles_y * batch, n fastest
+  int32_t n_tiles, tiles_x, tiles_y, batch;
+  int32_t tile_w, tile_h;      // tile_w * tile_h == 128
+  // epilogue
+  const float* bias;           // [bias_n] fp32 biases, then extras: [bias_n] = PReLU slope,
+                               // EPI_CONV_OUT: [bias_n+1..+3] = sub_mean bias, [bias_n+4..+6] = add_mean bias
+  int32_t bias_n;
+  int32_t act;                 // 1 = PReLU, 0 = identity
+  void* out;
+  int64_t out_pitch;           // bytes between consecutive output rows/pixels (EPI_ROWS)
+  int64_t out_off;             // byte offset inside a row (channel slice of a concat buffer)
+  int64_t flat_rows;           // >0: flat mode, rows are linear (tile_h == 1); else spatial
+  int32_t out_h, out_w;        // spatial extent of valid output rows (spatial mode)
+  int32_t lr_h, lr_w;          // LR size (block-layout masks, deconv geometry)
+  int32_t hrb_mask;            // EPI_ROWS flat over the HR block layout: zero the padding ring
+  int32_t deconv_nhwc;         // EPI_DECONV: 1 = write plain NHWC HR instead of the block layout
+  // EPI_CONV_OUT extras
+  const float* skip_src;       // network input x (M,3,h,w) fp32
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t addr = smem_u32(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(addr),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int kCols>
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+// tcgen05.commit: arrives on the mbarrier when all previously issued MMAs of this thread retire
+// (implies tcgen05.fence::before_thread_sync).
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, swizzled shared-memory matrix descriptor (PTX "matrix descriptor", sm_100 version 1):
+// bits [0,14) start>>4, [16,30) LBO>>4 (unused for swizzled K-major: 1), [32,46) SBO>>4 = bytes
+// between 8-row groups, [46,48) version=1, [61,64) layout (2 = 128B swizzle, 4 = 64B swizzle).
+template <int kSwizzleBytes>
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  constexpr uint64_t layout = (kSwizzleBytes == 128) ? 2ull : 4ull;
+  constexpr uint64_t sbo = (8ull * kSwizzleBytes) >> 4;
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+// kind::f16 instruction descriptor: D=F32 (bits 4-5 = 1), A=B=BF16 (bits 7-9, 10-12 = 1), both
+// K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float prelu(float v, float slope, int act) { return (act && v < 0.0f) ? v * slope : v; }
+
+struct TileCoord {
+  int n_tile, x0, y0, b;
+};
+__device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile) {
+  TileCoord t;
+  t.n_tile = tile % p.n_tiles;
+  int r = tile / p.n_tiles;
+  t.x0 = (r % p.tiles_x) * p.tile_w;
+  r /= p.tiles_x;
+  t.y0 = (r % p.tiles_y) * p.tile_h;
+  t.b = r / p.tiles_y;
+  return t;
+}
+
+// smem carve-up (dynamic, base aligned to 1024 by the kernel):
+//   [0, num_chunks*BN*CK*2)            resident weights, one swizzled [BN, CK] block per K chunk
+//   [.., + stages*128*CK*2)            A ring
+//   then barriers / tmem pointer / bias
+template <int CK, int BN>
+__host__ __device__ constexpr int b_chunk_bytes() { return BN * CK * 2; }
+template <int CK>
+__host__ __device__ constexpr int a_stage_bytes() { return kTileM * CK * 2; }
+
+template <int CK, int BN>
+inline size_t igemm_smem_bytes(int num_chunks, int num_stages) {
+  size_t b = (size_t)num_chunks * b_chunk_bytes<CK, BN>();
+  b = (b + 1023) / 1024 * 1024;
+  return 1024 /*align slack*/ + b + (size_t)num_stages * a_stage_bytes<CK>() + 1024 /*barriers + bias*/ + 2048;
+}
+
+template <int MODE, int CK, int BN>
+__global__ void __launch_bounds__(kIgemmThreads, 1)
+igemm_kernel(const __grid_constant__ IgemmParams p) {
+  static_assert(CK == 32 || CK == 64, "K chunk is 32 (64B swizzle) or 64 (128B swizzle) BF16");
+  static_assert(BN == 16 || BN == 32 || BN == 128 || BN == 256, "supported N tiles");
+  constexpr int kSwz = CK * 2;
+  constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator stages
+  constexpr int kABytes = a_stage_bytes<CK>();
+  constexpr int kBBytes = b_chunk_bytes<CK, BN>();
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int b_region = ((p.num_chunks * kBBytes) + 1023) / 1024 * 1024;
+  uint8_t* smem_b = smem;
+  uint8_t* smem_a = smem + b_region;
+  uint8_t* tail = smem_a + p.num_stages * kABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);          // [kMaxStages]
+  uint64_t* empty_bar = full_bar + kMaxStages;                     // [kMaxStages]
+  uint64_t* tmem_full = empty_bar + kMaxStages;                    // [2]
+  uint64_t* tmem_empty = tmem_full + 2;                            // [2]
+  uint64_t* b_full = tmem_empty + 2;                               // [1]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_full + 1);
+  float* s_bias = reinterpret_cast<float*>(tail + 512);            // up to 384 floats
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.n_tiles * p.tiles_x * p.tiles_y * p.batch;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.num_stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 128);
+    }
+    mbar_init(b_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_ptr);
+  constexpr int kBiasExtra = (MODE == EPI_CONV_OUT) ? 7 : 1;
+  for (int i = threadIdx.x; i < p.bias_n + kBiasExtra; i += kIgemmThreads) s_bias[i] = p.bias[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      // resident weights: every K chunk of this CTA's N tile, once
+      const int n_tile0 = blockIdx.x % p.n_tiles;
+      mbar_expect_tx(b_full, (uint32_t)(p.num_chunks * kBBytes));
+      for (int kc = 0; kc < p.num_chunks; ++kc)
+        tma_load_2d(smem_b + kc * kBBytes, &p.b_map, b_full, kc * CK, n_tile0 * BN);
+      int s = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        for (int kc = 0; kc < p.num_chunks; ++kc) {
+          mbar_wait(&empty_bar[s], phase ^ 1);
+          mbar_expect_tx(&full_bar[s], kABytes);
+          const Chunk c = p.chunks[kc];
+          tma_load_4d(smem_a + s * kABytes, &p.a_maps[c.map], &full_bar[s], c.c0, t.x0 + c.dx, t.y0 + c.dy, t.b);
+          if (++s == p.num_stages) { s = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc(BN);
+    mbar_wait(b_full, 0);
+    tc_fence_after();
+    int s = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty[as], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+      for (int kc = 0; kc < p.num_chunks; ++kc) {
+        mbar_wait(&full_bar[s], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem_a + s * kABytes);
+          const uint32_t b_addr = smem_u32(smem_b + kc * kBBytes);
+#pragma unroll
+          for (int k = 0; k < CK / 16; ++k) {
+            umma_bf16(d_tmem, make_smem_desc<kSwz>(a_addr + k * 32), make_smem_desc<kSwz>(b_addr + k * 32), idesc,
+                      (uint32_t)((kc | k) != 0));
+          }
+          umma_commit(&empty_bar[s]);                      // frees the A slot when these MMAs retire
+          if (kc == p.num_chunks - 1) umma_commit(&tmem_full[as]);
+        }
+        __syncwarp();
+        if (++s == p.num_stages) { s = 0; phase ^= 1; }
+      }
+      if (++as == 2) { as = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;          // row of the 128-pixel tile
+    int as = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      mbar_wait(&tmem_full[as], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+
+      if constexpr (MODE == EPI_ROWS) {
+        bool valid, zero = false;
+        uint8_t* dst;
+        if (p.flat_rows > 0) {
+          const int64_t R = (int64_t)t.x0 + row;
+          valid = R < p.flat_rows;
+          dst = reinterpret_cast<uint8_t*>(p.out) + R * p.out_pitch + p.out_off;
+          if (p.hrb_mask) {
+            const int s16 = (int)(R & 15);
+            const int64_t blk = R >> 4;
+            const int X = (int)(blk % (p.lr_w + 1));
+            const int Y = (int)((blk / (p.lr_w + 1)) % (p.lr_h + 1));
+            const int ry = s16 >> 2, rx = s16 & 3;
+            zero = (Y == 0 && ry < 2) || (Y == p.lr_h && ry >= 2) || (X == 0 && rx < 2) || (X == p.lr_w && rx >= 2);
+          }
+        } else {
+          const int y = t.y0 + row / p.tile_w, x = t.x0 + row % p.tile_w;
+          valid = (y < p.out_h) && (x < p.out_w);
+          dst = reinterpret_cast<uint8_t*>(p.out) + (((int64_t)t.b * p.out_h + y) * p.out_w + x) * p.out_pitch + p.out_off;
+        }
+        const float slope = s_bias[p.bias_n];
+#pragma unroll 1
+        for (int cg = 0; cg < BN / 32; ++cg) {
+          uint32_t v[32];
+          tmem_ld32(taddr + cg * 32, v);
+          tmem_ld_wait();
+          if (cg == BN / 32 - 1) {
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[as]);     // accumulator stage is free again
+          }
+          if (valid) {
+            uint32_t o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float a = prelu(__uint_as_float(v[2 * j]) + s_bias[cg * 32 + 2 * j], slope, p.act);
+              float b = prelu(__uint_as_float(v[2 * j + 1]) + s_bias[cg * 32 + 2 * j + 1], slope, p.act);
+              o[j] = zero ? 0u : pack_bf16(a, b);
+            }
+            uint4* d4 = reinterpret_cast<uint4*>(dst + cg * 64);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) d4[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          }
+        }
+      } else if constexpr (MODE == EPI_DECONV) {
+        // row = patch position (Y, X) in [0,h] x [0,w]; this N tile holds sub-positions
+        // s = n_tile*8 .. n_tile*8+7 (ry = s>>2, rx = s&3), 32 output channels each.
+        const int Y = t.y0 + row / p.tile_w, X = t.x0 + row % p.tile_w;
+        const bool valid = (Y <= p.lr_h) && (X <= p.lr_w);
+        const int H = 4 * p.lr_h, W = 4 * p.lr_w;
+        const float slope = s_bias[p.bias_n];
+#pragma unroll 1
+        for (int cg = 0; cg < 8; ++cg) {
+          uint32_t v[32];
+          tmem_ld32(taddr + cg * 32, v);
+          tmem_ld_wait();
+          if (cg == 7) {
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[as]);
+          }
+          const int s16 = t.n_tile * 8 + cg;
+          const int ry = s16 >> 2, rx = s16 & 3;
+          const int Yt = 4 * Y + ry - 2, Xt = 4 * X + rx - 2;       // true HR coordinates
+          const bool inside = (Yt >= 0) && (Yt < H) && (Xt >= 0) && (Xt < W);
+          uint8_t* dst;
+          bool store;
+          if (p.deconv_nhwc) {
+            store = valid && inside;
+            dst = reinterpret_cast<uint8_t*>(p.out) + (((int64_t)t.b * H + Yt) * W + Xt) * 64;
+          } else {
+            store = valid;
+            dst = reinterpret_cast<uint8_t*>(p.out) +
+                  ((((int64_t)t.b * (p.lr_h + 1) + Y) * (p.lr_w + 1) + X) * 16 + s16) * 64;
+          }
+          if (store) {
+            uint32_t o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float a = prelu(__uint_as_float(v[2 * j]) + s_bias[2 * j], slope, p.act);
+              float b = prelu(__uint_as_float(v[2 * j + 1]) + s_bias[2 * j + 1], slope, p.act);
+              o[j] = inside ? pack_bf16(a, b) : 0u;                 // padding ring of the block layout
+            }
+            uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) d4[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          }
+        }
+      } else {  // EPI_CONV_OUT
+        const int Y = t.y0 + row / p.tile_w, X = t.x0 + row % p.tile_w;
+        const bool valid = (Y < p.out_h) && (X < p.out_w);
+        uint32_t v[16];
+        tmem_ld16(taddr, v);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&tmem_empty[as]);
+        if (valid) {
+          // bilinear x4 skip, align_corners=False (SRProjectionModule.py:136; ATen
+          // upsample_bilinear2d: src = (dst+0.5)/4 - 0.5 clamped at 0), on sub_mean(x)
+          const int h = p.lr_h, w = p.lr_w;
+          float sy = fmaxf((Y + 0.5f) * 0.25f - 0.5f, 0.0f), sx = fmaxf((X + 0.5f) * 0.25f - 0.5f, 0.0f);
+          int y0i = (int)sy, x0i = (int)sx;
+          int y1i = y0i + (y0i < h - 1 ? 1 : 0), x1i = x0i + (x0i < w - 1 ? 1 : 0);
+          float ly = sy - y0i, lx = sx - x0i, hy = 1.0f - ly, hx = 1.0f - lx;
+          float* out = reinterpret_cast<float*>(p.out);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float* src = p.skip_src + ((int64_t)t.b * 3 + c) * h * w;
+            float v00 = __ldg(src + y0i * w + x0i) + s_bias[p.bias_n + 1 + c], v01 = __ldg(src + y0i * w + x1i) + s_bias[p.bias_n + 1 + c];
+            float v10 = __ldg(src + y1i * w + x0i) + s_bias[p.bias_n + 1 + c], v11 = __ldg(src + y1i * w + x1i) + s_bias[p.bias_n + 1 + c];
+            float skip = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
+            float r = skip + (__uint_as_float(v[c]) + s_bias[c]);
+            out[(((int64_t)t.b * 3 + c) * p.out_h + Y) * p.out_w + X] = r + s_bias[p.bias_n + 4 + c];
+          }
+        }
+      }
+      if (++as == 2) { as = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+}  // namespace vsr

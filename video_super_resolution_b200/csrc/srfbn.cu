@@ -1,0 +1,879 @@
+// srfbn.cu -- host side of the fusion / upsampling convolution stack (a6/a7): plan, weight packing,
+// TMA tensor maps and the launch sequence over the tcgen05 implicit-GEMM kernel (igemm.cuh), plus
+// the two small SIMT kernels around it (input im2col, per-pixel fc fuse over the map axis).
+//
+//   ref: my_packages/SRProjection/SRProjectionModule.py:96-150 (SRProjectionModule),
+//        :7-93 (FeedbackBlock), my_packages/SRProjection/blocks.py:7-74
+//   dataflow: the INTENDED dense-concat dataflow of SURVEY.md Appendix C (the reference stages its
+//   concats through torch.empty buffers it never fills, SRProjectionModule.py:55-59,70-74).
+//
+// Every dense layer is one launch of igemm_kernel (BF16 operands, FP32 accumulation in TMEM):
+//   conv_in 3x3 3->128    : im2col'd input (K padded 27->32), pointwise GEMM, N=128
+//   1x1 convs             : pointwise GEMM over up to 6 concatenated 32-channel sources (the
+//                           torch.cat never materialises), N=32
+//   ConvTranspose 8x8 s4  : output-stationary: block (Yb,Xb) of the "HR block layout" gets 2x2 LR
+//                           taps, N = 16 sub-positions x 32 channels (two N=256 halves)
+//   Conv 8x8 s4           : LR pixel (Y,X) reads the 2x2 blocks (Y..Y+1, X..X+1), K = 4*512, N=32
+//   conv_out 3x3 32->3    : 9 taps at HR, N=16 (3 used), epilogue adds the bilinear skip and the
+//                           mean shifts and writes fp32 planes
+// HR block layout: an HR feature map of (4h,4w) pixels is stored as (h+1, w+1) blocks of 4x4 pixels
+// whose origin is shifted by (-2,-2): block (Yb,Xb), sub-position s=ry*4+rx holds HR pixel
+// (4Yb+ry-2, 4Xb+rx-2); positions outside the image are a zero ring.  With this shift both 8x8-s4
+// operators touch exactly 2x2 blocks (padding 2 is absorbed by the ring), and a block is one
+// contiguous 1 KB row of 16 x 32 BF16.
+//
+// The `out` deconv and `conv_out` are evaluated for the last feedback step only: the reference
+// keeps `outs[-1:]` (SRProjectionModule.py:145), the earlier steps' images are dead values.
+#include "igemm.cuh"
+
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+namespace vsr {
+namespace {
+
+constexpr int kNF = 32;        // num_features
+constexpr int kGroups = 6;
+constexpr int kMaxMaps = 64;   // fc in-features bound (weights live in shared memory)
+
+// ------------------------------------------------------------------------------------------------
+// driver entry point (no link-time dependency on libcuda: the library must load on a CPU-only box)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// channels-last BF16 activation tensor (b, y, x, c), c innermost; box = [ck, tw, th, 1]
+int make_act_map(CUtensorMap* m, const void* base, int64_t C, int64_t W, int64_t H, int64_t B, int ck, int tw, int th) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return VSR_ERR_STATE;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * W, (cuuint64_t)C * 2 * W * H};
+  cuuint32_t box[4] = {(cuuint32_t)ck, (cuuint32_t)tw, (cuuint32_t)th, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, ck == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? VSR_OK : VSR_ERR_CUDA_BASE + 999;
+}
+
+// packed weights [N rows][K] BF16, K innermost; box = [ck, bn]
+int make_w_map(CUtensorMap* m, const void* base, int64_t K, int64_t N, int ck, int bn) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return VSR_ERR_STATE;
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)ck, (cuuint32_t)bn};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, ck == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? VSR_OK : VSR_ERR_CUDA_BASE + 999;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel variants
+// ------------------------------------------------------------------------------------------------
+enum Variant : int { V_PW32 = 0, V_PW128, V_DECONV, V_DOWN, V_CONVOUT, V_COUNT };
+
+// kernel classes for the per-launch accounting bench.py reads (vsr_srfbn_profile_*)
+static_assert(VSR_SRFBN_KERNEL_CLASSES == 8, "header constant");
+enum KClass : int { KC_IM2COL = 0, KC_CONV_IN, KC_PW_LR, KC_PW_HR, KC_DECONV, KC_DOWNCONV, KC_CONV_OUT, KC_FC, KC_COUNT };
+
+struct Layer {
+  int variant;
+  IgemmParams p;
+  int grid;
+  size_t smem;
+  int kclass;
+  double flops;   // 2*MAC of the layer as specified (padding / ring rows not counted)
+  double bytes;   // compulsory HBM bytes of this launch: its inputs + outputs, each once
+};
+
+template <int MODE, int CK, int BN>
+int launch_variant(const Layer& L, cudaStream_t st) {
+  static bool attr_set = false;   // per process; the attribute is sticky per function
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<MODE, CK, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         227 * 1024);
+    if (e != cudaSuccess) return cuda_status(e);
+    attr_set = true;
+  }
+  igemm_kernel<MODE, CK, BN><<<L.grid, kIgemmThreads, L.smem, st>>>(L.p);
+  return after_launch();
+}
+
+int launch_layer(const Layer& L, cudaStream_t st) {
+  switch (L.variant) {
+    case V_PW32: return launch_variant<EPI_ROWS, 32, 32>(L, st);
+    case V_PW128: return launch_variant<EPI_ROWS, 32, 128>(L, st);
+    case V_DECONV: return launch_variant<EPI_DECONV, 32, 256>(L, st);
+    case V_DOWN: return launch_variant<EPI_ROWS, 64, 32>(L, st);
+    case V_CONVOUT: return launch_variant<EPI_CONV_OUT, 32, 16>(L, st);
+    default: return VSR_ERR_INVALID_ARG;
+  }
+}
+
+size_t variant_smem(int variant, int chunks, int stages) {
+  switch (variant) {
+    case V_PW32: return igemm_smem_bytes<32, 32>(chunks, stages);
+    case V_PW128: return igemm_smem_bytes<32, 128>(chunks, stages);
+    case V_DECONV: return igemm_smem_bytes<32, 256>(chunks, stages);
+    case V_DOWN: return igemm_smem_bytes<64, 32>(chunks, stages);
+    default: return igemm_smem_bytes<32, 16>(chunks, stages);
+  }
+}
+
+void finish_layer(Layer& L, int ctas_per_sm) {
+  IgemmParams& p = L.p;
+  L.smem = variant_smem(L.variant, p.num_chunks, p.num_stages);
+  int64_t total = (int64_t)p.n_tiles * p.tiles_x * p.tiles_y * p.batch;
+  int64_t g = (int64_t)kNumSMs * ctas_per_sm;
+  if (g > total) g = total;
+  g -= g % p.n_tiles;                 // a CTA keeps one N tile's weights resident
+  if (g < p.n_tiles) g = p.n_tiles;
+  L.grid = (int)g;
+}
+
+struct Src {
+  const void* base;   // [rows][C] BF16
+  int C;              // channels of that buffer
+  int c0;             // first channel used
+  int nch;            // channels used (multiple of 32)
+};
+
+// 1x1 convolution over concatenated sources, flat rows.  BN = 32 or 128.
+int build_pointwise(Layer& L, const Src* src, int nsrc, int64_t rows, const void* w_dev, const float* bias_dev,
+                    int bn, int act, void* out, int64_t out_pitch, int64_t out_off, int hrb_mask, int lr_h, int lr_w) {
+  memset(&L, 0, sizeof(L));
+  L.variant = bn == 128 ? V_PW128 : V_PW32;
+  IgemmParams& p = L.p;
+  int K = 0, nc = 0;
+  if (nsrc > kMaxSources) return VSR_ERR_UNSUPPORTED;
+  for (int s = 0; s < nsrc; ++s) {
+    int rc = make_act_map(&p.a_maps[s], src[s].base, src[s].C, rows, 1, 1, 32, kTileM, 1);
+    if (rc) return rc;
+    for (int c = 0; c < src[s].nch; c += 32) {
+      if (nc >= kMaxChunks) return VSR_ERR_UNSUPPORTED;
+      p.chunks[nc].map = (int8_t)s;
+      p.chunks[nc].dx = p.chunks[nc].dy = 0;
+      p.chunks[nc].c0 = src[s].c0 + c;
+      ++nc;
+    }
+    K += src[s].nch;
+  }
+  int rc = make_w_map(&p.b_map, w_dev, K, bn, 32, bn);
+  if (rc) return rc;
+  p.num_chunks = nc;
+  p.num_stages = 6;
+  p.n_tiles = 1;
+  p.tiles_x = (int)ceil_div64(rows, kTileM);
+  p.tiles_y = 1;
+  p.batch = 1;
+  p.tile_w = kTileM;
+  p.tile_h = 1;
+  p.bias = bias_dev;
+  p.bias_n = bn;
+  p.act = act;
+  p.out = out;
+  p.out_pitch = out_pitch;
+  p.out_off = out_off;
+  p.flat_rows = rows;
+  p.lr_h = lr_h;
+  p.lr_w = lr_w;
+  p.hrb_mask = hrb_mask;
+  finish_layer(L, bn == 128 ? 2 : 3);
+  const double real_rows = hrb_mask ? (double)rows / ((double)(lr_h + 1) * (lr_w + 1)) * ((double)lr_h * lr_w) : (double)rows;
+  L.kclass = bn == 128 ? KC_CONV_IN : (hrb_mask ? KC_PW_HR : KC_PW_LR);
+  L.flops = 2.0 * real_rows * K * bn;
+  L.bytes = real_rows * (K + bn) * 2.0;
+  return VSR_OK;
+}
+
+constexpr int kTW = 16, kTH = 8;   // spatial tile (kTW * kTH == 128 rows)
+
+// ConvTranspose2d(32,32,8,4,2): x (B,h,w,32) -> HR block layout (B,h+1,w+1,16,32) or plain NHWC (B,4h,4w,32)
+int build_deconv(Layer& L, const void* x, int B, int h, int w, const void* w_dev, const float* bias_dev, void* out,
+                 int nhwc) {
+  memset(&L, 0, sizeof(L));
+  L.variant = V_DECONV;
+  IgemmParams& p = L.p;
+  int rc = make_act_map(&p.a_maps[0], x, kNF, w, h, B, 32, kTW, kTH);
+  if (rc) return rc;
+  rc = make_w_map(&p.b_map, w_dev, 4 * kNF, 512, 32, 256);
+  if (rc) return rc;
+  // chunk t = (dy+1)*2 + (dx+1), tap at LR (Yb+dy, Xb+dx), dy,dx in {-1,0}
+  for (int t = 0; t < 4; ++t) {
+    p.chunks[t].map = 0;
+    p.chunks[t].dy = (int8_t)((t >> 1) - 1);
+    p.chunks[t].dx = (int8_t)((t & 1) - 1);
+    p.chunks[t].c0 = 0;
+  }
+  p.num_chunks = 4;
+  p.num_stages = 4;
+  p.n_tiles = 2;
+  p.tiles_x = ceil_div(w + 1, kTW);
+  p.tiles_y = ceil_div(h + 1, kTH);
+  p.batch = B;
+  p.tile_w = kTW;
+  p.tile_h = kTH;
+  p.bias = bias_dev;
+  p.bias_n = kNF;
+  p.act = 1;
+  p.out = out;
+  p.lr_h = h;
+  p.lr_w = w;
+  p.deconv_nhwc = nhwc;
+  finish_layer(L, 1);
+  const double lrpx = (double)B * h * w;
+  L.kclass = KC_DECONV;
+  L.flops = lrpx * 131072.0;            // 2 * 64 taps * 32 * 32 per LR pixel
+  L.bytes = lrpx * 64.0 * 17.0;         // LR in + 16 HR pixels out, 32 BF16 channels each
+  return VSR_OK;
+}
+
+// Conv2d(32,32,8,4,2) on the HR block layout: (B,h+1,w+1,512) -> (B,h,w,32)
+int build_downconv(Layer& L, const void* xb, int B, int h, int w, const void* w_dev, const float* bias_dev,
+                   void* out) {
+  memset(&L, 0, sizeof(L));
+  L.variant = V_DOWN;
+  IgemmParams& p = L.p;
+  int rc = make_act_map(&p.a_maps[0], xb, 512, w + 1, h + 1, B, 64, kTW, kTH);
+  if (rc) return rc;
+  rc = make_w_map(&p.b_map, w_dev, 2048, kNF, 64, kNF);
+  if (rc) return rc;
+  int nc = 0;
+  for (int t = 0; t < 4; ++t)
+    for (int q = 0; q < 8; ++q, ++nc) {
+      p.chunks[nc].map = 0;
+      p.chunks[nc].dy = (int8_t)(t >> 1);
+      p.chunks[nc].dx = (int8_t)(t & 1);
+      p.chunks[nc].c0 = q * 64;
+    }
+  p.num_chunks = nc;
+  p.num_stages = 4;
+  p.n_tiles = 1;
+  p.tiles_x = ceil_div(w, kTW);
+  p.tiles_y = ceil_div(h, kTH);
+  p.batch = B;
+  p.tile_w = kTW;
+  p.tile_h = kTH;
+  p.bias = bias_dev;
+  p.bias_n = kNF;
+  p.act = 1;
+  p.out = out;
+  p.out_pitch = kNF * 2;
+  p.out_off = 0;
+  p.flat_rows = 0;
+  p.out_h = h;
+  p.out_w = w;
+  p.lr_h = h;
+  p.lr_w = w;
+  finish_layer(L, 1);
+  const double lrpx = (double)B * h * w;
+  L.kclass = KC_DOWNCONV;
+  L.flops = lrpx * 131072.0;
+  L.bytes = lrpx * 64.0 * 17.0;
+  return VSR_OK;
+}
+
+// conv_out 3x3 p1 32->3 at HR + bilinear skip + mean shifts, fp32 planar output (B,3,4h,4w)
+int build_conv_out(Layer& L, const void* xhr, int B, int h, int w, const void* w_dev, const float* bias_dev,
+                   float* out) {
+  memset(&L, 0, sizeof(L));
+  L.variant = V_CONVOUT;
+  IgemmParams& p = L.p;
+  const int H = 4 * h, W = 4 * w;
+  const int tw = 32, th = 4;
+  int rc = make_act_map(&p.a_maps[0], xhr, kNF, W, H, B, 32, tw, th);
+  if (rc) return rc;
+  rc = make_w_map(&p.b_map, w_dev, 9 * kNF, 16, 32, 16);
+  if (rc) return rc;
+  for (int t = 0; t < 9; ++t) {
+    p.chunks[t].map = 0;
+    p.chunks[t].dy = (int8_t)(t / 3 - 1);
+    p.chunks[t].dx = (int8_t)(t % 3 - 1);
+    p.chunks[t].c0 = 0;
+  }
+  p.num_chunks = 9;
+  p.num_stages = 6;
+  p.n_tiles = 1;
+  p.tiles_x = ceil_div(W, tw);
+  p.tiles_y = ceil_div(H, th);
+  p.batch = B;
+  p.tile_w = tw;
+  p.tile_h = th;
+  p.bias = bias_dev;
+  p.bias_n = 16;
+  p.act = 0;
+  p.out = out;
+  p.out_h = H;
+  p.out_w = W;
+  p.lr_h = h;
+  p.lr_w = w;
+  finish_layer(L, 2);
+  const double hrpx = (double)B * H * W;
+  L.kclass = KC_CONV_OUT;
+  L.flops = hrpx * 2.0 * 288 * 3;
+  L.bytes = hrpx * (64.0 + 12.0) + hrpx / 16.0 * 12.0;
+  return VSR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packing (host): reference state-dict layouts -> K-major BF16 GEMM operands
+// ------------------------------------------------------------------------------------------------
+inline uint16_t f2bf(float f) {   // round to nearest even, like __float2bfloat16_rn
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+// Conv2d 1x1 weight (N, K, 1, 1) -> [N][K]
+void pack_pointwise(const float* w, int N, int K, uint16_t* dst) {
+  for (int i = 0; i < N * K; ++i) dst[i] = f2bf(w[i]);
+}
+// conv_in (128,3,3,3) -> [128][32], k = c*9 + ky*3 + kx, zero padded
+void pack_conv_in(const float* w, uint16_t* dst) {
+  for (int n = 0; n < 128; ++n)
+    for (int k = 0; k < 32; ++k) dst[n * 32 + k] = k < 27 ? f2bf(w[n * 27 + k]) : 0;
+}
+// ConvTranspose2d weight (c in, o out, 8, 8) -> [512 = s*32+o][128 = t*32+c],
+// t = (dy+1)*2+(dx+1), ky = ry - 4*dy, kx = rx - 4*dx   (out y = 4i - 2 + ky)
+void pack_deconv(const float* w, uint16_t* dst) {
+  for (int s = 0; s < 16; ++s)
+    for (int o = 0; o < 32; ++o)
+      for (int t = 0; t < 4; ++t)
+        for (int c = 0; c < 32; ++c) {
+          int ry = s >> 2, rx = s & 3, dy = (t >> 1) - 1, dx = (t & 1) - 1;
+          int ky = ry - 4 * dy, kx = rx - 4 * dx;
+          dst[(s * 32 + o) * 128 + t * 32 + c] = f2bf(w[((c * 32 + o) * 8 + ky) * 8 + kx]);
+        }
+}
+// Conv2d weight (o, c, 8, 8) s4 p2 -> [32][2048], k = ((dy*2+dx)*16 + s)*32 + c, ky = 4dy+ry, kx = 4dx+rx
+void pack_downconv(const float* w, uint16_t* dst) {
+  for (int o = 0; o < 32; ++o)
+    for (int t = 0; t < 4; ++t)
+      for (int s = 0; s < 16; ++s)
+        for (int c = 0; c < 32; ++c) {
+          int ky = 4 * (t >> 1) + (s >> 2), kx = 4 * (t & 1) + (s & 3);
+          dst[o * 2048 + (t * 16 + s) * 32 + c] = f2bf(w[((o * 32 + c) * 8 + ky) * 8 + kx]);
+        }
+}
+// conv_out (3,32,3,3) -> [16][288], k = (ky*3+kx)*32 + c, rows 3..15 zero
+void pack_conv_out(const float* w, uint16_t* dst) {
+  memset(dst, 0, 16 * 288 * 2);
+  for (int o = 0; o < 3; ++o)
+    for (int t = 0; t < 9; ++t)
+      for (int c = 0; c < 32; ++c) dst[o * 288 + t * 32 + c] = f2bf(w[(o * 32 + c) * 9 + t]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// SIMT kernels around the GEMMs
+// ------------------------------------------------------------------------------------------------
+// sub_mean + zero-padded 3x3 im2col: x (M,3,h,w) f32 -> A0 [M*h*w][32] BF16 (blocks.py:46-55 MeanShift is
+// an identity 1x1 conv with bias -255*mean; conv_in pads ITS input, i.e. the shifted image, with zeros).
+__global__ void __launch_bounds__(256)
+im2col_kernel(const float* __restrict__ x, const float* __restrict__ sub_bias, uint4* __restrict__ a0, int M, int h,
+              int w) {
+  const int64_t n = (int64_t)M * h * w;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int xx = (int)(i % w), yy = (int)((i / w) % h);
+    const int64_t m = i / ((int64_t)h * w);
+    float v[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[k] = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float* pl = x + (m * 3 + c) * (int64_t)h * w;
+      const float sb = __ldg(sub_bias + c);
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          int y2 = yy + ky - 1, x2 = xx + kx - 1;
+          if (y2 >= 0 && y2 < h && x2 >= 0 && x2 < w) v[c * 9 + ky * 3 + kx] = __ldg(pl + (int64_t)y2 * w + x2) + sb;
+        }
+    }
+    uint4* dst = a0 + i * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      dst[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                          pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+  }
+}
+
+// fc over the map axis per (channel, HR pixel): Linear(M,32)-ReLU-Linear(32,1)-ReLU
+// (SRProjectionModule.py:126-131,146).  maps (M,3,H,W) f32 -> y (1,3,H,W) f32.
+// fcw: [32*M fc0_w][32 fc0_b][32 fc2_w][1 fc2_b]
+__global__ void __launch_bounds__(256)
+fc_fuse_kernel(const float* __restrict__ maps, const float* __restrict__ fcw, float* __restrict__ y, int M, int64_t n) {
+  __shared__ float s_w[32 * kMaxMaps + 65];
+  const int nw = 32 * M + 65;
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) s_w[i] = fcw[i];
+  __syncthreads();
+  const float* w0 = s_w;
+  const float* b0 = s_w + 32 * M;
+  const float* w2 = b0 + 32;
+  const float b2 = w2[32];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float hid[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) hid[j] = b0[j];
+    for (int m = 0; m < M; ++m) {
+      const float v = __ldg(maps + (int64_t)m * n + i);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) hid[j] = fmaf(w0[j * M + m], v, hid[j]);
+    }
+    float o = b2;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) o = fmaf(w2[j], fmaxf(hid[j], 0.0f), o);
+    y[i] = fmaxf(o, 0.0f);
+  }
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+}  // namespace vsr
+
+using namespace vsr;
+
+// ------------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------------
+enum LayerId : int {
+  W_CONV_IN = 0, W_FEAT_IN, W_COMPRESS_IN, W_UPTRAN0, W_UP0 = W_UPTRAN0 + 5, W_DOWNTRAN0 = W_UP0 + 6,
+  W_DOWN0 = W_DOWNTRAN0 + 5, W_COMPRESS_OUT = W_DOWN0 + 6, W_OUT, W_CONV_OUT, W_COUNT
+};
+
+struct WEntry {
+  size_t w_off, b_off;   // byte offsets in the packed buffer
+  int N, K;
+};
+
+struct vsr_srfbn_plan {
+  vsr_srfbn_config cfg;
+  WEntry we[W_COUNT];
+  size_t fc_off;          // fp32: fc0_w (32*M), fc0_b (32), fc2_w (32), fc2_b (1)
+  size_t misc_off;        // fp32: sub_mean bias (3)
+  size_t weight_bytes;
+  // workspace offsets
+  size_t o_a0, o_c128, o_xfeat, o_hidden, o_lr[7], o_u, o_hr[6], o_hb, o_premix, ws_bytes;
+  bool bound;
+  const uint8_t* dev_w;
+  uint8_t* ws;
+  std::vector<Layer> layers;
+  int conv_out_layer;
+  std::vector<cudaEvent_t> events;   // profiling: one before every launch + one after the last
+  bool profile;
+};
+
+static void layout_weights(vsr_srfbn_plan* pl) {
+  size_t off = 0;
+  auto put = [&](int id, int N, int K, int bias_floats) {
+    pl->we[id].N = N;
+    pl->we[id].K = K;
+    pl->we[id].w_off = off;
+    off = align_up(off + (size_t)N * K * 2, 256);
+    pl->we[id].b_off = off;
+    off = align_up(off + (size_t)bias_floats * 4, 256);
+  };
+  put(W_CONV_IN, 128, 32, 129);
+  put(W_FEAT_IN, 32, 128, 33);
+  put(W_COMPRESS_IN, 32, 64, 33);
+  for (int i = 0; i < 5; ++i) put(W_UPTRAN0 + i, 32, 32 * (i + 2), 33);
+  for (int i = 0; i < 6; ++i) put(W_UP0 + i, 512, 128, 33);
+  for (int i = 0; i < 5; ++i) put(W_DOWNTRAN0 + i, 32, 32 * (i + 2), 33);
+  for (int i = 0; i < 6; ++i) put(W_DOWN0 + i, 32, 2048, 33);
+  put(W_COMPRESS_OUT, 32, 192, 33);
+  put(W_OUT, 512, 128, 33);
+  put(W_CONV_OUT, 16, 288, 16 + 7);
+  pl->fc_off = off;
+  off = align_up(off + (size_t)(32 * pl->cfg.num_maps + 65) * 4, 256);
+  pl->misc_off = off;
+  off = align_up(off + 16, 256);
+  pl->weight_bytes = off;
+}
+
+static void layout_workspace(vsr_srfbn_plan* pl) {
+  const vsr_srfbn_config& c = pl->cfg;
+  const size_t P = (size_t)c.num_maps * c.h * c.w;
+  const size_t Rb = (size_t)c.num_maps * (c.h + 1) * (c.w + 1) * 16;
+  size_t off = 0;
+  auto put = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 1024);
+    return o;
+  };
+  pl->o_a0 = put(P * 64);
+  pl->o_c128 = put(P * 256);
+  pl->o_xfeat = put(P * 64);
+  pl->o_hidden = put(P * 64);
+  for (int i = 0; i < 7; ++i) pl->o_lr[i] = put(P * 64);
+  pl->o_u = put(P * 64);
+  for (int i = 0; i < 6; ++i) pl->o_hr[i] = put(Rb * 64);
+  pl->o_hb = put(Rb * 64);   // downtran output; reused for the plain-NHWC `out` deconv result (16P*64 <= Rb*64)
+  pl->o_premix = put(P * 16 * 3 * 4);
+  pl->ws_bytes = off;
+}
+
+extern "C" int vsr_srfbn_plan_create(const vsr_srfbn_config* cfg, vsr_srfbn_plan** out_plan) {
+  if (!cfg || !out_plan) return VSR_ERR_INVALID_ARG;
+  *out_plan = nullptr;
+  if (cfg->num_maps < 1 || cfg->h < 1 || cfg->w < 1 || cfg->num_steps < 1) return VSR_ERR_INVALID_ARG;
+  // geometry hard-wired by the reference: x4, k8 s4 p2, 32 features, 6 groups (SRProjectionModule.py:97-103)
+  if (cfg->num_groups != kGroups || cfg->num_features != kNF || cfg->upscale != 4 || cfg->num_maps > kMaxMaps)
+    return VSR_ERR_UNSUPPORTED;
+  vsr_srfbn_plan* pl = new (std::nothrow) vsr_srfbn_plan();
+  if (!pl) return VSR_ERR_INVALID_ARG;
+  pl->cfg = *cfg;
+  pl->bound = false;
+  pl->dev_w = nullptr;
+  pl->ws = nullptr;
+  pl->conv_out_layer = -1;
+  pl->profile = false;
+  layout_weights(pl);
+  layout_workspace(pl);
+  *out_plan = pl;
+  return VSR_OK;
+}
+
+extern "C" void vsr_srfbn_plan_destroy(vsr_srfbn_plan* plan) {
+  if (!plan) return;
+  for (cudaEvent_t e : plan->events) cudaEventDestroy(e);
+  delete plan;
+}
+
+extern "C" size_t vsr_srfbn_weight_bytes(const vsr_srfbn_plan* plan) { return plan ? plan->weight_bytes : 0; }
+extern "C" size_t vsr_srfbn_workspace_bytes(const vsr_srfbn_plan* plan) { return plan ? plan->ws_bytes : 0; }
+
+extern "C" int vsr_srfbn_pack_weights(const vsr_srfbn_plan* pl, const vsr_srfbn_weights* w, void* host_packed) {
+  if (!pl || !w || !host_packed) return VSR_ERR_INVALID_ARG;
+  uint8_t* base = reinterpret_cast<uint8_t*>(host_packed);
+  memset(base, 0, pl->weight_bytes);
+  auto W = [&](int id) { return reinterpret_cast<uint16_t*>(base + pl->we[id].w_off); };
+  auto Bv = [&](int id) { return reinterpret_cast<float*>(base + pl->we[id].b_off); };
+  auto bias = [&](int id, const float* b, int n, float slope) {
+    if (!b) return false;
+    memcpy(Bv(id), b, (size_t)n * 4);
+    Bv(id)[n] = slope;
+    return true;
+  };
+  bool ok = w->conv_in_w && w->feat_in_w && w->compress_in_w && w->compress_out_w && w->out_w && w->conv_out_w &&
+            w->fc0_w && w->fc0_b && w->fc2_w && w->fc2_b && w->sub_mean_bias && w->add_mean_bias;
+  for (int i = 0; i < 6; ++i) ok = ok && w->up_w[i] && w->down_w[i];
+  for (int i = 0; i < 5; ++i) ok = ok && w->uptran_w[i] && w->downtran_w[i];
+  if (!ok) return VSR_ERR_INVALID_ARG;
+  pack_conv_in(w->conv_in_w, W(W_CONV_IN));
+  ok = ok && bias(W_CONV_IN, w->conv_in_b, 128, w->conv_in_slope);
+  pack_pointwise(w->feat_in_w, 32, 128, W(W_FEAT_IN));
+  ok = ok && bias(W_FEAT_IN, w->feat_in_b, 32, w->feat_in_slope);
+  pack_pointwise(w->compress_in_w, 32, 64, W(W_COMPRESS_IN));
+  ok = ok && bias(W_COMPRESS_IN, w->compress_in_b, 32, w->compress_in_slope);
+  for (int i = 0; i < 5; ++i) {
+    pack_pointwise(w->uptran_w[i], 32, 32 * (i + 2), W(W_UPTRAN0 + i));
+    ok = ok && bias(W_UPTRAN0 + i, w->uptran_b[i], 32, w->uptran_slope[i]);
+    pack_pointwise(w->downtran_w[i], 32, 32 * (i + 2), W(W_DOWNTRAN0 + i));
+    ok = ok && bias(W_DOWNTRAN0 + i, w->downtran_b[i], 32, w->downtran_slope[i]);
+  }
+  for (int i = 0; i < 6; ++i) {
+    pack_deconv(w->up_w[i], W(W_UP0 + i));
+    ok = ok && bias(W_UP0 + i, w->up_b[i], 32, w->up_slope[i]);
+    pack_downconv(w->down_w[i], W(W_DOWN0 + i));
+    ok = ok && bias(W_DOWN0 + i, w->down_b[i], 32, w->down_slope[i]);
+  }
+  pack_pointwise(w->compress_out_w, 32, 192, W(W_COMPRESS_OUT));
+  ok = ok && bias(W_COMPRESS_OUT, w->compress_out_b, 32, w->compress_out_slope);
+  pack_deconv(w->out_w, W(W_OUT));
+  ok = ok && bias(W_OUT, w->out_b, 32, w->out_slope);
+  pack_conv_out(w->conv_out_w, W(W_CONV_OUT));
+  if (!w->conv_out_b) return VSR_ERR_INVALID_ARG;
+  {
+    float* b = Bv(W_CONV_OUT);
+    memcpy(b, w->conv_out_b, 3 * 4);
+    b[16] = 0.0f;
+    memcpy(b + 17, w->sub_mean_bias, 3 * 4);
+    memcpy(b + 20, w->add_mean_bias, 3 * 4);
+  }
+  if (!ok) return VSR_ERR_INVALID_ARG;
+  const int M = pl->cfg.num_maps;
+  float* fc = reinterpret_cast<float*>(base + pl->fc_off);
+  memcpy(fc, w->fc0_w, (size_t)32 * M * 4);
+  memcpy(fc + 32 * M, w->fc0_b, 32 * 4);
+  memcpy(fc + 32 * M + 32, w->fc2_w, 32 * 4);
+  fc[32 * M + 64] = w->fc2_b[0];
+  memcpy(base + pl->misc_off, w->sub_mean_bias, 3 * 4);
+  return VSR_OK;
+}
+
+extern "C" int vsr_srfbn_bind(vsr_srfbn_plan* pl, const void* dev_weights, void* dev_workspace,
+                              size_t workspace_bytes) {
+  if (!pl || !dev_weights || !dev_workspace) return VSR_ERR_INVALID_ARG;
+  if (workspace_bytes < pl->ws_bytes) return VSR_ERR_WORKSPACE;
+  if (reinterpret_cast<uintptr_t>(dev_weights) % 256 || reinterpret_cast<uintptr_t>(dev_workspace) % 256)
+    return VSR_ERR_INVALID_ARG;
+  pl->bound = false;
+  pl->dev_w = reinterpret_cast<const uint8_t*>(dev_weights);
+  pl->ws = reinterpret_cast<uint8_t*>(dev_workspace);
+  pl->layers.clear();
+  const vsr_srfbn_config& c = pl->cfg;
+  const int M = c.num_maps, h = c.h, w = c.w;
+  const int64_t P = (int64_t)M * h * w;
+  const int64_t Rb = (int64_t)M * (h + 1) * (w + 1) * 16;
+  uint8_t* ws = pl->ws;
+  auto Wp = [&](int id) { return (const void*)(pl->dev_w + pl->we[id].w_off); };
+  auto Bp = [&](int id) { return reinterpret_cast<const float*>(pl->dev_w + pl->we[id].b_off); };
+  int rc;
+  Layer L;
+#define PUSH(expr)        \
+  do {                    \
+    rc = (expr);          \
+    if (rc) return rc;    \
+    pl->layers.push_back(L); \
+  } while (0)
+
+  {  // conv_in: A0 [P,32] -> C128 [P,128]
+    Src s{ws + pl->o_a0, 32, 0, 32};
+    PUSH(build_pointwise(L, &s, 1, P, Wp(W_CONV_IN), Bp(W_CONV_IN), 128, 1, ws + pl->o_c128, 256, 0, 0, h, w));
+  }
+  {  // feat_in: C128 -> xfeat
+    Src s{ws + pl->o_c128, 128, 0, 128};
+    PUSH(build_pointwise(L, &s, 1, P, Wp(W_FEAT_IN), Bp(W_FEAT_IN), 32, 1, ws + pl->o_xfeat, 64, 0, 0, h, w));
+  }
+  for (int step = 0; step < c.num_steps; ++step) {
+    {  // compress_in(cat(x, last_hidden)); first step: last_hidden = x (SRProjectionModule.py:45-48)
+      Src s[2] = {{ws + pl->o_xfeat, 32, 0, 32}, {ws + (step == 0 ? pl->o_xfeat : pl->o_hidden), 32, 0, 32}};
+      PUSH(build_pointwise(L, s, 2, P, Wp(W_COMPRESS_IN), Bp(W_COMPRESS_IN), 32, 1, ws + pl->o_lr[0], 64, 0, 0, h, w));
+    }
+    for (int i = 0; i < kGroups; ++i) {
+      const void* up_in = ws + pl->o_lr[0];
+      if (i > 0) {  // uptran(cat(lr[0..i]))
+        Src s[6];
+        for (int j = 0; j <= i; ++j) s[j] = Src{ws + pl->o_lr[j], 32, 0, 32};
+        PUSH(build_pointwise(L, s, i + 1, P, Wp(W_UPTRAN0 + i - 1), Bp(W_UPTRAN0 + i - 1), 32, 1, ws + pl->o_u, 64, 0,
+                             0, h, w));
+        up_in = ws + pl->o_u;
+      }
+      PUSH(build_deconv(L, up_in, M, h, w, Wp(W_UP0 + i), Bp(W_UP0 + i), ws + pl->o_hr[i], 0));
+      const void* down_in = ws + pl->o_hr[0];
+      if (i > 0) {  // downtran(cat(hr[0..i])) on the block layout, ring kept at zero
+        Src s[6];
+        for (int j = 0; j <= i; ++j) s[j] = Src{ws + pl->o_hr[j], 32, 0, 32};
+        PUSH(build_pointwise(L, s, i + 1, Rb, Wp(W_DOWNTRAN0 + i - 1), Bp(W_DOWNTRAN0 + i - 1), 32, 1, ws + pl->o_hb,
+                             64, 0, 1, h, w));
+        down_in = ws + pl->o_hb;
+      }
+      PUSH(build_downconv(L, down_in, M, h, w, Wp(W_DOWN0 + i), Bp(W_DOWN0 + i), ws + pl->o_lr[i + 1]));
+    }
+    {  // compress_out(cat(lr[1..6])) -> hidden
+      Src s[6];
+      for (int j = 0; j < 6; ++j) s[j] = Src{ws + pl->o_lr[j + 1], 32, 0, 32};
+      PUSH(build_pointwise(L, s, 6, P, Wp(W_COMPRESS_OUT), Bp(W_COMPRESS_OUT), 32, 1, ws + pl->o_hidden, 64, 0, 0, h,
+                           w));
+    }
+  }
+  PUSH(build_deconv(L, ws + pl->o_hidden, M, h, w, Wp(W_OUT), Bp(W_OUT), ws + pl->o_hb, 1));
+  PUSH(build_conv_out(L, ws + pl->o_hb, M, h, w, Wp(W_CONV_OUT), Bp(W_CONV_OUT),
+                      reinterpret_cast<float*>(ws + pl->o_premix)));
+  pl->conv_out_layer = (int)pl->layers.size() - 1;
+#undef PUSH
+  pl->bound = true;
+  return VSR_OK;
+}
+
+extern "C" int vsr_srfbn_forward(vsr_srfbn_plan* pl, const float* x, float* y, vsr_stream_t stream) {
+  if (!pl || !x || !y) return VSR_ERR_INVALID_ARG;
+  if (!pl->bound) return VSR_ERR_STATE;
+  cudaStream_t st = as_stream(stream);
+  const vsr_srfbn_config& c = pl->cfg;
+  const int64_t P = (int64_t)c.num_maps * c.h * c.w;
+  size_t ev = 0;
+  auto mark = [&]() {
+    if (pl->profile && ev < pl->events.size()) cudaEventRecord(pl->events[ev++], st);
+  };
+  mark();
+  {
+    int64_t blocks = ceil_div64(P, 256);
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    im2col_kernel<<<(int)blocks, 256, 0, st>>>(x, reinterpret_cast<const float*>(pl->dev_w + pl->misc_off),
+                                               reinterpret_cast<uint4*>(pl->ws + pl->o_a0), c.num_maps, c.h, c.w);
+    int rc = after_launch();
+    if (rc) return rc;
+  }
+  pl->layers[pl->conv_out_layer].p.skip_src = x;
+  for (const Layer& L : pl->layers) {
+    mark();
+    int rc = launch_layer(L, st);
+    if (rc) return rc;
+  }
+  mark();
+  {
+    const int64_t n = (int64_t)3 * 16 * c.h * c.w;
+    int64_t blocks = ceil_div64(n, 256);
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    fc_fuse_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const float*>(pl->ws + pl->o_premix),
+                                                reinterpret_cast<const float*>(pl->dev_w + pl->fc_off), y, c.num_maps, n);
+    int rc = after_launch();
+    if (rc) return rc;
+  }
+  mark();
+  return VSR_OK;
+}
+
+extern "C" const char* vsr_srfbn_kernel_class_name(int k) {
+  static const char* names[KC_COUNT] = {"im2col", "conv_in_gemm", "pointwise_lr", "pointwise_hr", "deconv8x8s4",
+                                        "conv8x8s4", "conv_out3x3", "fc_fuse"};
+  return (k >= 0 && k < KC_COUNT) ? names[k] : "?";
+}
+
+extern "C" int vsr_srfbn_profile_enable(vsr_srfbn_plan* pl, int enable) {
+  if (!pl) return VSR_ERR_INVALID_ARG;
+  if (!pl->bound) return VSR_ERR_STATE;
+  pl->profile = enable != 0;
+  if (pl->profile && pl->events.empty()) {
+    pl->events.resize(pl->layers.size() + 3);
+    for (cudaEvent_t& e : pl->events) {
+      cudaError_t r = cudaEventCreate(&e);
+      if (r != cudaSuccess) return cuda_status(r);
+    }
+  }
+  return VSR_OK;
+}
+
+extern "C" int vsr_srfbn_profile_read(vsr_srfbn_plan* pl, double* ms, int32_t* launches, double* flops, double* bytes) {
+  if (!pl || !ms || !launches || !flops || !bytes) return VSR_ERR_INVALID_ARG;
+  if (!pl->bound || pl->events.empty()) return VSR_ERR_STATE;
+  for (int k = 0; k < VSR_SRFBN_KERNEL_CLASSES; ++k) { ms[k] = 0; launches[k] = 0; flops[k] = 0; bytes[k] = 0; }
+  cudaError_t r = cudaEventSynchronize(pl->events.back());
+  if (r != cudaSuccess) return cuda_status(r);
+  const vsr_srfbn_config& c = pl->cfg;
+  const double P = (double)c.num_maps * c.h * c.w;
+  const size_t n = pl->layers.size() + 2;
+  for (size_t i = 0; i < n; ++i) {
+    float t = 0;
+    r = cudaEventElapsedTime(&t, pl->events[i], pl->events[i + 1]);
+    if (r != cudaSuccess) return cuda_status(r);
+    int k;
+    double f, b;
+    if (i == 0) { k = KC_IM2COL; f = 0; b = P * (12.0 + 64.0); }
+    else if (i == n - 1) { k = KC_FC; f = 16.0 * P / c.num_maps * 3 * 2.0 * (32.0 * c.num_maps + 32.0); b = 16.0 * P * 12.0 + 16.0 * P / c.num_maps * 12.0; }
+    else { const Layer& L = pl->layers[i - 1]; k = L.kclass; f = L.flops; b = L.bytes; }
+    ms[k] += t; launches[k] += 1; flops[k] += f; bytes[k] += b;
+  }
+  return VSR_OK;
+}
+
+extern "C" int vsr_srfbn_debug_premix(const vsr_srfbn_plan* pl, float* out_maps, vsr_stream_t stream) {
+  if (!pl || !out_maps) return VSR_ERR_INVALID_ARG;
+  if (!pl->bound) return VSR_ERR_STATE;
+  const vsr_srfbn_config& c = pl->cfg;
+  size_t bytes = (size_t)c.num_maps * 3 * 16 * c.h * c.w * 4;
+  return cuda_status(cudaMemcpyAsync(out_maps, pl->ws + pl->o_premix, bytes, cudaMemcpyDeviceToDevice, as_stream(stream)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// single-layer test hooks: same kernels, same packing, one layer
+// ------------------------------------------------------------------------------------------------
+extern "C" size_t vsr_test_workspace_bytes(int B, int h, int w) {
+  (void)B; (void)h; (void)w;
+  return 512 * 1024;   // packed weights (<= 128 KB) + bias
+}
+
+static int upload(void* dev, const void* host, size_t bytes, cudaStream_t st) {
+  cudaError_t e = cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return cuda_status(e);
+  return cuda_status(cudaStreamSynchronize(st));   // the host staging vector dies with the caller
+}
+
+extern "C" int vsr_test_pointwise(const void* x_bf16, int64_t rows, int K, const float* w_host, const float* b_host,
+                                  float slope, int act, void* y_bf16, void* workspace, size_t workspace_bytes,
+                                  vsr_stream_t stream) {
+  if (!x_bf16 || !w_host || !b_host || !y_bf16 || !workspace || rows <= 0) return VSR_ERR_INVALID_ARG;
+  if (K % 32 || K < 32 || K > 224) return VSR_ERR_UNSUPPORTED;
+  if (workspace_bytes < vsr_test_workspace_bytes(1, 1, 1)) return VSR_ERR_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  std::vector<uint16_t> wp((size_t)32 * K);
+  pack_pointwise(w_host, 32, K, wp.data());
+  float bias[33];
+  memcpy(bias, b_host, 32 * 4);
+  bias[32] = slope;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  int rc = upload(ws, wp.data(), wp.size() * 2, st);
+  if (rc) return rc;
+  rc = upload(ws + 256 * 1024, bias, sizeof(bias), st);
+  if (rc) return rc;
+  Layer L;
+  Src s{x_bf16, K, 0, K};
+  rc = build_pointwise(L, &s, 1, rows, ws, reinterpret_cast<const float*>(ws + 256 * 1024), 32, act, y_bf16, 64, 0, 0,
+                       1, 1);
+  if (rc) return rc;
+  rc = launch_layer(L, st);
+  if (rc) return rc;
+  return cuda_status(cudaStreamSynchronize(st));
+}
+
+extern "C" int vsr_test_deconv(const void* x_bf16, int B, int h, int w, const float* w_host, const float* b_host,
+                               float slope, int block_layout, void* y_bf16, void* workspace,
+                               size_t workspace_bytes, vsr_stream_t stream) {
+  if (!x_bf16 || !w_host || !b_host || !y_bf16 || !workspace || B <= 0 || h <= 0 || w <= 0) return VSR_ERR_INVALID_ARG;
+  if (workspace_bytes < vsr_test_workspace_bytes(B, h, w)) return VSR_ERR_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  std::vector<uint16_t> wp((size_t)512 * 128);
+  pack_deconv(w_host, wp.data());
+  float bias[33];
+  memcpy(bias, b_host, 32 * 4);
+  bias[32] = slope;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  int rc = upload(ws, wp.data(), wp.size() * 2, st);
+  if (rc) return rc;
+  rc = upload(ws + 256 * 1024, bias, sizeof(bias), st);
+  if (rc) return rc;
+  Layer L;
+  rc = build_deconv(L, x_bf16, B, h, w, ws, reinterpret_cast<const float*>(ws + 256 * 1024), y_bf16, block_layout ? 0 : 1);
+  if (rc) return rc;
+  rc = launch_layer(L, st);
+  if (rc) return rc;
+  return cuda_status(cudaStreamSynchronize(st));
+}
+
+// x is passed already in the HR block layout (B,h+1,w+1,16,32); tests build it with torch
+// (pad by 2, unfold 4x4), which keeps the hook allocation-free.
+extern "C" int vsr_test_downconv(const void* x_bf16, int B, int h, int w, const float* w_host, const float* b_host,
+                                 float slope, void* y_bf16, void* workspace, size_t workspace_bytes,
+                                 vsr_stream_t stream) {
+  if (!x_bf16 || !w_host || !b_host || !y_bf16 || !workspace || B <= 0 || h <= 0 || w <= 0) return VSR_ERR_INVALID_ARG;
+  if (workspace_bytes < vsr_test_workspace_bytes(B, h, w)) return VSR_ERR_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  std::vector<uint16_t> wp((size_t)32 * 2048);
+  pack_downconv(w_host, wp.data());
+  float bias[33];
+  memcpy(bias, b_host, 32 * 4);
+  bias[32] = slope;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  int rc = upload(ws, wp.data(), wp.size() * 2, st);
+  if (rc) return rc;
+  rc = upload(ws + 256 * 1024, bias, sizeof(bias), st);
+  if (rc) return rc;
+  Layer L;
+  rc = build_downconv(L, x_bf16, B, h, w, ws, reinterpret_cast<const float*>(ws + 256 * 1024), y_bf16);
+  if (rc) return rc;
+  rc = launch_layer(L, st);
+  if (rc) return rc;
+  return cuda_status(cudaStreamSynchronize(st));
+}

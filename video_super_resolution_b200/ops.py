@@ -164,3 +164,46 @@ def mask_fill(image: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
         _lib.check(_lib.lib().vsr_mask_fill(image.data_ptr(), mask.data_ptr(), out.data_ptr(), C, h, w, _stream()),
                    "mask_fill")
     return out
+
+
+def assemble_stack(warped: torch.Tensor, centre: torch.Tensor, proj: torch.Tensor, resid: torch.Tensor,
+                   depth: torch.Tensor, estimate: torch.Tensor | None, centre_idx: int,
+                   out: torch.Tensor | None = None) -> torch.Tensor:
+    """One-pass assembly of the (3T-1,3,h,w) map stack (video_super_resolution.py:33-40).
+    warped (T-1,h,w,3), centre (h,w,3), proj (T-1,h,w,2), resid/depth (T-1,h,w), estimate (3,h,w)|None."""
+    for t, n in ((warped, "warped"), (centre, "centre"), (proj, "proj"), (resid, "resid"), (depth, "depth")):
+        _req(t, torch.float32, n)
+    Tm1, h, w, _ = warped.shape
+    T = Tm1 + 1
+    if tuple(centre.shape) != (h, w, 3) or tuple(proj.shape) != (Tm1, h, w, 2) or \
+            tuple(resid.shape) != (Tm1, h, w) or tuple(depth.shape) != (Tm1, h, w):
+        raise ValueError("assemble_stack: inconsistent shapes")
+    if estimate is not None:
+        _req(estimate, torch.float32, "estimate")
+        if tuple(estimate.shape) != (3, h, w):
+            raise ValueError("assemble_stack: estimate must be (3,h,w)")
+    if out is None:
+        out = torch.empty((3 * T - 1, 3, h, w), dtype=torch.float32, device=warped.device)
+    with torch.cuda.device(warped.device):
+        _lib.check(_lib.lib().vsr_assemble_stack(warped.data_ptr(), centre.data_ptr(), proj.data_ptr(), resid.data_ptr(),
+                                                 depth.data_ptr(), estimate.data_ptr() if estimate is not None else None,
+                                                 out.data_ptr(), T, int(centre_idx), h, w, _stream()), "assemble_stack")
+    return out
+
+
+def estimate_slot(hr: torch.Tensor, mask: torch.Tensor | None, slot: torch.Tensor, scale: int = 4) -> torch.Tensor:
+    """slot (3,h,w) <- nearest-downsized hr (3,h*scale,w*scale) with masked pixels zeroed
+    (video_super_resolution.py:44,58-60).  `slot` is written in place (a view of the stack)."""
+    _req(hr, torch.float32, "hr")
+    _req(slot, torch.float32, "slot")
+    _, h, w = slot.shape
+    if tuple(hr.shape) != (3, h * scale, w * scale):
+        raise ValueError("estimate_slot: hr must be (3,h*scale,w*scale)")
+    if mask is not None:
+        _req(mask, torch.uint8, "mask")
+        if tuple(mask.shape) != (h, w):
+            raise ValueError("estimate_slot: mask must be (h,w)")
+    with torch.cuda.device(hr.device):
+        _lib.check(_lib.lib().vsr_estimate_slot(hr.data_ptr(), mask.data_ptr() if mask is not None else None,
+                                                slot.data_ptr(), h, w, int(scale), _stream()), "estimate_slot")
+    return slot

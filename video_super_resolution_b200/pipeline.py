@@ -1,0 +1,92 @@
+"""The per-frame warp-and-fuse hot path on one GPU, and its sharding over frame windows.
+
+`WarpFusePipeline.step` is the sequence VSR.forward runs per output frame
+(network/video_super_resolution.py:23-69) with the learned estimators replaced by given geometry
+(flow, inverse depth, segmentation logits -- SURVEY.md 8: FlowNet2 / MegaDepth / OSVOS bodies are
+out of scope), generalised from the reference's 3-frame window to T frames (M = 3T-1 maps):
+
+  a1  flow projection            ops.project_flow          (FlowProjectionModule)
+  a2  depth-aware projection     ops.project_depth_flow    (DepthProjectionModule)
+  a3  bilinear warp of the T-1 neighbour frames along the projected flow, a4 fused residual norm
+  a5  mask threshold + nearest label warp                   (VOSProjectionModule)
+  a7  one-pass stack assembly    ops.assemble_stack
+  a6  fusion convs, pass 1       SRProjectionModule         (video_super_resolution.py:41)
+  a7  downsized + masked estimate into the stack's last slot (:43-44,:57-62)
+  a6  fusion convs, pass 2       SRProjectionModule         (:64)
+
+Sharding: windows are independent once the recurrence is reset at chunk starts
+(main.py:196), so rank r takes a contiguous chunk of windows; no collective on the hot path.
+`gather_frames` is the one collective: an all-gather of the u8-quantised output frames.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .my_packages.SRProjection.SRProjectionModule import SRProjectionModule
+
+
+def shard_windows(num_windows: int, world_size: int, rank: int) -> range:
+    """Contiguous chunk of window indices for `rank` ([r*ceil(N/G), (r+1)*ceil(N/G)))."""
+    per = -(-num_windows // world_size)
+    return range(min(rank * per, num_windows), min((rank + 1) * per, num_windows))
+
+
+class WarpFusePipeline:
+    def __init__(self, T: int, h: int, w: int, sr: SRProjectionModule | None = None, scale: int = 4,
+                 device="cuda:0", run_fusion: bool = True):
+        if T < 2:
+            raise ValueError("window must hold at least 2 frames")
+        self.T, self.h, self.w, self.scale = T, h, w, scale
+        self.M = 3 * T - 1
+        self.centre = T // 2
+        self.device = torch.device(device)
+        self.run_fusion = run_fusion
+        self.sr = sr if sr is not None else SRProjectionModule(num_maps=self.M)
+        if self.sr.num_maps != self.M:
+            raise ValueError(f"SRProjectionModule.num_maps={self.sr.num_maps}, window needs {self.M}")
+        self.stack = torch.empty((self.M, 3, h, w), dtype=torch.float32, device=self.device)
+        self._neigh = [t for t in range(T) if t != self.centre]
+
+    def project_and_warp(self, frames, flows, inv_depth, logits_a, logits_b, estimate=None):
+        """a1-a5 + a7: fills self.stack; returns the intermediate results (for tests)."""
+        T, c = self.T, self.centre
+        proj_f, _, cnt_f, hole_f = ops.project_flow(flows)
+        proj_d, wsum, cnt_d, hole_d = ops.project_depth_flow(flows, inv_depth)
+        neigh = frames[self._neigh].contiguous()
+        ref = frames[c].unsqueeze(0).expand(T - 1, -1, -1, -1).contiguous()
+        warped, resid = ops.warp(neigh, proj_d, True, ref=ref)
+        mask = ops.vos_threshold(logits_a, logits_b)
+        mask_w = ops.warp_labels(mask.unsqueeze(0), proj_d[min(c, T - 2)].unsqueeze(0))[0]
+        ops.assemble_stack(warped, frames[c], proj_f, resid, wsum, estimate, c, out=self.stack)
+        return {"proj_flow": proj_f, "count_flow": cnt_f, "hole_flow": hole_f, "proj_depth": proj_d, "wsum": wsum,
+                "count_depth": cnt_d, "hole_depth": hole_d, "warped": warped, "resid": resid, "mask": mask,
+                "mask_warped": mask_w}
+
+    def step(self, frames, flows, inv_depth, logits_a, logits_b, estimate=None):
+        """frames (T,h,w,3) 0..255, flows (T-1,h,w,2), inv_depth (T-1,h,w), logits (h,w) x2,
+        estimate (3,h,w)|None -> SR frame (1,3,s*h,s*w) fp32."""
+        r = self.project_and_warp(frames, flows, inv_depth, logits_a, logits_b, estimate)
+        if not self.run_fusion:
+            return self.stack
+        out1 = self.sr(self.stack)                                             # pass 1
+        ops.estimate_slot(out1[0], r["mask_warped"], self.stack[self.M - 1], self.scale)
+        return self.sr(self.stack)                                             # pass 2 (fuse)
+
+
+def quantise_u8(frame: torch.Tensor) -> torch.Tensor:
+    """(1,3,H,W) fp32 0..255 -> (H,W,3) u8, the format the reference's loader reads (utils/video_utils.py:23)."""
+    return frame[0].clamp(0, 255).round().to(torch.uint8).permute(1, 2, 0).contiguous()
+
+
+def gather_frames(local_frames: torch.Tensor, group=None) -> torch.Tensor:
+    """All-gather of each rank's (n,H,W,3) u8 output frames into (world*n,H,W,3), rank-major = window
+    order under shard_windows.  The only collective of the pipeline (NCCL over NVLink on GPUs, gloo in
+    the CPU tests)."""
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local_frames
+    world = dist.get_world_size(group)
+    out = torch.empty((world,) + tuple(local_frames.shape), dtype=local_frames.dtype, device=local_frames.device)
+    dist.all_gather_into_tensor(out, local_frames.contiguous(), group=group)
+    return out.flatten(0, 1)
