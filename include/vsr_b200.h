@@ -200,7 +200,7 @@ int vsr_srfbn_forward(vsr_srfbn_plan* plan, const float* x, float* y, vsr_stream
  * forward and returns, per kernel class, the summed device time (ms), the number of launches, and
  * the layers' specified 2*MAC FLOPs and compulsory bytes (inputs + outputs of each launch, once).
  * Arrays have VSR_SRFBN_KERNEL_CLASSES entries, in the order of vsr_srfbn_kernel_class_name(). */
-#define VSR_SRFBN_KERNEL_CLASSES 8
+#define VSR_SRFBN_KERNEL_CLASSES 10
 const char* vsr_srfbn_kernel_class_name(int k);
 int vsr_srfbn_profile_enable(vsr_srfbn_plan* plan, int enable);
 int vsr_srfbn_profile_read(vsr_srfbn_plan* plan, double* ms, int32_t* launches, double* flops, double* bytes);
@@ -228,6 +228,15 @@ int vsr_test_downconv(const void* x_bf16, int B, int h, int w, const float* w_ho
                       const float* b_host, float slope, void* y_bf16,
                       void* workspace, size_t workspace_bytes, vsr_stream_t stream);
 size_t vsr_test_workspace_bytes(int B, int h, int w);
+/*   fused_down: the kernel the plan uses for the HR half of a feedback group
+ *              (SRProjectionModule.py:70-80): PReLU(Conv1x1 over nsrc concatenated HR maps) ->
+ *              Conv2d(32,32,8,4,2) -> PReLU.  hr: (nsrc,B,h+1,w+1,16,32) bf16 block layout; nsrc==1
+ *              skips the 1x1 (group 0).  wt (32,32*nsrc), wd (32,32,8,8) fp32 host.  y (B,h,w,32) bf16.
+ *              workspace: vsr_test_workspace_bytes + B*h*w*128 bytes. */
+int vsr_test_fused_down(const void* hr_bf16, int nsrc, int B, int h, int w, const float* wt_host,
+                        const float* bt_host, float slope_t, const float* wd_host, const float* bd_host,
+                        float slope_d, void* y_bf16, void* workspace, size_t workspace_bytes,
+                        vsr_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -69,3 +69,24 @@ def downconv(xb_bf16, w, b, slope):
                                             y.data_ptr(), ws.data_ptr(), ws.numel(),
                                             torch.cuda.current_stream().cuda_stream), "test_downconv")
     return y
+
+
+def fused_down(hr_bf16, wt, bt, slope_t, wd, bd, slope_d):
+    """hr (nsrc,B,h+1,w+1,16,32) bf16 block layout; wt (32,32*nsrc)|None; wd (32,32,8,8) -> (B,h,w,32) bf16."""
+    nsrc, B, hb, wb = hr_bf16.shape[:4]
+    h, wd_ = hb - 1, wb - 1
+    dev = hr_bf16.device
+    y = torch.full((B, h, wd_, 32), float("nan"), dtype=torch.bfloat16, device=dev)
+    n = int(_lib.lib().vsr_test_workspace_bytes(B, h, wd_)) + B * h * wd_ * 128
+    ws = torch.empty(n, dtype=torch.uint8, device=dev)
+    wd = wd.contiguous().float()
+    bd = bd.contiguous().float()
+    if nsrc > 1:
+        wt = wt.contiguous().float()
+        bt = bt.contiguous().float()
+    _lib.check(_lib.lib().vsr_test_fused_down(hr_bf16.data_ptr(), nsrc, B, h, wd_,
+                                              _fp(wt) if nsrc > 1 else None, _fp(bt) if nsrc > 1 else None,
+                                              float(slope_t), _fp(wd), _fp(bd), float(slope_d), y.data_ptr(),
+                                              ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream),
+               "test_fused_down")
+    return y

@@ -77,6 +77,26 @@ def test_downconv_layer(B, h, w):
     _close(got, want, f"downconv B={B} {h}x{w}")
 
 
+@pytest.mark.parametrize("nsrc,B,h,w", [(1, 1, 8, 16), (2, 2, 5, 7), (3, 1, 19, 33), (6, 1, 9, 17)])
+def test_fused_downtran_downconv(nsrc, B, h, w):
+    """The kernel the plan runs for the HR half of a feedback group (SRProjectionModule.py:70-80)."""
+    g = torch.Generator().manual_seed(nsrc * 1000 + h * 10 + w)
+    hr = _bf(torch.randn((nsrc, B, 4 * h, 4 * w, 32), generator=g))
+    wd = _bf(torch.randn((32, 32, 8, 8), generator=g) / 45).float()
+    bd = torch.randn(32, generator=g) * 0.1
+    wt = _bf(torch.randn((32, 32 * nsrc), generator=g) / math.sqrt(32 * nsrc)).float()
+    bt = torch.randn(32, generator=g) * 0.1
+    hrb = torch.stack([hk.to_block(hr[j]) for j in range(nsrc)])
+    got = hk.fused_down(hrb.to(DEV), wt, bt, 0.3, wd, bd, 0.15)
+    x = hr.float().permute(1, 4, 0, 2, 3)                                  # (B, c, nsrc, H, W)
+    x = x.permute(0, 2, 1, 3, 4).reshape(B, nsrc * 32, 4 * h, 4 * w)       # cat over sources along channels
+    if nsrc > 1:
+        x = F.prelu(F.conv2d(x, wt.view(32, 32 * nsrc, 1, 1), bt), torch.tensor([0.3]))
+        x = _bf(x).float()                                                 # the kernel rounds H to BF16 on chip
+    want = F.prelu(F.conv2d(x, wd, bd, stride=4, padding=2), torch.tensor([0.15])).permute(0, 2, 3, 1)
+    _close(got, want, f"fused_down nsrc={nsrc} B={B} {h}x{w}")
+
+
 def _psnr(a, b):
     mse = ((a - b) ** 2).mean().item()
     return 10 * math.log10(255.0 ** 2 / max(mse, 1e-20))

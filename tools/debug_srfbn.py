@@ -9,7 +9,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-CASES = ["pw:128:32", "pw:1000:64", "pw:4173:192", "deconv:1:8:16:0", "deconv:2:5:7:0", "deconv:1:8:16:1",
+CASES = ["fused:1:1:8:16", "fused:2:1:8:16", "fused:3:2:5:7", "fused:6:1:19:33", "deconv:1:19:33:1", "pw:128:32", "pw:1000:64", "pw:4173:192", "deconv:1:8:16:0", "deconv:2:5:7:0", "deconv:1:8:16:1",
          "down:1:8:16", "down:2:5:7", "full:8:16:16:3", "full:20:24:40:3"]
 
 
@@ -63,6 +63,22 @@ def run_case(case):
         want = F.prelu(F.conv2d(x.float().permute(0, 3, 1, 2), wt, b, stride=4, padding=2),
                        torch.tensor([0.15])).permute(0, 2, 3, 1)
         stats(case, got, want)
+    elif parts[0] == "fused":
+        nsrc, B, h, w = map(int, parts[1:])
+        hr = torch.randn((nsrc, B, 4 * h, 4 * w, 32), generator=g).bfloat16()
+        wd = (torch.randn((32, 32, 8, 8), generator=g) / 45).bfloat16().float()
+        bd = torch.randn(32, generator=g) * 0.1
+        wt = (torch.randn((32, 32 * nsrc), generator=g) / math.sqrt(32 * nsrc)).bfloat16().float()
+        bt = torch.randn(32, generator=g) * 0.1
+        hrb = torch.stack([hk.to_block(hr[j]) for j in range(nsrc)])
+        got = hk.fused_down(hrb.to(dev), wt, bt, 0.3, wd, bd, 0.15)
+        x = hr.float().permute(1, 0, 4, 2, 3).reshape(B, nsrc * 32, 4 * h, 4 * w)
+        if nsrc > 1:
+            x = F.prelu(F.conv2d(x, wt.view(32, 32 * nsrc, 1, 1), bt), torch.tensor([0.3])).bfloat16().float()
+        want = F.prelu(F.conv2d(x, wd, bd, stride=4, padding=2), torch.tensor([0.15])).permute(0, 2, 3, 1)
+        err = stats(case, got, want)
+        print("  err by row:", [round(err[0, y].max().item(), 3) for y in range(min(h, 12))])
+        print("  err by col:", [round(err[0, :, xx].max().item(), 3) for xx in range(min(w, 20))])
     elif parts[0] == "full":
         M, h, w, steps = map(int, parts[1:])
         from oracle import srfbn_oracle as so

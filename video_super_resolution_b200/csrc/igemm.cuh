@@ -211,11 +211,13 @@ __host__ __device__ constexpr int b_chunk_bytes() { return BN * CK * 2; }
 template <int CK>
 __host__ __device__ constexpr int a_stage_bytes() { return kTileM * CK * 2; }
 
+constexpr int kDeconvStageBytes = 4 * 32 * 512;   // EPI_DECONV: 4 epilogue warps x 32 blocks x 512 B
+
 template <int CK, int BN>
-inline size_t igemm_smem_bytes(int num_chunks, int num_stages) {
+inline size_t igemm_smem_bytes(int num_chunks, int num_stages, int extra = 0) {
   size_t b = (size_t)num_chunks * b_chunk_bytes<CK, BN>();
   b = (b + 1023) / 1024 * 1024;
-  return 1024 /*align slack*/ + b + (size_t)num_stages * a_stage_bytes<CK>() + 1024 /*barriers + bias*/ + 2048;
+  return 1024 /*align slack*/ + b + (size_t)num_stages * a_stage_bytes<CK>() + 1024 /*barriers + bias*/ + 2048 + extra;
 }
 
 template <int MODE, int CK, int BN>
@@ -241,6 +243,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
   uint64_t* b_full = tmem_empty + 2;                               // [1]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_full + 1);
   float* s_bias = reinterpret_cast<float*>(tail + 512);            // up to 384 floats
+  uint8_t* s_stage = tail + 2048;                                  // EPI_DECONV store staging (64 KB)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -381,41 +384,78 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
         const bool valid = (Y <= p.lr_h) && (X <= p.lr_w);
         const int H = 4 * p.lr_h, W = 4 * p.lr_w;
         const float slope = s_bias[p.bias_n];
+        if (p.deconv_nhwc) {
 #pragma unroll 1
-        for (int cg = 0; cg < 8; ++cg) {
-          uint32_t v[32];
-          tmem_ld32(taddr + cg * 32, v);
-          tmem_ld_wait();
-          if (cg == 7) {
-            tc_fence_before();
-            mbar_arrive(&tmem_empty[as]);
+          for (int cg = 0; cg < 8; ++cg) {
+            uint32_t v[32];
+            tmem_ld32(taddr + cg * 32, v);
+            tmem_ld_wait();
+            if (cg == 7) {
+              tc_fence_before();
+              mbar_arrive(&tmem_empty[as]);
+            }
+            const int s16 = t.n_tile * 8 + cg;
+            const int ry = s16 >> 2, rx = s16 & 3;
+            const int Yt = 4 * Y + ry - 2, Xt = 4 * X + rx - 2;       // true HR coordinates
+            if (valid && (Yt >= 0) && (Yt < H) && (Xt >= 0) && (Xt < W)) {
+              uint32_t o[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                float a = prelu(__uint_as_float(v[2 * j]) + s_bias[2 * j], slope, p.act);
+                float b = prelu(__uint_as_float(v[2 * j + 1]) + s_bias[2 * j + 1], slope, p.act);
+                o[j] = pack_bf16(a, b);
+              }
+              uint4* d4 = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) + (((int64_t)t.b * H + Yt) * W + Xt) * 64);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) d4[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            }
           }
-          const int s16 = t.n_tile * 8 + cg;
-          const int ry = s16 >> 2, rx = s16 & 3;
-          const int Yt = 4 * Y + ry - 2, Xt = 4 * X + rx - 2;       // true HR coordinates
-          const bool inside = (Yt >= 0) && (Yt < H) && (Xt >= 0) && (Xt < W);
-          uint8_t* dst;
-          bool store;
-          if (p.deconv_nhwc) {
-            store = valid && inside;
-            dst = reinterpret_cast<uint8_t*>(p.out) + (((int64_t)t.b * H + Yt) * W + Xt) * 64;
-          } else {
-            store = valid;
-            dst = reinterpret_cast<uint8_t*>(p.out) +
-                  ((((int64_t)t.b * (p.lr_h + 1) + Y) * (p.lr_w + 1) + X) * 16 + s16) * 64;
-          }
-          if (store) {
+        } else {
+          // Block layout: this N tile owns 512 contiguous bytes (8 sub-positions x 32 ch) of every
+          // block row.  Stage the warp's 32 rows in shared memory (16-byte pieces XOR-swizzled by the
+          // row so that both phases are bank-conflict free), then write each row with ONE fully
+          // coalesced 512-byte warp store.
+          uint8_t* stg = s_stage + (warp - 2) * (32 * 512);
+#pragma unroll 1
+          for (int cg = 0; cg < 8; ++cg) {
+            uint32_t v[32];
+            tmem_ld32(taddr + cg * 32, v);
+            tmem_ld_wait();
+            if (cg == 7) {
+              tc_fence_before();
+              mbar_arrive(&tmem_empty[as]);
+            }
+            const int s16 = t.n_tile * 8 + cg;
+            const int ry = s16 >> 2, rx = s16 & 3;
+            const int Yt = 4 * Y + ry - 2, Xt = 4 * X + rx - 2;
+            const bool inside = (Yt >= 0) && (Yt < H) && (Xt >= 0) && (Xt < W);   // else: zero ring
             uint32_t o[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               float a = prelu(__uint_as_float(v[2 * j]) + s_bias[2 * j], slope, p.act);
               float b = prelu(__uint_as_float(v[2 * j + 1]) + s_bias[2 * j + 1], slope, p.act);
-              o[j] = inside ? pack_bf16(a, b) : 0u;                 // padding ring of the block layout
+              o[j] = inside ? pack_bf16(a, b) : 0u;
             }
-            uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) d4[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            for (int j = 0; j < 4; ++j) {
+              const int piece = cg * 4 + j;
+              *reinterpret_cast<uint4*>(stg + lane * 512 + ((piece ^ lane) & 31) * 16) =
+                  make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            }
           }
+          __syncwarp();
+#pragma unroll 4
+          for (int r = 0; r < 32; ++r) {
+            const int R = q * 32 + r;
+            const int Yr = t.y0 + R / p.tile_w, Xr = t.x0 + R % p.tile_w;
+            if (Yr <= p.lr_h && Xr <= p.lr_w) {
+              const uint4 val = *reinterpret_cast<const uint4*>(stg + r * 512 + ((lane ^ r) & 31) * 16);
+              uint8_t* dst = reinterpret_cast<uint8_t*>(p.out) +
+                             ((((int64_t)t.b * (p.lr_h + 1) + Yr) * (p.lr_w + 1) + Xr) * 16 + t.n_tile * 8) * 64;
+              *reinterpret_cast<uint4*>(dst + lane * 16) = val;
+            }
+          }
+          __syncwarp();
         }
       } else {  // EPI_CONV_OUT
         const int Y = t.y0 + row / p.tile_w, X = t.x0 + row % p.tile_w;

@@ -24,7 +24,7 @@
 //
 // The `out` deconv and `conv_out` are evaluated for the last feedback step only: the reference
 // keeps `outs[-1:]` (SRProjectionModule.py:145), the earlier steps' images are dead values.
-#include "igemm.cuh"
+#include "fused_down.cuh"
 
 #include <string.h>
 
@@ -88,15 +88,20 @@ int make_w_map(CUtensorMap* m, const void* base, int64_t K, int64_t N, int ck, i
 // ------------------------------------------------------------------------------------------------
 // kernel variants
 // ------------------------------------------------------------------------------------------------
-enum Variant : int { V_PW32 = 0, V_PW128, V_DECONV, V_DOWN, V_CONVOUT, V_COUNT };
+enum Variant : int { V_PW32 = 0, V_PW128, V_DECONV, V_DOWN, V_CONVOUT, V_FUSED_TRAN, V_FUSED_PLAIN, V_FINALIZE, V_COUNT };
 
 // kernel classes for the per-launch accounting bench.py reads (vsr_srfbn_profile_*)
-static_assert(VSR_SRFBN_KERNEL_CLASSES == 8, "header constant");
-enum KClass : int { KC_IM2COL = 0, KC_CONV_IN, KC_PW_LR, KC_PW_HR, KC_DECONV, KC_DOWNCONV, KC_CONV_OUT, KC_FC, KC_COUNT };
+static_assert(VSR_SRFBN_KERNEL_CLASSES == 10, "header constant");
+enum KClass : int { KC_IM2COL = 0, KC_CONV_IN, KC_PW_LR, KC_PW_HR, KC_DECONV, KC_DOWNCONV, KC_CONV_OUT, KC_FC, KC_FUSED_DOWN, KC_FINALIZE, KC_COUNT };
 
 struct Layer {
   int variant;
   IgemmParams p;
+  FusedDownParams f;     // V_FUSED_*
+  float* fin_acc;        // V_FINALIZE
+  const float* fin_bias;
+  void* fin_out;
+  int64_t fin_n8;
   int grid;
   size_t smem;
   int kclass;
@@ -117,8 +122,30 @@ int launch_variant(const Layer& L, cudaStream_t st) {
   return after_launch();
 }
 
+template <bool HAS_TRAN>
+int launch_fused(const Layer& L, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(fused_down_kernel<HAS_TRAN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         227 * 1024);
+    if (e != cudaSuccess) return cuda_status(e);
+    attr_set = true;
+  }
+  fused_down_kernel<HAS_TRAN><<<L.grid, kFusedThreads, L.smem, st>>>(L.f);
+  return after_launch();
+}
+
 int launch_layer(const Layer& L, cudaStream_t st) {
   switch (L.variant) {
+    case V_FUSED_TRAN: return launch_fused<true>(L, st);
+    case V_FUSED_PLAIN: return launch_fused<false>(L, st);
+    case V_FINALIZE: {
+      int64_t blocks = ceil_div64(L.fin_n8, 256);
+      if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+      finalize_lr_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<float4*>(L.fin_acc), L.fin_bias,
+                                                      reinterpret_cast<uint4*>(L.fin_out), L.fin_n8);
+      return after_launch();
+    }
     case V_PW32: return launch_variant<EPI_ROWS, 32, 32>(L, st);
     case V_PW128: return launch_variant<EPI_ROWS, 32, 128>(L, st);
     case V_DECONV: return launch_variant<EPI_DECONV, 32, 256>(L, st);
@@ -132,7 +159,7 @@ size_t variant_smem(int variant, int chunks, int stages) {
   switch (variant) {
     case V_PW32: return igemm_smem_bytes<32, 32>(chunks, stages);
     case V_PW128: return igemm_smem_bytes<32, 128>(chunks, stages);
-    case V_DECONV: return igemm_smem_bytes<32, 256>(chunks, stages);
+    case V_DECONV: return igemm_smem_bytes<32, 256>(chunks, stages, kDeconvStageBytes);
     case V_DOWN: return igemm_smem_bytes<64, 32>(chunks, stages);
     default: return igemm_smem_bytes<32, 16>(chunks, stages);
   }
@@ -291,6 +318,75 @@ int build_downconv(Layer& L, const void* xb, int B, int h, int w, const void* w_
   return VSR_OK;
 }
 
+// HR block layout viewed as (c, s, Xb, Yb, map): one sub-position of a 16x8 block tile per box
+int make_hr5d_map(CUtensorMap* m, const void* base, int h, int w, int B) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return VSR_ERR_STATE;
+  cuuint64_t dims[5] = {32, 16, (cuuint64_t)(w + 1), (cuuint64_t)(h + 1), (cuuint64_t)B};
+  cuuint64_t strides[4] = {64, 1024, (cuuint64_t)1024 * (w + 1), (cuuint64_t)1024 * (w + 1) * (h + 1)};
+  cuuint32_t box[5] = {32, 1, 16, 8, 1};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? VSR_OK : VSR_ERR_CUDA_BASE + 999;
+}
+
+// downtran (1x1 over hr[0..nsrc-1], nsrc >= 2) + PReLU + Conv2d(32,32,8,4,2) pre-activation sums -> acc;
+// nsrc == 1: the conv alone on hr[0].  hr[j]: HR block layout (B,h+1,w+1,16,32); acc (B,h,w,32) fp32.
+int build_fused_down(Layer& L, const void* const* hr, int nsrc, int B, int h, int w, const void* wt_dev,
+                     const float* tran_bias_dev, const void* wd_dev, float* acc) {
+  memset(&L, 0, sizeof(L));
+  const bool tran = nsrc > 1;
+  L.variant = tran ? V_FUSED_TRAN : V_FUSED_PLAIN;
+  FusedDownParams& f = L.f;
+  if (nsrc < 1 || nsrc > kMaxSources) return VSR_ERR_UNSUPPORTED;
+  int rc;
+  if (tran) {
+    for (int j = 0; j < nsrc; ++j) {
+      rc = make_hr5d_map(&f.hr_maps[j], hr[j], h, w, B);
+      if (rc) return rc;
+    }
+    rc = make_w_map(&f.wt_map, wt_dev, 32 * nsrc, 32, 32, 32);
+    if (rc) return rc;
+  } else {
+    rc = make_act_map(&f.h0_map, hr[0], 512, w + 1, h + 1, B, 64, 16, 8);
+    if (rc) return rc;
+  }
+  rc = make_w_map(&f.wd_map, wd_dev, 512, 128, 64, 128);
+  if (rc) return rc;
+  f.nsrc = nsrc;
+  f.num_stages = tran ? 6 : 2;
+  f.tiles_x = ceil_div(w + 1, 16);
+  f.tiles_y = ceil_div(h + 1, 8);
+  f.batch = B;
+  f.lr_h = h;
+  f.lr_w = w;
+  f.tran_bias = tran_bias_dev;
+  f.acc = acc;
+  L.smem = tran ? fused_down_smem_bytes<true>(nsrc, f.num_stages) : fused_down_smem_bytes<false>(nsrc, f.num_stages);
+  int64_t total = (int64_t)f.tiles_x * f.tiles_y * B;
+  L.grid = (int)(total < kNumSMs ? total : kNumSMs);
+  const double lrpx = (double)B * h * w;
+  L.kclass = KC_FUSED_DOWN;
+  L.flops = lrpx * 131072.0 + (tran ? lrpx * 16.0 * 2.0 * 32.0 * nsrc * 32.0 : 0.0);
+  L.bytes = lrpx * 64.0 * (16.0 * nsrc) + lrpx * 128.0;
+  return VSR_OK;
+}
+
+int build_finalize(Layer& L, float* acc, const float* bias_dev, void* out, int64_t pixels) {
+  memset(&L, 0, sizeof(L));
+  L.variant = V_FINALIZE;
+  L.fin_acc = acc;
+  L.fin_bias = bias_dev;
+  L.fin_out = out;
+  L.fin_n8 = pixels * 4;
+  L.kclass = KC_FINALIZE;
+  L.flops = 0;
+  L.bytes = (double)pixels * (128.0 + 128.0 + 64.0);
+  return VSR_OK;
+}
+
 // conv_out 3x3 p1 32->3 at HR + bilinear skip + mean shifts, fp32 planar output (B,3,4h,4w)
 int build_conv_out(Layer& L, const void* xhr, int B, int h, int w, const void* w_dev, const float* bias_dev,
                    float* out) {
@@ -373,6 +469,17 @@ void pack_downconv(const float* w, uint16_t* dst) {
         for (int c = 0; c < 32; ++c) {
           int ky = 4 * (t >> 1) + (s >> 2), kx = 4 * (t & 1) + (s & 3);
           dst[o * 2048 + (t * 16 + s) * 32 + c] = f2bf(w[((o * 32 + c) * 8 + ky) * 8 + kx]);
+        }
+}
+// Conv2d weight (o, c, 8, 8) s4 p2 for the fused kernel's output-shift form -> [128 = t*32+o][512 = s*32+c],
+// tap t = dy*2+dx (block offset of the LR pixel's window), ky = 4dy+ry, kx = 4dx+rx, s = ry*4+rx
+void pack_downconv_fused(const float* w, uint16_t* dst) {
+  for (int t = 0; t < 4; ++t)
+    for (int o = 0; o < 32; ++o)
+      for (int s = 0; s < 16; ++s)
+        for (int c = 0; c < 32; ++c) {
+          int ky = 4 * (t >> 1) + (s >> 2), kx = 4 * (t & 1) + (s & 3);
+          dst[(t * 32 + o) * 512 + s * 32 + c] = f2bf(w[((o * 32 + c) * 8 + ky) * 8 + kx]);
         }
 }
 // conv_out (3,32,3,3) -> [16][288], k = (ky*3+kx)*32 + c, rows 3..15 zero
@@ -474,7 +581,7 @@ struct vsr_srfbn_plan {
   size_t misc_off;        // fp32: sub_mean bias (3)
   size_t weight_bytes;
   // workspace offsets
-  size_t o_a0, o_c128, o_xfeat, o_hidden, o_lr[7], o_u, o_hr[6], o_hb, o_premix, ws_bytes;
+  size_t o_a0, o_c128, o_xfeat, o_hidden, o_lr[7], o_u, o_hr[6], o_hb, o_acc, o_premix, ws_bytes;
   bool bound;
   const uint8_t* dev_w;
   uint8_t* ws;
@@ -500,7 +607,7 @@ static void layout_weights(vsr_srfbn_plan* pl) {
   for (int i = 0; i < 5; ++i) put(W_UPTRAN0 + i, 32, 32 * (i + 2), 33);
   for (int i = 0; i < 6; ++i) put(W_UP0 + i, 512, 128, 33);
   for (int i = 0; i < 5; ++i) put(W_DOWNTRAN0 + i, 32, 32 * (i + 2), 33);
-  for (int i = 0; i < 6; ++i) put(W_DOWN0 + i, 32, 2048, 33);
+  for (int i = 0; i < 6; ++i) put(W_DOWN0 + i, 128, 512, 33);
   put(W_COMPRESS_OUT, 32, 192, 33);
   put(W_OUT, 512, 128, 33);
   put(W_CONV_OUT, 16, 288, 16 + 7);
@@ -528,7 +635,8 @@ static void layout_workspace(vsr_srfbn_plan* pl) {
   for (int i = 0; i < 7; ++i) pl->o_lr[i] = put(P * 64);
   pl->o_u = put(P * 64);
   for (int i = 0; i < 6; ++i) pl->o_hr[i] = put(Rb * 64);
-  pl->o_hb = put(Rb * 64);   // downtran output; reused for the plain-NHWC `out` deconv result (16P*64 <= Rb*64)
+  pl->o_hb = put(P * 16 * 64);   // plain-NHWC result of the `out` deconv
+  pl->o_acc = put(P * 128);
   pl->o_premix = put(P * 16 * 3 * 4);
   pl->ws_bytes = off;
 }
@@ -595,7 +703,7 @@ extern "C" int vsr_srfbn_pack_weights(const vsr_srfbn_plan* pl, const vsr_srfbn_
   for (int i = 0; i < 6; ++i) {
     pack_deconv(w->up_w[i], W(W_UP0 + i));
     ok = ok && bias(W_UP0 + i, w->up_b[i], 32, w->up_slope[i]);
-    pack_downconv(w->down_w[i], W(W_DOWN0 + i));
+    pack_downconv_fused(w->down_w[i], W(W_DOWN0 + i));
     ok = ok && bias(W_DOWN0 + i, w->down_b[i], 32, w->down_slope[i]);
   }
   pack_pointwise(w->compress_out_w, 32, 192, W(W_COMPRESS_OUT));
@@ -671,15 +779,14 @@ extern "C" int vsr_srfbn_bind(vsr_srfbn_plan* pl, const void* dev_weights, void*
         up_in = ws + pl->o_u;
       }
       PUSH(build_deconv(L, up_in, M, h, w, Wp(W_UP0 + i), Bp(W_UP0 + i), ws + pl->o_hr[i], 0));
-      const void* down_in = ws + pl->o_hr[0];
-      if (i > 0) {  // downtran(cat(hr[0..i])) on the block layout, ring kept at zero
-        Src s[6];
-        for (int j = 0; j <= i; ++j) s[j] = Src{ws + pl->o_hr[j], 32, 0, 32};
-        PUSH(build_pointwise(L, s, i + 1, Rb, Wp(W_DOWNTRAN0 + i - 1), Bp(W_DOWNTRAN0 + i - 1), 32, 1, ws + pl->o_hb,
-                             64, 0, 1, h, w));
-        down_in = ws + pl->o_hb;
+      {  // downtran(cat(hr[0..i])) + downBlocks[i], fused; sums land in the fp32 LR accumulator
+        const void* hrs[6];
+        for (int j = 0; j <= i; ++j) hrs[j] = ws + pl->o_hr[j];
+        PUSH(build_fused_down(L, hrs, i + 1, M, h, w, i > 0 ? Wp(W_DOWNTRAN0 + i - 1) : nullptr,
+                              i > 0 ? Bp(W_DOWNTRAN0 + i - 1) : nullptr, Wp(W_DOWN0 + i),
+                              reinterpret_cast<float*>(ws + pl->o_acc)));
+        PUSH(build_finalize(L, reinterpret_cast<float*>(ws + pl->o_acc), Bp(W_DOWN0 + i), ws + pl->o_lr[i + 1], P));
       }
-      PUSH(build_downconv(L, down_in, M, h, w, Wp(W_DOWN0 + i), Bp(W_DOWN0 + i), ws + pl->o_lr[i + 1]));
     }
     {  // compress_out(cat(lr[1..6])) -> hidden
       Src s[6];
@@ -703,6 +810,10 @@ extern "C" int vsr_srfbn_forward(vsr_srfbn_plan* pl, const float* x, float* y, v
   cudaStream_t st = as_stream(stream);
   const vsr_srfbn_config& c = pl->cfg;
   const int64_t P = (int64_t)c.num_maps * c.h * c.w;
+  {
+    cudaError_t e = cudaMemsetAsync(pl->ws + pl->o_acc, 0, (size_t)P * 128, st);   // LR accumulator (finalize re-zeroes)
+    if (e != cudaSuccess) return cuda_status(e);
+  }
   size_t ev = 0;
   auto mark = [&]() {
     if (pl->profile && ev < pl->events.size()) cudaEventRecord(pl->events[ev++], st);
@@ -738,7 +849,8 @@ extern "C" int vsr_srfbn_forward(vsr_srfbn_plan* pl, const float* x, float* y, v
 
 extern "C" const char* vsr_srfbn_kernel_class_name(int k) {
   static const char* names[KC_COUNT] = {"im2col", "conv_in_gemm", "pointwise_lr", "pointwise_hr", "deconv8x8s4",
-                                        "conv8x8s4", "conv_out3x3", "fc_fuse"};
+                                        "conv8x8s4", "conv_out3x3", "fc_fuse", "fused_downtran_conv8x8s4",
+                                        "finalize_lr"};
   return (k >= 0 && k < KC_COUNT) ? names[k] : "?";
 }
 
@@ -872,6 +984,59 @@ extern "C" int vsr_test_downconv(const void* x_bf16, int B, int h, int w, const 
   if (rc) return rc;
   Layer L;
   rc = build_downconv(L, x_bf16, B, h, w, ws, reinterpret_cast<const float*>(ws + 256 * 1024), y_bf16);
+  if (rc) return rc;
+  rc = launch_layer(L, st);
+  if (rc) return rc;
+  return cuda_status(cudaStreamSynchronize(st));
+}
+
+// downtran (nsrc >= 2; wt (32, 32*nsrc) fp32 host, bt (32), slope_t) + PReLU + Conv2d(32,32,8,4,2) (wd (32,32,8,8),
+// bd (32), slope_d) + PReLU through the fused kernel and finalize_lr_kernel.  hr: nsrc maps in block layout,
+// contiguous (nsrc, B, h+1, w+1, 16, 32) BF16.  y (B,h,w,32) BF16.  workspace additionally holds the fp32
+// accumulator: vsr_test_workspace_bytes(B,h,w) + B*h*w*128 bytes.
+extern "C" int vsr_test_fused_down(const void* hr_bf16, int nsrc, int B, int h, int w, const float* wt_host,
+                                   const float* bt_host, float slope_t, const float* wd_host, const float* bd_host,
+                                   float slope_d, void* y_bf16, void* workspace, size_t workspace_bytes,
+                                   vsr_stream_t stream) {
+  if (!hr_bf16 || !wd_host || !bd_host || !y_bf16 || !workspace || B <= 0 || h <= 0 || w <= 0 || nsrc < 1 || nsrc > 6)
+    return VSR_ERR_INVALID_ARG;
+  if (nsrc > 1 && (!wt_host || !bt_host)) return VSR_ERR_INVALID_ARG;
+  const size_t base_bytes = vsr_test_workspace_bytes(B, h, w);
+  const size_t acc_bytes = (size_t)B * h * w * 128;
+  if (workspace_bytes < base_bytes + acc_bytes) return VSR_ERR_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  std::vector<uint16_t> wd((size_t)128 * 512);
+  pack_downconv_fused(wd_host, wd.data());
+  int rc = upload(ws, wd.data(), wd.size() * 2, st);
+  if (rc) return rc;
+  float bd[33], bt[33];
+  memcpy(bd, bd_host, 32 * 4);
+  bd[32] = slope_d;
+  rc = upload(ws + 256 * 1024, bd, sizeof(bd), st);
+  if (rc) return rc;
+  if (nsrc > 1) {
+    std::vector<uint16_t> wt((size_t)32 * 32 * nsrc);
+    pack_pointwise(wt_host, 32, 32 * nsrc, wt.data());
+    rc = upload(ws + 160 * 1024, wt.data(), wt.size() * 2, st);
+    if (rc) return rc;
+    memcpy(bt, bt_host, 32 * 4);
+    bt[32] = slope_t;
+    rc = upload(ws + 257 * 1024, bt, sizeof(bt), st);
+    if (rc) return rc;
+  }
+  float* acc = reinterpret_cast<float*>(ws + base_bytes);
+  cudaError_t e = cudaMemsetAsync(acc, 0, acc_bytes, st);
+  if (e != cudaSuccess) return cuda_status(e);
+  const void* hrs[6];
+  const size_t plane = (size_t)B * (h + 1) * (w + 1) * 16 * 64;
+  for (int j = 0; j < nsrc; ++j) hrs[j] = reinterpret_cast<const uint8_t*>(hr_bf16) + j * plane;
+  Layer L;
+  rc = build_fused_down(L, hrs, nsrc, B, h, w, ws + 160 * 1024, reinterpret_cast<const float*>(ws + 257 * 1024), ws, acc);
+  if (rc) return rc;
+  rc = launch_layer(L, st);
+  if (rc) return rc;
+  rc = build_finalize(L, acc, reinterpret_cast<const float*>(ws + 256 * 1024), y_bf16, (int64_t)B * h * w);
   if (rc) return rc;
   rc = launch_layer(L, st);
   if (rc) return rc;

@@ -178,7 +178,7 @@ class SRProjectionModule(nn.Module):
     def profile_read(self):
         """{kernel class: dict(ms, launches, flops, bytes)} of the last forward of each plan, summed."""
         L = _lib.lib()
-        n = 8
+        n = 10
         out = {}
         for ent in self._plans.values():
             ms = (ctypes.c_double * n)()
