@@ -204,6 +204,9 @@ int vsr_srfbn_forward(vsr_srfbn_plan* plan, const float* x, float* y, vsr_stream
 const char* vsr_srfbn_kernel_class_name(int k);
 int vsr_srfbn_profile_enable(vsr_srfbn_plan* plan, int enable);
 int vsr_srfbn_profile_read(vsr_srfbn_plan* plan, double* ms, int32_t* launches, double* flops, double* bytes);
+/* per-launch device time of the last profiled forward, in launch order; returns the number of
+ * launches (<0 on error) and fills at most `capacity` entries */
+int vsr_srfbn_profile_launches(vsr_srfbn_plan* plan, float* ms, int32_t* kclass, int32_t capacity);
 
 /* Test hook: per-map network output before the fc fuse, (M,3,4h,4w) f32 (SRProjectionModule.py:143);
  * valid after vsr_srfbn_forward on the same stream. */
@@ -232,7 +235,7 @@ size_t vsr_test_workspace_bytes(int B, int h, int w);
  *              (SRProjectionModule.py:70-80): PReLU(Conv1x1 over nsrc concatenated HR maps) ->
  *              Conv2d(32,32,8,4,2) -> PReLU.  hr: (nsrc,B,h+1,w+1,16,32) bf16 block layout; nsrc==1
  *              skips the 1x1 (group 0).  wt (32,32*nsrc), wd (32,32,8,8) fp32 host.  y (B,h,w,32) bf16.
- *              workspace: vsr_test_workspace_bytes + B*h*w*128 bytes. */
+ *              workspace: vsr_test_workspace_bytes + B*h*w*512 bytes. */
 int vsr_test_fused_down(const void* hr_bf16, int nsrc, int B, int h, int w, const float* wt_host,
                         const float* bt_host, float slope_t, const float* wd_host, const float* bd_host,
                         float slope_d, void* y_bf16, void* workspace, size_t workspace_bytes,

@@ -77,7 +77,7 @@ def fused_down(hr_bf16, wt, bt, slope_t, wd, bd, slope_d):
     h, wd_ = hb - 1, wb - 1
     dev = hr_bf16.device
     y = torch.full((B, h, wd_, 32), float("nan"), dtype=torch.bfloat16, device=dev)
-    n = int(_lib.lib().vsr_test_workspace_bytes(B, h, wd_)) + B * h * wd_ * 128
+    n = int(_lib.lib().vsr_test_workspace_bytes(B, h, wd_)) + B * h * wd_ * 512
     ws = torch.empty(n, dtype=torch.uint8, device=dev)
     wd = wd.contiguous().float()
     bd = bd.contiguous().float()

@@ -17,9 +17,11 @@
 //   phase B: D_B[128, 4 taps x 32] += H_g[128, 128] * Wd_g[128, 128]^T        (K = 512 over 4 groups)
 //            "output-shift" form of the strided conv: block (Yb,Xb) contributes its tap-(dy,dx)
 //            partial product to LR pixel (Yb-dy, Xb-dx); every block is read exactly once
-//   epilogue: the four 32-channel partials of each block are added into an FP32 LR accumulator
-//            with vector reductions (red.global.add.v4.f32); finalize_lr_kernel applies
-//            bias + PReLU, rounds to BF16 and re-zeroes the accumulator.
+//   epilogue: the four 32-channel partials of each block go to per-pixel FP32 "slots" with exactly one
+//            writer each (dx taps are first combined across lanes by shuffle), finalize_lr_kernel sums
+//            the slots, applies bias + PReLU and rounds to BF16 -- no atomics, deterministic.
+//            (A first version used red.global.add.v4.f32: ~10k cycles per tile of L2 atomic
+//            throughput, the kernel's fixed cost; see profiles/.)
 //
 // HAS_TRAN = false is group 0 (no downtran: H = hr[0]); phase B's A operand then comes straight from
 // TMA.  Warp roles as in igemm.cuh: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue.
@@ -28,14 +30,17 @@
 
 namespace vsr {
 
-constexpr int kFusedThreads = 192;
-constexpr int kFusedMaxStages = 8;
-constexpr int kWdBytes = 128 * 512 * 2;      // resident 8x8-s4 weights, 8 chunks [128 n][64 k]
-constexpr int kWtChunkBytes = 32 * 32 * 2;   // one 32x32 downtran slice
+constexpr int kFusedEpiWarps = 16;   // 4 per TMEM lane quarter: one sub-position / one tap each
+constexpr int kFusedWdWarp = 2 + kFusedEpiWarps;             // last warp: streams the conv weights
+constexpr int kFusedThreads = 32 * (kFusedWdWarp + 1);
+constexpr int kFusedMaxStages = 16;
+constexpr int kWdGroupBytes = 128 * 128 * 2; // 8x8-s4 weights of one sub-position group: 2 chunks [128 n][64 k]
+constexpr int kWdRingBytes = 2 * kWdGroupBytes;  // streamed per group from L2 through a 2-deep ring
+constexpr int kWtChunkBytes = 32 * 32 * 2;   // one 32x32 downtran slice (64-byte rows, 64B swizzle)
 constexpr int kHBytes = 128 * 128 * 2;       // phase-B A operand of one sub-position group
 
 struct alignas(64) FusedDownParams {
-  CUtensorMap hr_maps[kMaxSources];   // HAS_TRAN: 5-D (32, 16, w+1, h+1, B), box (32,1,16,8,1), 64B swizzle
+  CUtensorMap hr_maps[kMaxSources];   // HAS_TRAN: 4-D (512, w+1, h+1, B), box (64,16,8,1) = 2 sub-positions, 128B swizzle
   CUtensorMap h0_map;                 // !HAS_TRAN: 4-D (512, w+1, h+1, B), box (64,16,8,1), 128B swizzle
   CUtensorMap wt_map;                 // 2-D (32*nsrc, 32), box (32,32), 64B swizzle
   CUtensorMap wd_map;                 // 2-D (512, 128), box (64,128), 128B swizzle
@@ -43,8 +48,10 @@ struct alignas(64) FusedDownParams {
   int32_t num_stages;
   int32_t tiles_x, tiles_y, batch;
   int32_t lr_h, lr_w;
+  int32_t prefetch_ahead;             // L2 prefetch distance in half-tiles
+  int32_t debug;                      // bring-up knob: bit0 = do not issue the phase-A MMAs
   const float* tran_bias;             // [32] biases + [1] PReLU slope of the downtran
-  float* acc;                         // (B, h, w, 32) fp32, zero on entry
+  float* part;                        // (B, h, w, 4 slots, 32) fp32 partial sums (see final epilogue)
 };
 
 __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
@@ -55,37 +62,56 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
+// TMA prefetch into L2 only (no shared memory, no barrier): lets the producer run far ahead of its
+// shared-memory ring, so that the ring's loads hit L2 instead of paying the full HBM latency.
+__device__ __forceinline__ void tma_prefetch_5d(const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
 }
 
 template <bool HAS_TRAN>
 inline size_t fused_down_smem_bytes(int nsrc, int num_stages) {
   size_t wt = HAS_TRAN ? ((size_t)nsrc * kWtChunkBytes + 1023) / 1024 * 1024 : 0;
-  size_t stage = HAS_TRAN ? 8192 : 2 * 16384;
-  return 1024 + kWdBytes + wt + (HAS_TRAN ? kHBytes : 0) + (size_t)num_stages * stage + 1024;
+  size_t stage = HAS_TRAN ? 16384 : 2 * 16384;
+  return 1024 + kWdRingBytes + wt + (HAS_TRAN ? kHBytes : 0) + (size_t)num_stages * stage + 1024;
 }
 
 template <bool HAS_TRAN>
 __global__ void __launch_bounds__(kFusedThreads, 1)
 fused_down_kernel(const __grid_constant__ FusedDownParams p) {
-  constexpr int kStageBytes = HAS_TRAN ? 8192 : 2 * 16384;
+  constexpr int kStageBytes = HAS_TRAN ? 16384 : 2 * 16384;
   constexpr int kTmemCols = HAS_TRAN ? 512 : 256;
   constexpr uint32_t kDB = HAS_TRAN ? 256 : 0;       // first column of the two D_B accumulators
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* s_wd = smem;
-  uint8_t* s_wt = s_wd + kWdBytes;
+  uint8_t* s_wt = s_wd + kWdRingBytes;
   const int wt_region = HAS_TRAN ? ((p.nsrc * kWtChunkBytes + 1023) / 1024 * 1024) : 0;
   uint8_t* s_h = s_wt + wt_region;
   uint8_t* s_a = s_h + (HAS_TRAN ? kHBytes : 0);
   uint8_t* tail = s_a + p.num_stages * kStageBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);      // [kFusedMaxStages]
   uint64_t* empty_bar = full_bar + kFusedMaxStages;            // [kFusedMaxStages]
-  uint64_t* w_full = empty_bar + kFusedMaxStages;              // [1]
-  uint64_t* da_full = w_full + 1;                              // [2]
+  uint64_t* w_full = empty_bar + kFusedMaxStages;              // [1] downtran weights resident
+  uint64_t* wd_full = w_full + 1;                              // [2] conv-weight ring
+  uint64_t* wd_empty = wd_full + 2;                            // [2]
+  uint64_t* da_full = wd_empty + 2;                            // [2]
   uint64_t* da_empty = da_full + 2;                            // [2]
   uint64_t* h_full = da_empty + 2;                             // [1]
   uint64_t* h_empty = h_full + 1;                              // [1]
@@ -105,12 +131,14 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
     }
     mbar_init(w_full, 1);
     for (int s = 0; s < 2; ++s) {
+      mbar_init(&wd_full[s], 1);
+      mbar_init(&wd_empty[s], 1);
       mbar_init(&da_full[s], 1);
-      mbar_init(&da_empty[s], 128);
+      mbar_init(&da_empty[s], 32 * kFusedEpiWarps);
       mbar_init(&db_full[s], 1);
-      mbar_init(&db_empty[s], 128);
+      mbar_init(&db_empty[s], 32 * kFusedEpiWarps);
     }
-    mbar_init(h_full, 128);
+    mbar_init(h_full, 32 * kFusedEpiWarps);
     mbar_init(h_empty, 1);
     fence_barrier_init();
   }
@@ -132,30 +160,60 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      mbar_expect_tx(w_full, (uint32_t)(kWdBytes + (HAS_TRAN ? p.nsrc * kWtChunkBytes : 0)));
-      for (int kc = 0; kc < 8; ++kc) tma_load_2d(s_wd + kc * 16384, &p.wd_map, w_full, kc * 64, 0);
-      if (HAS_TRAN)
+      if (HAS_TRAN) {
+        mbar_expect_tx(w_full, (uint32_t)(p.nsrc * kWtChunkBytes));
         for (int j = 0; j < p.nsrc; ++j) tma_load_2d(s_wt + j * kWtChunkBytes, &p.wt_map, w_full, j * 32, 0);
+      }
       int s = 0;
       uint32_t phase = 0;
+      // L2 prefetch cursor: runs kAhead half-tiles (8 sub-positions of every source = 64 KB per source)
+      // ahead of the loads.  Unit of the linear order: (tile, half) with half = sub-positions 8*half..+7.
+      const int kAhead = p.prefetch_ahead;   // 0 disables
+      auto prefetch_half = [&](int tile, int half) {
+        if (tile >= total_tiles) return;
+        int px0, py0, pb;
+        tile_coord(tile, px0, py0, pb);
+        if (HAS_TRAN) {
+          for (int sp = half * 8; sp < half * 8 + 8; sp += 2)
+            for (int j = 0; j < p.nsrc; ++j) tma_prefetch_4d(&p.hr_maps[j], sp * 32, px0, py0, pb);
+        } else {
+          for (int c = half * 256; c < half * 256 + 256; c += 64) tma_prefetch_4d(&p.h0_map, c, px0, py0, pb);
+        }
+      };
+      {
+        int t = blockIdx.x, hf = 0;
+        for (int i = 0; i < kAhead; ++i) {
+          prefetch_half(t, hf);
+          if (++hf == 2) { hf = 0; t += gridDim.x; }
+        }
+      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int x0, y0, b;
         tile_coord(tile, x0, y0, b);
-        if (HAS_TRAN) {
-          for (int sp = 0; sp < 16; ++sp)
-            for (int j = 0; j < p.nsrc; ++j) {
+        for (int half = 0; half < 2; ++half) {
+          if (kAhead > 0) {  // the half-tile kAhead units ahead of (tile, half)
+            const int u = half + kAhead;
+            prefetch_half(tile + (u >> 1) * gridDim.x, u & 1);
+          }
+          if (HAS_TRAN) {
+            // one box = 2 sub-positions x 128 blocks x 32 ch (16 KB): a [128 x 64] K-major tile whose K
+            // halves are the two sub-positions (box count, not bytes, limits a single-thread producer)
+            for (int sp = half * 8; sp < half * 8 + 8; sp += 2) {
+              for (int j = 0; j < p.nsrc; ++j) {
+                mbar_wait(&empty_bar[s], phase ^ 1);
+                mbar_expect_tx(&full_bar[s], kStageBytes);
+                tma_load_4d(s_a + s * kStageBytes, &p.hr_maps[j], &full_bar[s], sp * 32, x0, y0, b);
+                if (++s == p.num_stages) { s = 0; phase ^= 1; }
+              }
+            }
+          } else {
+            for (int g = half * 2; g < half * 2 + 2; ++g) {
               mbar_wait(&empty_bar[s], phase ^ 1);
               mbar_expect_tx(&full_bar[s], kStageBytes);
-              tma_load_5d(s_a + s * kStageBytes, &p.hr_maps[j], &full_bar[s], 0, sp, x0, y0, b);
+              tma_load_4d(s_a + s * kStageBytes, &p.h0_map, &full_bar[s], g * 128, x0, y0, b);
+              tma_load_4d(s_a + s * kStageBytes + 16384, &p.h0_map, &full_bar[s], g * 128 + 64, x0, y0, b);
               if (++s == p.num_stages) { s = 0; phase ^= 1; }
             }
-        } else {
-          for (int g = 0; g < 4; ++g) {
-            mbar_wait(&empty_bar[s], phase ^ 1);
-            mbar_expect_tx(&full_bar[s], kStageBytes);
-            tma_load_4d(s_a + s * kStageBytes, &p.h0_map, &full_bar[s], g * 128, x0, y0, b);
-            tma_load_4d(s_a + s * kStageBytes + 16384, &p.h0_map, &full_bar[s], g * 128 + 64, x0, y0, b);
-            if (++s == p.num_stages) { s = 0; phase ^= 1; }
           }
         }
       }
@@ -164,11 +222,11 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc_a = make_idesc(32);
     constexpr uint32_t idesc_b = make_idesc(128);
-    mbar_wait(w_full, 0);
+    if (HAS_TRAN) mbar_wait(w_full, 0);
     tc_fence_after();
     int s = 0;
     uint32_t phase = 0;
-    uint32_t n_a[2] = {0, 0}, n_b[2] = {0, 0}, n_h = 0;
+    uint32_t n_a[2] = {0, 0}, n_b[2] = {0, 0}, n_h = 0, n_wd = 0;
     int tb = 0;
 
     // phase A of sub-position group g: D_A[g&1] = sum_j A(s, j) * Wt_j^T for the 4 sub-positions
@@ -176,18 +234,22 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
       const int buf = g & 1;
       mbar_wait(&da_empty[buf], (n_a[buf] & 1) ^ 1);
       tc_fence_after();
-      for (int sl = 0; sl < 4; ++sl)
+      for (int pair = 0; pair < 2; ++pair)
         for (int j = 0; j < p.nsrc; ++j) {
           mbar_wait(&full_bar[s], phase);
           tc_fence_after();
           if (lane == 0) {
             const uint32_t a_addr = smem_u32(s_a + s * kStageBytes);
             const uint32_t b_addr = smem_u32(s_wt + j * kWtChunkBytes);
-            const uint32_t d = tmem_base + (uint32_t)(buf * 128 + sl * 32);
+            if (!(p.debug & 1))
 #pragma unroll
-            for (int k = 0; k < 2; ++k)
-              umma_bf16(d, make_smem_desc<64>(a_addr + k * 32), make_smem_desc<64>(b_addr + k * 32), idesc_a,
-                        (uint32_t)((j | k) != 0));
+            for (int sl2 = 0; sl2 < 2; ++sl2) {
+              const uint32_t d = tmem_base + (uint32_t)(buf * 128 + (pair * 2 + sl2) * 32);
+#pragma unroll
+              for (int k = 0; k < 2; ++k)
+                umma_bf16(d, make_smem_desc<128>(a_addr + sl2 * 64 + k * 32), make_smem_desc<64>(b_addr + k * 32),
+                          idesc_a, (uint32_t)((j | k) != 0));
+            }
             umma_commit(&empty_bar[s]);
           }
           __syncwarp();
@@ -208,22 +270,26 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
         a_addr = smem_u32(s_a + s * kStageBytes);
       }
       if (g == 0) mbar_wait(&db_empty[tb], (n_b[tb] & 1) ^ 1);
+      const int wslot = n_wd & 1;
+      mbar_wait(&wd_full[wslot], (n_wd >> 1) & 1);
       tc_fence_after();
       if (lane == 0) {
         const uint32_t d = tmem_base + kDB + (uint32_t)(tb * 128);
 #pragma unroll
         for (int kc = 0; kc < 2; ++kc) {
-          const uint32_t b_addr = smem_u32(s_wd + (g * 2 + kc) * 16384);
+          const uint32_t b_addr = smem_u32(s_wd + wslot * kWdGroupBytes + kc * 16384);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_bf16(d, make_smem_desc<128>(a_addr + kc * 16384 + k * 32), make_smem_desc<128>(b_addr + k * 32),
                       idesc_b, (uint32_t)((g | kc | k) != 0));
         }
+        umma_commit(&wd_empty[wslot]);
         if (HAS_TRAN) umma_commit(h_empty);
         else umma_commit(&empty_bar[s]);
         if (g == 3) umma_commit(&db_full[tb]);
       }
       __syncwarp();
+      ++n_wd;
       if (HAS_TRAN) ++n_h;
       else if (++s == p.num_stages) { s = 0; phase ^= 1; }
       if (g == 3) { ++n_b[tb]; tb ^= 1; }
@@ -243,14 +309,35 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
         for (int g = 0; g < 4; ++g) issue_b(g);
       }
     }
+  } else if (warp == kFusedWdWarp) {
+    // ===================== conv-weight streamer =====================
+    // every tile needs the 128 KB of 8x8-s4 weights once, 32 KB per sub-position group; all SMs
+    // stream the same bytes, so these are L2 hits.  A 2-deep ring instead of a resident copy frees
+    // 64 KB of shared memory for the activation pipeline (HBM latency hiding).
+    if (lane == 0) {
+      uint32_t n_wd = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x)
+        for (int g = 0; g < 4; ++g) {
+          const int slot = n_wd & 1;
+          mbar_wait(&wd_empty[slot], ((n_wd >> 1) & 1) ^ 1);
+          mbar_expect_tx(&wd_full[slot], kWdGroupBytes);
+          tma_load_2d(s_wd + slot * kWdGroupBytes, &p.wd_map, &wd_full[slot], (2 * g) * 64, 0);
+          tma_load_2d(s_wd + slot * kWdGroupBytes + 16384, &p.wd_map, &wd_full[slot], (2 * g + 1) * 64, 0);
+          ++n_wd;
+        }
+    }
   } else {
-    // ===================== epilogue warps 2..5 =====================
+    // ===================== epilogue warps 2..17 =====================
+    // warp -> TMEM lane quarter q = warp % 4 (hardware rule) and sub = which of the 4 column groups
+    // (phase A: sub-position within the group; final: tap) this warp handles
     const int q = warp & 3;
+    const int sub = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t m_a[2] = {0, 0}, m_b[2] = {0, 0}, m_h = 0;
     int tb = 0;
-    const float slope = HAS_TRAN ? s_bias[32] : 0.0f;
+    const float slope = HAS_TRAN ? s_bias[32] : 1.0f;
+    const __nv_bfloat162 slope2 = __floats2bfloat162_rn(slope, slope);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       int x0, y0, b;
       tile_coord(tile, x0, y0, b);
@@ -262,61 +349,73 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
           const int buf = g & 1;
           mbar_wait(&da_full[buf], m_a[buf] & 1);
           tc_fence_after();
-          uint32_t o[4][16];
-#pragma unroll
-          for (int sl = 0; sl < 4; ++sl) {
+          uint32_t o[16];
+          {
             uint32_t v[32];
-            tmem_ld32(lane_base + (uint32_t)(buf * 128 + sl * 32), v);
+            tmem_ld32(lane_base + (uint32_t)(buf * 128 + sub * 32), v);
             tmem_ld_wait();
-            const int s16 = g * 4 + sl, ry = s16 >> 2, rx = s16 & 3;
+            tc_fence_before();
+            mbar_arrive(&da_empty[buf]);
+            const int s16 = g * 4 + sub, ry = s16 >> 2, rx = s16 & 3;
             const bool ring = (Yb == 0 && ry < 2) || (Yb == p.lr_h && ry >= 2) || (Xb == 0 && rx < 2) ||
                               (Xb == p.lr_w && rx >= 2);
-            const bool keep = in_tensor && !ring;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float a = prelu(__uint_as_float(v[2 * j]) + s_bias[2 * j], slope, 1);
-              float c = prelu(__uint_as_float(v[2 * j + 1]) + s_bias[2 * j + 1], slope, 1);
-              o[sl][j] = keep ? pack_bf16(a, c) : 0u;
-            }
+            convert32(v, s_bias, slope2, in_tensor && !ring, o);
           }
-          tc_fence_before();
-          mbar_arrive(&da_empty[buf]);
           ++m_a[buf];
           mbar_wait(h_empty, (m_h & 1) ^ 1);
-          // K index inside the group: k = sl*32 + c -> 64-element chunk kc = sl>>1, 16-byte piece (sl&1)*4 + j
-          uint8_t* hrow = s_h + (row >> 3) * 1024 + (row & 7) * 128;
+          // K index inside the group: k = sub*32 + c -> 64-element chunk kc = sub>>1, 16-byte piece (sub&1)*4 + j
+          uint8_t* hrow = s_h + (sub >> 1) * 16384 + (row >> 3) * 1024 + (row & 7) * 128;
 #pragma unroll
-          for (int sl = 0; sl < 4; ++sl)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int piece = (sl & 1) * 4 + j;
-              *reinterpret_cast<uint4*>(hrow + (sl >> 1) * 16384 + ((piece ^ (row & 7)) << 4)) =
-                  make_uint4(o[sl][4 * j], o[sl][4 * j + 1], o[sl][4 * j + 2], o[sl][4 * j + 3]);
-            }
+          for (int j = 0; j < 4; ++j) {
+            const int piece = (sub & 1) * 4 + j;
+            *reinterpret_cast<uint4*>(hrow + ((piece ^ (row & 7)) << 4)) =
+                make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          }
           fence_proxy_async_smem();
           mbar_arrive(h_full);
           ++m_h;
         }
       }
-      // final: D_B[tb] -> shifted accumulation into the LR sums
+      // final: channels [8*sub, 8*sub+8) of the four tap partials of D_B[tb].  Block (Yb,Xb)'s tap (dy,dx)
+      // belongs to LR pixel (Yb-dy, Xb-dx).  The dx=1 partial is handed to the left neighbour lane
+      // (same block row of the tile) by shuffle; what is left is written, without atomics, to a
+      // slot that has exactly one writer:  slot 2*dy   : tap (dy,0) + right neighbour's tap (dy,1)
+      //                                     slot 2*dy+1 : tap (dy,1) arriving from the next tile
+      //                                                   (only pixels with X % 16 == 15 have one)
       mbar_wait(&db_full[tb], m_b[tb] & 1);
       tc_fence_after();
-#pragma unroll 1
-      for (int t = 0; t < 4; ++t) {
-        uint32_t v[32];
-        tmem_ld32(lane_base + kDB + (uint32_t)(tb * 128 + t * 32), v);
-        tmem_ld_wait();
-        if (t == 3) {
-          tc_fence_before();
-          mbar_arrive(&db_empty[tb]);
-        }
-        const int Y = Yb - (t >> 1), X = Xb - (t & 1);
-        if (in_tensor && Y >= 0 && Y < p.lr_h && X >= 0 && X < p.lr_w) {
-          float* dst = p.acc + (((int64_t)b * p.lr_h + Y) * p.lr_w + X) * 32;
+      {
+        uint32_t v[4][8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            red_add_v4(dst + 4 * j, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                       __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        for (int t = 0; t < 4; ++t) tmem_ld8(lane_base + kDB + (uint32_t)(tb * 128 + t * 32 + sub * 8), v[t]);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&db_empty[tb]);
+        const int xl = lane & 15;
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+          float comb[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float right = __uint_as_float(v[dy * 2 + 1][k]);
+            const float from_right = __shfl_down_sync(0xffffffffu, right, 1);
+            comb[k] = __uint_as_float(v[dy * 2][k]) + (xl < 15 ? from_right : 0.0f);
+          }
+          const int Y = Yb - dy;
+          if (in_tensor && Y >= 0 && Y < p.lr_h) {
+            if (Xb < p.lr_w) {
+              float4* dst = reinterpret_cast<float4*>(p.part + ((((int64_t)b * p.lr_h + Y) * p.lr_w + Xb) * 4 + 2 * dy) * 32 + sub * 8);
+              dst[0] = make_float4(comb[0], comb[1], comb[2], comb[3]);
+              dst[1] = make_float4(comb[4], comb[5], comb[6], comb[7]);
+            }
+            if (xl == 0 && Xb > 0) {
+              float4* dst = reinterpret_cast<float4*>(p.part + ((((int64_t)b * p.lr_h + Y) * p.lr_w + Xb - 1) * 4 + 2 * dy + 1) * 32 + sub * 8);
+              dst[0] = make_float4(__uint_as_float(v[dy * 2 + 1][0]), __uint_as_float(v[dy * 2 + 1][1]),
+                                   __uint_as_float(v[dy * 2 + 1][2]), __uint_as_float(v[dy * 2 + 1][3]));
+              dst[1] = make_float4(__uint_as_float(v[dy * 2 + 1][4]), __uint_as_float(v[dy * 2 + 1][5]),
+                                   __uint_as_float(v[dy * 2 + 1][6]), __uint_as_float(v[dy * 2 + 1][7]));
+            }
+          }
         }
       }
       ++m_b[tb];
@@ -332,18 +431,29 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
   }
 }
 
-// lr_out[p, c] = bf16(PReLU(acc[p, c] + bias[c])); acc[p, c] = 0.   8 channels per thread.
+// lr_out[p, c] = bf16(PReLU(sum of the pixel's partial slots + bias[c])).  8 channels per thread.
+// Deterministic: every slot has one writer, the sum order is fixed.
 __global__ void __launch_bounds__(256)
-finalize_lr_kernel(float4* __restrict__ acc, const float* __restrict__ bias, uint4* __restrict__ out, int64_t n8) {
+finalize_lr_kernel(const float4* __restrict__ part, const float* __restrict__ bias, uint4* __restrict__ out, int64_t n8,
+                   int w) {
   const float slope = __ldg(bias + 32);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i & 3) * 8;
-    float4 a = acc[2 * i], b = acc[2 * i + 1];
-    acc[2 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    acc[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-    float r[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    const int64_t px = i >> 2;
+    const int c8 = (int)(i & 3);
+    const int X = (int)(px % w);
+    const float4* base = part + px * 32 + c8 * 2;          // 32 float4 per pixel, 8 per slot
+    float4 a0 = base[0], a1 = base[1];
+    const float4 b0 = base[16], b1 = base[17];
+    a0 = make_float4(a0.x + b0.x, a0.y + b0.y, a0.z + b0.z, a0.w + b0.w);
+    a1 = make_float4(a1.x + b1.x, a1.y + b1.y, a1.z + b1.z, a1.w + b1.w);
+    if ((X & 15) == 15) {
+      const float4 c0 = base[8], c1 = base[9], d0 = base[24], d1 = base[25];
+      a0 = make_float4(a0.x + (c0.x + d0.x), a0.y + (c0.y + d0.y), a0.z + (c0.z + d0.z), a0.w + (c0.w + d0.w));
+      a1 = make_float4(a1.x + (c1.x + d1.x), a1.y + (c1.y + d1.y), a1.z + (c1.z + d1.z), a1.w + (c1.w + d1.w));
+    }
+    float r[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
-    for (int k = 0; k < 8; ++k) r[k] = prelu(r[k] + __ldg(bias + c + k), slope, 1);
+    for (int k = 0; k < 8; ++k) r[k] = prelu(r[k] + __ldg(bias + c8 * 8 + k), slope, 1);
     out[i] = make_uint4(pack_bf16(r[0], r[1]), pack_bf16(r[2], r[3]), pack_bf16(r[4], r[5]), pack_bf16(r[6], r[7]));
   }
 }

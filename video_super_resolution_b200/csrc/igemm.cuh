@@ -26,7 +26,9 @@ constexpr int kTileM = 128;          // UMMA M
 constexpr int kMaxChunks = 72;       // K chunks per tile (downconv: 32 with CK=64, 64 with CK=32)
 constexpr int kMaxSources = 6;       // concatenated A sources (downtran of group 5)
 constexpr int kMaxStages = 8;
-constexpr int kIgemmThreads = 192;   // 6 warps
+constexpr int kIgemmThreads = 192;   // 6 warps: producer, MMA, 4 epilogue (EPI_ROWS / EPI_CONV_OUT)
+constexpr int kDeconvEpiWarps = 16;  // EPI_DECONV: 4 warps per TMEM lane quarter, 2 sub-positions each
+constexpr int kDeconvThreads = 64 + 32 * kDeconvEpiWarps;
 
 enum EpiMode : int {
   EPI_ROWS = 0,        // BN=32: 64-byte BF16 row per pixel at out + row*pitch + off
@@ -187,6 +189,27 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 __device__ __forceinline__ float prelu(float v, float slope, int act) { return (act && v < 0.0f) ? v * slope : v; }
+// Two activations at once: round to BF16, then PReLU in packed BF16 (max(x,0) + slope*min(x,0), one
+// rounding of the product) -- 2 instructions per element instead of 4.5.  slope2 = (1,1) is identity.
+__device__ __forceinline__ uint32_t prelu_pack(float a, float b, __nv_bfloat162 slope2) {
+  const __nv_bfloat162 x = __floats2bfloat162_rn(a, b);
+  const __nv_bfloat162 z = __floats2bfloat162_rn(0.0f, 0.0f);
+  const __nv_bfloat162 r = __hfma2(__hmin2(x, z), slope2, __hmax2(x, z));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+// 32 accumulator columns -> 16 packed BF16 pairs with bias (fp32 add) and PReLU
+__device__ __forceinline__ void convert32(const uint32_t (&v)[32], const float* bias, __nv_bfloat162 slope2, bool keep,
+                                          uint32_t (&o)[16]) {
+  const float4* b4 = reinterpret_cast<const float4*>(bias);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 bb = b4[j];
+    const uint32_t lo = prelu_pack(__uint_as_float(v[4 * j]) + bb.x, __uint_as_float(v[4 * j + 1]) + bb.y, slope2);
+    const uint32_t hi = prelu_pack(__uint_as_float(v[4 * j + 2]) + bb.z, __uint_as_float(v[4 * j + 3]) + bb.w, slope2);
+    o[2 * j] = keep ? lo : 0u;
+    o[2 * j + 1] = keep ? hi : 0u;
+  }
+}
 
 struct TileCoord {
   int n_tile, x0, y0, b;
@@ -211,7 +234,7 @@ __host__ __device__ constexpr int b_chunk_bytes() { return BN * CK * 2; }
 template <int CK>
 __host__ __device__ constexpr int a_stage_bytes() { return kTileM * CK * 2; }
 
-constexpr int kDeconvStageBytes = 4 * 32 * 512;   // EPI_DECONV: 4 epilogue warps x 32 blocks x 512 B
+constexpr int kDeconvStageBytes = kDeconvEpiWarps * 32 * 128;   // EPI_DECONV: per warp 32 blocks x 2 sub-positions x 64 B
 
 template <int CK, int BN>
 inline size_t igemm_smem_bytes(int num_chunks, int num_stages, int extra = 0) {
@@ -221,8 +244,10 @@ inline size_t igemm_smem_bytes(int num_chunks, int num_stages, int extra = 0) {
 }
 
 template <int MODE, int CK, int BN>
-__global__ void __launch_bounds__(kIgemmThreads, 1)
+__global__ void __launch_bounds__(MODE == EPI_DECONV ? kDeconvThreads : kIgemmThreads, 1)
 igemm_kernel(const __grid_constant__ IgemmParams p) {
+  constexpr int kThreadsHere = MODE == EPI_DECONV ? kDeconvThreads : kIgemmThreads;
+  constexpr int kEpiThreads = kThreadsHere - 64;
   static_assert(CK == 32 || CK == 64, "K chunk is 32 (64B swizzle) or 64 (128B swizzle) BF16");
   static_assert(BN == 16 || BN == 32 || BN == 128 || BN == 256, "supported N tiles");
   constexpr int kSwz = CK * 2;
@@ -231,7 +256,8 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
   constexpr int kBBytes = b_chunk_bytes<CK, BN>();
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // align by pointer arithmetic (an integer round trip would demote every access to generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int b_region = ((p.num_chunks * kBBytes) + 1023) / 1024 * 1024;
   uint8_t* smem_b = smem;
   uint8_t* smem_a = smem + b_region;
@@ -256,14 +282,14 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 128);
+      mbar_init(&tmem_empty[s], kEpiThreads);
     }
     mbar_init(b_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<kTmemCols>(tmem_ptr);
   constexpr int kBiasExtra = (MODE == EPI_CONV_OUT) ? 7 : 1;
-  for (int i = threadIdx.x; i < p.bias_n + kBiasExtra; i += kIgemmThreads) s_bias[i] = p.bias[i];
+  for (int i = threadIdx.x; i < p.bias_n + kBiasExtra; i += kThreadsHere) s_bias[i] = p.bias[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -350,11 +376,12 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
             zero = (Y == 0 && ry < 2) || (Y == p.lr_h && ry >= 2) || (X == 0 && rx < 2) || (X == p.lr_w && rx >= 2);
           }
         } else {
-          const int y = t.y0 + row / p.tile_w, x = t.x0 + row % p.tile_w;
+          const int y = t.y0 + (row >> 4), x = t.x0 + (row & 15);   // spatial EPI_ROWS tiles are 16 x 8
           valid = (y < p.out_h) && (x < p.out_w);
           dst = reinterpret_cast<uint8_t*>(p.out) + (((int64_t)t.b * p.out_h + y) * p.out_w + x) * p.out_pitch + p.out_off;
         }
-        const float slope = s_bias[p.bias_n];
+        const float slope = p.act ? s_bias[p.bias_n] : 1.0f;
+        const __nv_bfloat162 slope2 = __floats2bfloat162_rn(slope, slope);
 #pragma unroll 1
         for (int cg = 0; cg < BN / 32; ++cg) {
           uint32_t v[32];
@@ -366,12 +393,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
           }
           if (valid) {
             uint32_t o[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float a = prelu(__uint_as_float(v[2 * j]) + s_bias[cg * 32 + 2 * j], slope, p.act);
-              float b = prelu(__uint_as_float(v[2 * j + 1]) + s_bias[cg * 32 + 2 * j + 1], slope, p.act);
-              o[j] = zero ? 0u : pack_bf16(a, b);
-            }
+            convert32(v, s_bias + cg * 32, slope2, !zero, o);
             uint4* d4 = reinterpret_cast<uint4*>(dst + cg * 64);
 #pragma unroll
             for (int j = 0; j < 4; ++j) d4[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
@@ -380,17 +402,20 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
       } else if constexpr (MODE == EPI_DECONV) {
         // row = patch position (Y, X) in [0,h] x [0,w]; this N tile holds sub-positions
         // s = n_tile*8 .. n_tile*8+7 (ry = s>>2, rx = s&3), 32 output channels each.
-        const int Y = t.y0 + row / p.tile_w, X = t.x0 + row % p.tile_w;
+        const int Y = t.y0 + (row >> 4), X = t.x0 + (row & 15);     // deconv tiles are 16 x 8 blocks
         const bool valid = (Y <= p.lr_h) && (X <= p.lr_w);
         const int H = 4 * p.lr_h, W = 4 * p.lr_w;
         const float slope = s_bias[p.bias_n];
+        const __nv_bfloat162 slope2 = __floats2bfloat162_rn(slope, slope);
+        const int sub = (warp - 2) >> 2;             // which pair of sub-positions this warp converts
         if (p.deconv_nhwc) {
 #pragma unroll 1
-          for (int cg = 0; cg < 8; ++cg) {
+          for (int c2 = 0; c2 < 2; ++c2) {
+            const int cg = sub * 2 + c2;
             uint32_t v[32];
             tmem_ld32(taddr + cg * 32, v);
             tmem_ld_wait();
-            if (cg == 7) {
+            if (c2 == 1) {
               tc_fence_before();
               mbar_arrive(&tmem_empty[as]);
             }
@@ -399,29 +424,24 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
             const int Yt = 4 * Y + ry - 2, Xt = 4 * X + rx - 2;       // true HR coordinates
             if (valid && (Yt >= 0) && (Yt < H) && (Xt >= 0) && (Xt < W)) {
               uint32_t o[16];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                float a = prelu(__uint_as_float(v[2 * j]) + s_bias[2 * j], slope, p.act);
-                float b = prelu(__uint_as_float(v[2 * j + 1]) + s_bias[2 * j + 1], slope, p.act);
-                o[j] = pack_bf16(a, b);
-              }
+              convert32(v, s_bias, slope2, true, o);
               uint4* d4 = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) + (((int64_t)t.b * H + Yt) * W + Xt) * 64);
 #pragma unroll
               for (int j = 0; j < 4; ++j) d4[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
             }
           }
         } else {
-          // Block layout: this N tile owns 512 contiguous bytes (8 sub-positions x 32 ch) of every
-          // block row.  Stage the warp's 32 rows in shared memory (16-byte pieces XOR-swizzled by the
-          // row so that both phases are bank-conflict free), then write each row with ONE fully
-          // coalesced 512-byte warp store.
-          uint8_t* stg = s_stage + (warp - 2) * (32 * 512);
-#pragma unroll 1
-          for (int cg = 0; cg < 8; ++cg) {
+          // Block layout: this warp owns 128 contiguous bytes (2 sub-positions x 32 ch) of each of its
+          // 32 block rows.  Stage them in shared memory (16-byte pieces XOR-swizzled by the row: both
+          // phases are bank-conflict free), then store 4 rows per instruction as full 128-byte lines.
+          uint8_t* stg = s_stage + (warp - 2) * (32 * 128);
+#pragma unroll
+          for (int c2 = 0; c2 < 2; ++c2) {
+            const int cg = sub * 2 + c2;
             uint32_t v[32];
             tmem_ld32(taddr + cg * 32, v);
             tmem_ld_wait();
-            if (cg == 7) {
+            if (c2 == 1) {
               tc_fence_before();
               mbar_arrive(&tmem_empty[as]);
             }
@@ -430,35 +450,32 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
             const int Yt = 4 * Y + ry - 2, Xt = 4 * X + rx - 2;
             const bool inside = (Yt >= 0) && (Yt < H) && (Xt >= 0) && (Xt < W);   // else: zero ring
             uint32_t o[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float a = prelu(__uint_as_float(v[2 * j]) + s_bias[2 * j], slope, p.act);
-              float b = prelu(__uint_as_float(v[2 * j + 1]) + s_bias[2 * j + 1], slope, p.act);
-              o[j] = inside ? pack_bf16(a, b) : 0u;
-            }
+            convert32(v, s_bias, slope2, inside, o);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const int piece = cg * 4 + j;
-              *reinterpret_cast<uint4*>(stg + lane * 512 + ((piece ^ lane) & 31) * 16) =
+              const int piece = c2 * 4 + j;
+              *reinterpret_cast<uint4*>(stg + lane * 128 + ((piece ^ (lane & 7)) << 4)) =
                   make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
             }
           }
           __syncwarp();
-#pragma unroll 4
-          for (int r = 0; r < 32; ++r) {
+          const int pr = lane >> 3, pc = lane & 7;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + pr;
             const int R = q * 32 + r;
-            const int Yr = t.y0 + R / p.tile_w, Xr = t.x0 + R % p.tile_w;
+            const int Yr = t.y0 + (R >> 4), Xr = t.x0 + (R & 15);
             if (Yr <= p.lr_h && Xr <= p.lr_w) {
-              const uint4 val = *reinterpret_cast<const uint4*>(stg + r * 512 + ((lane ^ r) & 31) * 16);
-              uint8_t* dst = reinterpret_cast<uint8_t*>(p.out) +
-                             ((((int64_t)t.b * (p.lr_h + 1) + Yr) * (p.lr_w + 1) + Xr) * 16 + t.n_tile * 8) * 64;
-              *reinterpret_cast<uint4*>(dst + lane * 16) = val;
+              const uint4 val = *reinterpret_cast<const uint4*>(stg + r * 128 + ((pc ^ (r & 7)) << 4));
+              const int64_t blk = ((int64_t)t.b * (p.lr_h + 1) + Yr) * (p.lr_w + 1) + Xr;
+              uint8_t* dst = reinterpret_cast<uint8_t*>(p.out) + blk * 1024 + (t.n_tile * 8 + sub * 2) * 64 + pc * 16;
+              *reinterpret_cast<uint4*>(dst) = val;
             }
           }
           __syncwarp();
         }
       } else {  // EPI_CONV_OUT
-        const int Y = t.y0 + row / p.tile_w, X = t.x0 + row % p.tile_w;
+        const int Y = t.y0 + (row >> 5), X = t.x0 + (row & 31);     // conv_out tiles are 32 x 4
         const bool valid = (Y < p.out_h) && (X < p.out_w);
         uint32_t v[16];
         tmem_ld16(taddr, v);

@@ -26,6 +26,7 @@
 // keeps `outs[-1:]` (SRProjectionModule.py:145), the earlier steps' images are dead values.
 #include "fused_down.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -102,6 +103,7 @@ struct Layer {
   const float* fin_bias;
   void* fin_out;
   int64_t fin_n8;
+  int fin_w;
   int grid;
   size_t smem;
   int kclass;
@@ -118,7 +120,7 @@ int launch_variant(const Layer& L, cudaStream_t st) {
     if (e != cudaSuccess) return cuda_status(e);
     attr_set = true;
   }
-  igemm_kernel<MODE, CK, BN><<<L.grid, kIgemmThreads, L.smem, st>>>(L.p);
+  igemm_kernel<MODE, CK, BN><<<L.grid, MODE == EPI_DECONV ? kDeconvThreads : kIgemmThreads, L.smem, st>>>(L.p);
   return after_launch();
 }
 
@@ -142,8 +144,8 @@ int launch_layer(const Layer& L, cudaStream_t st) {
     case V_FINALIZE: {
       int64_t blocks = ceil_div64(L.fin_n8, 256);
       if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-      finalize_lr_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<float4*>(L.fin_acc), L.fin_bias,
-                                                      reinterpret_cast<uint4*>(L.fin_out), L.fin_n8);
+      finalize_lr_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(L.fin_acc), L.fin_bias,
+                                                      reinterpret_cast<uint4*>(L.fin_out), L.fin_n8, L.fin_w);
       return after_launch();
     }
     case V_PW32: return launch_variant<EPI_ROWS, 32, 32>(L, st);
@@ -324,10 +326,10 @@ int make_hr5d_map(CUtensorMap* m, const void* base, int h, int w, int B) {
   if (!enc) return VSR_ERR_STATE;
   cuuint64_t dims[5] = {32, 16, (cuuint64_t)(w + 1), (cuuint64_t)(h + 1), (cuuint64_t)B};
   cuuint64_t strides[4] = {64, 1024, (cuuint64_t)1024 * (w + 1), (cuuint64_t)1024 * (w + 1) * (h + 1)};
-  cuuint32_t box[5] = {32, 1, 16, 8, 1};
+  cuuint32_t box[5] = {32, 2, 16, 8, 1};
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? VSR_OK : VSR_ERR_CUDA_BASE + 999;
 }
@@ -335,7 +337,7 @@ int make_hr5d_map(CUtensorMap* m, const void* base, int h, int w, int B) {
 // downtran (1x1 over hr[0..nsrc-1], nsrc >= 2) + PReLU + Conv2d(32,32,8,4,2) pre-activation sums -> acc;
 // nsrc == 1: the conv alone on hr[0].  hr[j]: HR block layout (B,h+1,w+1,16,32); acc (B,h,w,32) fp32.
 int build_fused_down(Layer& L, const void* const* hr, int nsrc, int B, int h, int w, const void* wt_dev,
-                     const float* tran_bias_dev, const void* wd_dev, float* acc) {
+                     const float* tran_bias_dev, const void* wd_dev, float* part) {
   memset(&L, 0, sizeof(L));
   const bool tran = nsrc > 1;
   L.variant = tran ? V_FUSED_TRAN : V_FUSED_PLAIN;
@@ -344,7 +346,7 @@ int build_fused_down(Layer& L, const void* const* hr, int nsrc, int B, int h, in
   int rc;
   if (tran) {
     for (int j = 0; j < nsrc; ++j) {
-      rc = make_hr5d_map(&f.hr_maps[j], hr[j], h, w, B);
+      rc = make_act_map(&f.hr_maps[j], hr[j], 512, w + 1, h + 1, B, 64, 16, 8);
       if (rc) return rc;
     }
     rc = make_w_map(&f.wt_map, wt_dev, 32 * nsrc, 32, 32, 32);
@@ -356,34 +358,50 @@ int build_fused_down(Layer& L, const void* const* hr, int nsrc, int B, int h, in
   rc = make_w_map(&f.wd_map, wd_dev, 512, 128, 64, 128);
   if (rc) return rc;
   f.nsrc = nsrc;
-  f.num_stages = tran ? 6 : 2;
+  f.num_stages = tran ? 7 : 5;
   f.tiles_x = ceil_div(w + 1, 16);
   f.tiles_y = ceil_div(h + 1, 8);
   f.batch = B;
   f.lr_h = h;
   f.lr_w = w;
+  {
+    const char* e = getenv("VSR_PREFETCH_AHEAD");   // tuning knob (half-tiles of L2 prefetch distance)
+    f.prefetch_ahead = e ? atoi(e) : 0;   // measured: hurts (strided 64 B boxes over-fetch), see DESIGN.md
+  }
+  {
+    const char* e = getenv("VSR_FUSED_DEBUG");
+    f.debug = e ? atoi(e) : 0;
+  }
+  {
+    const char* e = getenv("VSR_FUSED_STAGES");
+    if (e && atoi(e) > 0 && atoi(e) <= (tran ? 7 : 5)) f.num_stages = atoi(e);
+  }
   f.tran_bias = tran_bias_dev;
-  f.acc = acc;
+  f.part = part;
+  while (f.num_stages > 2 && (tran ? fused_down_smem_bytes<true>(nsrc, f.num_stages)
+                                   : fused_down_smem_bytes<false>(nsrc, f.num_stages)) > 227 * 1024)
+    --f.num_stages;
   L.smem = tran ? fused_down_smem_bytes<true>(nsrc, f.num_stages) : fused_down_smem_bytes<false>(nsrc, f.num_stages);
   int64_t total = (int64_t)f.tiles_x * f.tiles_y * B;
   L.grid = (int)(total < kNumSMs ? total : kNumSMs);
   const double lrpx = (double)B * h * w;
   L.kclass = KC_FUSED_DOWN;
   L.flops = lrpx * 131072.0 + (tran ? lrpx * 16.0 * 2.0 * 32.0 * nsrc * 32.0 : 0.0);
-  L.bytes = lrpx * 64.0 * (16.0 * nsrc) + lrpx * 128.0;
+  L.bytes = lrpx * 64.0 * (16.0 * nsrc) + lrpx * 272.0;
   return VSR_OK;
 }
 
-int build_finalize(Layer& L, float* acc, const float* bias_dev, void* out, int64_t pixels) {
+int build_finalize(Layer& L, float* acc, const float* bias_dev, void* out, int64_t pixels, int w) {
   memset(&L, 0, sizeof(L));
   L.variant = V_FINALIZE;
   L.fin_acc = acc;
   L.fin_bias = bias_dev;
   L.fin_out = out;
   L.fin_n8 = pixels * 4;
+  L.fin_w = w;
   L.kclass = KC_FINALIZE;
   L.flops = 0;
-  L.bytes = (double)pixels * (128.0 + 128.0 + 64.0);
+  L.bytes = (double)pixels * (272.0 + 64.0);
   return VSR_OK;
 }
 
@@ -636,7 +654,7 @@ static void layout_workspace(vsr_srfbn_plan* pl) {
   pl->o_u = put(P * 64);
   for (int i = 0; i < 6; ++i) pl->o_hr[i] = put(Rb * 64);
   pl->o_hb = put(P * 16 * 64);   // plain-NHWC result of the `out` deconv
-  pl->o_acc = put(P * 128);
+  pl->o_acc = put(P * 512);   // fp32 partial slots of the fused down kernel
   pl->o_premix = put(P * 16 * 3 * 4);
   pl->ws_bytes = off;
 }
@@ -785,7 +803,7 @@ extern "C" int vsr_srfbn_bind(vsr_srfbn_plan* pl, const void* dev_weights, void*
         PUSH(build_fused_down(L, hrs, i + 1, M, h, w, i > 0 ? Wp(W_DOWNTRAN0 + i - 1) : nullptr,
                               i > 0 ? Bp(W_DOWNTRAN0 + i - 1) : nullptr, Wp(W_DOWN0 + i),
                               reinterpret_cast<float*>(ws + pl->o_acc)));
-        PUSH(build_finalize(L, reinterpret_cast<float*>(ws + pl->o_acc), Bp(W_DOWN0 + i), ws + pl->o_lr[i + 1], P));
+        PUSH(build_finalize(L, reinterpret_cast<float*>(ws + pl->o_acc), Bp(W_DOWN0 + i), ws + pl->o_lr[i + 1], P, w));
       }
     }
     {  // compress_out(cat(lr[1..6])) -> hidden
@@ -810,10 +828,6 @@ extern "C" int vsr_srfbn_forward(vsr_srfbn_plan* pl, const float* x, float* y, v
   cudaStream_t st = as_stream(stream);
   const vsr_srfbn_config& c = pl->cfg;
   const int64_t P = (int64_t)c.num_maps * c.h * c.w;
-  {
-    cudaError_t e = cudaMemsetAsync(pl->ws + pl->o_acc, 0, (size_t)P * 128, st);   // LR accumulator (finalize re-zeroes)
-    if (e != cudaSuccess) return cuda_status(e);
-  }
   size_t ev = 0;
   auto mark = [&]() {
     if (pl->profile && ev < pl->events.size()) cudaEventRecord(pl->events[ev++], st);
@@ -889,6 +903,20 @@ extern "C" int vsr_srfbn_profile_read(vsr_srfbn_plan* pl, double* ms, int32_t* l
     ms[k] += t; launches[k] += 1; flops[k] += f; bytes[k] += b;
   }
   return VSR_OK;
+}
+
+extern "C" int vsr_srfbn_profile_launches(vsr_srfbn_plan* pl, float* ms, int32_t* kclass, int32_t capacity) {
+  if (!pl || !ms || !kclass) return -1;
+  if (!pl->bound || pl->events.empty()) return -1;
+  if (cudaEventSynchronize(pl->events.back()) != cudaSuccess) return -1;
+  const size_t n = pl->layers.size() + 2;
+  for (size_t i = 0; i < n && (int32_t)i < capacity; ++i) {
+    float t = 0;
+    cudaEventElapsedTime(&t, pl->events[i], pl->events[i + 1]);
+    ms[i] = t;
+    kclass[i] = i == 0 ? KC_IM2COL : (i == n - 1 ? KC_FC : pl->layers[i - 1].kclass);
+  }
+  return (int)n;
 }
 
 extern "C" int vsr_srfbn_debug_premix(const vsr_srfbn_plan* pl, float* out_maps, vsr_stream_t stream) {
@@ -993,7 +1021,7 @@ extern "C" int vsr_test_downconv(const void* x_bf16, int B, int h, int w, const 
 // downtran (nsrc >= 2; wt (32, 32*nsrc) fp32 host, bt (32), slope_t) + PReLU + Conv2d(32,32,8,4,2) (wd (32,32,8,8),
 // bd (32), slope_d) + PReLU through the fused kernel and finalize_lr_kernel.  hr: nsrc maps in block layout,
 // contiguous (nsrc, B, h+1, w+1, 16, 32) BF16.  y (B,h,w,32) BF16.  workspace additionally holds the fp32
-// accumulator: vsr_test_workspace_bytes(B,h,w) + B*h*w*128 bytes.
+// partial-sum slots: vsr_test_workspace_bytes(B,h,w) + B*h*w*512 bytes.
 extern "C" int vsr_test_fused_down(const void* hr_bf16, int nsrc, int B, int h, int w, const float* wt_host,
                                    const float* bt_host, float slope_t, const float* wd_host, const float* bd_host,
                                    float slope_d, void* y_bf16, void* workspace, size_t workspace_bytes,
@@ -1002,7 +1030,7 @@ extern "C" int vsr_test_fused_down(const void* hr_bf16, int nsrc, int B, int h, 
     return VSR_ERR_INVALID_ARG;
   if (nsrc > 1 && (!wt_host || !bt_host)) return VSR_ERR_INVALID_ARG;
   const size_t base_bytes = vsr_test_workspace_bytes(B, h, w);
-  const size_t acc_bytes = (size_t)B * h * w * 128;
+  const size_t acc_bytes = (size_t)B * h * w * 512;
   if (workspace_bytes < base_bytes + acc_bytes) return VSR_ERR_WORKSPACE;
   cudaStream_t st = as_stream(stream);
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
@@ -1026,8 +1054,6 @@ extern "C" int vsr_test_fused_down(const void* hr_bf16, int nsrc, int B, int h, 
     if (rc) return rc;
   }
   float* acc = reinterpret_cast<float*>(ws + base_bytes);
-  cudaError_t e = cudaMemsetAsync(acc, 0, acc_bytes, st);
-  if (e != cudaSuccess) return cuda_status(e);
   const void* hrs[6];
   const size_t plane = (size_t)B * (h + 1) * (w + 1) * 16 * 64;
   for (int j = 0; j < nsrc; ++j) hrs[j] = reinterpret_cast<const uint8_t*>(hr_bf16) + j * plane;
@@ -1036,7 +1062,7 @@ extern "C" int vsr_test_fused_down(const void* hr_bf16, int nsrc, int B, int h, 
   if (rc) return rc;
   rc = launch_layer(L, st);
   if (rc) return rc;
-  rc = build_finalize(L, acc, reinterpret_cast<const float*>(ws + 256 * 1024), y_bf16, (int64_t)B * h * w);
+  rc = build_finalize(L, acc, reinterpret_cast<const float*>(ws + 256 * 1024), y_bf16, (int64_t)B * h * w, w);
   if (rc) return rc;
   rc = launch_layer(L, st);
   if (rc) return rc;
