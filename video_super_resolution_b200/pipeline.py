@@ -88,5 +88,8 @@ def gather_frames(local_frames: torch.Tensor, group=None) -> torch.Tensor:
         return local_frames
     world = dist.get_world_size(group)
     out = torch.empty((world,) + tuple(local_frames.shape), dtype=local_frames.dtype, device=local_frames.device)
-    dist.all_gather_into_tensor(out, local_frames.contiguous(), group=group)
+    if local_frames.is_cuda:
+        dist.all_gather_into_tensor(out, local_frames.contiguous(), group=group)      # ncclAllGather
+    else:
+        dist.all_gather(list(out.unbind(0)), local_frames.contiguous(), group=group)  # gloo (CPU tests)
     return out.flatten(0, 1)
