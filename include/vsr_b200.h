@@ -58,7 +58,9 @@ int vsr_resample2d_forward(const float* input1, const float* flow, float* output
  * f32, flow (B,H,W,2) f32.  If norm_out != NULL it additionally receives, per pixel,
  * sqrt(sum_c (ref[b,y,x,c] - dst[b,y,x,c])^2) with fp32 accumulation, i.e. the reference's
  * `channelnorm(img - resampled)` (models.py:86-88) fused into the warp; `ref` may be NULL iff
- * norm_out is NULL.  Same arithmetic as vsr_resample2d_forward. */
+ * norm_out is NULL.  `bilinear`: 0 = nearest, 1 = the reference's arithmetic bit for bit (as
+ * vsr_resample2d_forward), 2 = fast: same taps / border rule with fp32 FMA weights (differs from
+ * mode 1 by a few fp32 ulps, <= 1e-4 on 0..255 data; no fp64 conversions, the pipeline default). */
 int vsr_warp_nhwc_f32(const float* src, const float* flow, float* dst,
                       const float* ref, float* norm_out,
                       int B, int H, int W, int C, int bilinear, vsr_stream_t stream);

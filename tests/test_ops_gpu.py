@@ -57,6 +57,38 @@ def test_warp_fused_residual_norm(C):
     assert np.array_equal(_np(norm), want_n)
 
 
+@pytest.mark.parametrize("C", [3, 32, 5])
+def test_warp_fast_mode_within_tolerance(C):
+    """mode 2 (pipeline default): fp32 FMA weights instead of the reference's double products;
+    north star: max-abs <= 1e-3 for warps."""
+    B, H, W = 2, 45, 71
+    g = torch.Generator().manual_seed(40 + C)
+    src = torch.rand((B, H, W, C), generator=g) * 255
+    flow = synthetic.smooth_flow(B, H, W, 8.0, seed=C) + (torch.rand((B, H, W, 2), generator=g) - 0.5)
+    flow[0, 0, 0] = torch.tensor([1e9, -1e9])          # beyond 2^22: takes the conversion fallback
+    got = _np(ops.warp(src.to(DEV), flow.to(DEV), 2))
+    want = orc.warp_nhwc(src.numpy(), flow.numpy(), True)
+    assert np.abs(got - want).max() <= TOL
+    ref = torch.rand((B, H, W, C), generator=g) * 255
+    if C == 3:
+        w2, n2 = ops.warp(src.to(DEV), flow.to(DEV), 2, ref=ref.to(DEV))
+        assert np.abs(_np(n2) - orc.channelnorm_nhwc(ref.numpy() - want)).max() <= 4 * TOL
+
+
+def test_huge_and_nan_flow_take_the_exact_fallback():
+    B, H, W = 1, 9, 33
+    g = torch.Generator().manual_seed(77)
+    src = torch.rand((B, H, W, 3), generator=g) * 255
+    lab = (torch.rand((B, H, W), generator=g) * 255).to(torch.uint8)
+    flow = (torch.rand((B, H, W, 2), generator=g) - 0.5) * 6
+    flow[0, 1, 1] = torch.tensor([5e6, -5e6])
+    flow[0, 2, 2] = torch.tensor([-3e38, 3e38])
+    flow[0, 3, 3] = torch.tensor([-4194304.5, 4194303.5])
+    for mode in (True, False):
+        assert np.array_equal(_np(ops.warp(src.to(DEV), flow.to(DEV), mode)), orc.warp_nhwc(src.numpy(), flow.numpy(), mode))
+    assert np.array_equal(_np(ops.warp_labels(lab.to(DEV), flow.to(DEV))), orc.warp_labels(lab.numpy(), flow.numpy()))
+
+
 def test_warp_unaligned_views_and_ragged_tail():
     # 1 pixel short of a vector multiple, and an output carved at a non-16-byte offset
     B, H, W = 1, 17, 19

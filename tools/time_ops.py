@@ -53,8 +53,9 @@ def main():
             report(f"depth_projection B={B} {name}", timeit(lambda: ops.project_flow(f, inv)), 29 * P)
         f = flows["smooth8"].to(DEV)
         src = (torch.rand((B, h, w, 3)) * 255).to(DEV)
-        report(f"warp nhwc C=3 bilinear B={B}", timeit(lambda: ops.warp(src, f)), 32 * P)
-        report(f"warp nhwc C=3 + norm   B={B}", timeit(lambda: ops.warp(src, f, True, ref=src)), 48 * P)
+        report(f"warp nhwc C=3 exact    B={B}", timeit(lambda: ops.warp(src, f)), 32 * P)
+        report(f"warp nhwc C=3 fast     B={B}", timeit(lambda: ops.warp(src, f, 2)), 32 * P)
+        report(f"warp nhwc C=3 fast+norm B={B}", timeit(lambda: ops.warp(src, f, 2, ref=src)), 48 * P)
         src_nchw = src.permute(0, 3, 1, 2).contiguous()
         f_nchw = f.permute(0, 3, 1, 2).contiguous()
         report(f"resample2d nchw C=3    B={B}", timeit(lambda: ops.resample2d(src_nchw, f_nchw)), 32 * P)
@@ -62,7 +63,8 @@ def main():
         report(f"label warp u8          B={B}", timeit(lambda: ops.warp_labels(lab, f)), 10 * P)
         if B == 1:
             feat = torch.rand((B, h, w, 32), device=DEV)
-            report(f"warp nhwc C=32 bilinear B={B}", timeit(lambda: ops.warp(feat, f)), 264 * P)
+            report(f"warp nhwc C=32 exact B={B}", timeit(lambda: ops.warp(feat, f)), 264 * P)
+            report(f"warp nhwc C=32 fast  B={B}", timeit(lambda: ops.warp(feat, f, 2)), 264 * P)
         # plain copy reference point on this box
         a = torch.empty(P * 8, dtype=torch.float32, device=DEV)
         b = torch.empty_like(a)

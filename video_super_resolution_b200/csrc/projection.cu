@@ -25,7 +25,7 @@ namespace vsr {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kRows = 4;  // rows walked by one thread
+constexpr int kRows = 8;  // rows walked by one thread (all of their flow / depth loads are issued up front)
 
 __device__ __forceinline__ void red_add_f4(float4* addr, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
@@ -57,6 +57,22 @@ splat_kernel(const float* __restrict__ flow, const float* __restrict__ inv_depth
     int carry_t = 0;
     float4 carry = make_float4(0.f, 0.f, 0.f, 0.f);
 
+    // ncu: 48 % of this kernel's stall samples sat on the first use of the flow load -- a warp
+    // walked its rows with one dependent load per row.  Issue every row's loads first.
+    float2 fl[kRows];
+    float dp[kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      const int y = y0 + r;
+      fl[r] = make_float2(0.f, 0.f);
+      dp[r] = 1.0f;
+      if (x < w && y < h) {
+        const int64_t p = (int64_t)y * w + x;
+        fl[r] = ldg_stream_f2(reinterpret_cast<const float2*>(flow) + p);
+        if (inv_depth) dp[r] = __ldg(inv_depth + p);
+      }
+    }
+
 #pragma unroll
     for (int r = 0; r < kRows; ++r) {
       const int y = y0 + r;
@@ -64,13 +80,12 @@ splat_kernel(const float* __restrict__ flow, const float* __restrict__ inv_depth
       int xL = 0, xR = 0, yT = 0, yB = 0;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (x < w && y < h) {
-        int64_t p = (int64_t)y * w + x;
-        float2 f = ldg_stream_f2(reinterpret_cast<const float2*>(flow) + p);
+        const float2 f = fl[r];
         float x2 = __fadd_rn((float)x, f.x);
         float y2 = __fadd_rn((float)y, f.y);
         // Appendix B step 2 (the comparison form also rejects NaN)
         if (x2 >= 0.0f && x2 <= (float)(w - 1) && y2 >= 0.0f && y2 <= (float)(h - 1)) {
-          float d = inv_depth ? __ldg(inv_depth + p) : 1.0f;
+          float d = dp[r];
           valid = true;
           xL = (int)x2;
           yT = (int)y2;
@@ -123,61 +138,75 @@ splat_kernel(const float* __restrict__ flow, const float* __restrict__ inv_depth
   }
 }
 
-// Normalise + hole mask + 4-direction fill for one image.  Only non-hole pixels are read by the
-// fill, so the result does not depend on execution order (Appendix B step 4).
+// 4-direction fill of one hole pixel (Appendix B step 4): nearest non-hole pixel to the left,
+// right, up and down; mean of the found (1-4) normalised values in that order; (0,0) if none.
+// Only non-hole pixels are read, so the result does not depend on execution order.
+__device__ __forceinline__ float2 fill_hole(const float4* __restrict__ acc, int x, int y, int h, int w) {
+  float sx = 0.f, sy = 0.f;
+  int found = 0;
+  for (int xx = x - 1; xx >= 0; --xx) {
+    const float4 q = acc[y * w + xx];
+    if (q.w > 0.0f) { sx += __fdiv_rn(q.x, q.z); sy += __fdiv_rn(q.y, q.z); ++found; break; }
+  }
+  for (int xx = x + 1; xx < w; ++xx) {
+    const float4 q = acc[y * w + xx];
+    if (q.w > 0.0f) { sx += __fdiv_rn(q.x, q.z); sy += __fdiv_rn(q.y, q.z); ++found; break; }
+  }
+  for (int yy = y - 1; yy >= 0; --yy) {
+    const float4 q = acc[yy * w + x];
+    if (q.w > 0.0f) { sx += __fdiv_rn(q.x, q.z); sy += __fdiv_rn(q.y, q.z); ++found; break; }
+  }
+  for (int yy = y + 1; yy < h; ++yy) {
+    const float4 q = acc[yy * w + x];
+    if (q.w > 0.0f) { sx += __fdiv_rn(q.x, q.z); sy += __fdiv_rn(q.y, q.z); ++found; break; }
+  }
+  if (found == 0) return make_float2(0.f, 0.f);
+  return make_float2(__fdiv_rn(sx, (float)found), __fdiv_rn(sy, (float)found));
+}
+
+// Normalise + hole mask + fill for one image; kPix consecutive pixels per thread so that the four
+// accumulator loads are in flight together and every output leaves as one vector store
+// (kPix = 4: proj 2 x 16 B, wsum 16 B, count 16 B, hole 4 B).  kPix = 1 is the ragged fallback.
+template <int kPix>
 __global__ void __launch_bounds__(kThreads)
 normalise_fill_kernel(const float4* __restrict__ acc, float* __restrict__ proj, float* __restrict__ wsum,
                       int32_t* __restrict__ count, uint8_t* __restrict__ hole, int h, int w) {
-  const int n = h * w;
-  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
-    float4 a = acc[p];
-    float2 o = make_float2(0.f, 0.f);
-    const bool is_hole = !(a.w > 0.0f);
-    if (!is_hole) {
-      o.x = __fdiv_rn(a.x, a.z);
-      o.y = __fdiv_rn(a.y, a.z);
-    } else {
-      const int y = p / w, x = p - y * w;
-      float sx = 0.f, sy = 0.f;
-      int found = 0;
-      // order left, right, up, down -- the oracle sums in the same order
-      for (int xx = x - 1; xx >= 0; --xx) {
-        if (acc[y * w + xx].w > 0.0f) {
-          float4 q = acc[y * w + xx];
-          sx += __fdiv_rn(q.x, q.z); sy += __fdiv_rn(q.y, q.z); ++found;
-          break;
-        }
+  const int n = h * w / kPix;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int p0 = i * kPix;
+    float4 a[kPix];
+#pragma unroll
+    for (int k = 0; k < kPix; ++k) a[k] = acc[p0 + k];
+    float2 o[kPix];
+    float ws[kPix];
+    int32_t cn[kPix];
+    uint8_t hl[kPix];
+#pragma unroll
+    for (int k = 0; k < kPix; ++k) {
+      const bool is_hole = !(a[k].w > 0.0f);
+      if (!is_hole) {
+        o[k] = make_float2(__fdiv_rn(a[k].x, a[k].z), __fdiv_rn(a[k].y, a[k].z));
+      } else {
+        const int p = p0 + k;
+        const int y = p / w;
+        o[k] = fill_hole(acc, p - y * w, y, h, w);
       }
-      for (int xx = x + 1; xx < w; ++xx) {
-        if (acc[y * w + xx].w > 0.0f) {
-          float4 q = acc[y * w + xx];
-          sx += __fdiv_rn(q.x, q.z); sy += __fdiv_rn(q.y, q.z); ++found;
-          break;
-        }
-      }
-      for (int yy = y - 1; yy >= 0; --yy) {
-        if (acc[yy * w + x].w > 0.0f) {
-          float4 q = acc[yy * w + x];
-          sx += __fdiv_rn(q.x, q.z); sy += __fdiv_rn(q.y, q.z); ++found;
-          break;
-        }
-      }
-      for (int yy = y + 1; yy < h; ++yy) {
-        if (acc[yy * w + x].w > 0.0f) {
-          float4 q = acc[yy * w + x];
-          sx += __fdiv_rn(q.x, q.z); sy += __fdiv_rn(q.y, q.z); ++found;
-          break;
-        }
-      }
-      if (found > 0) {
-        o.x = __fdiv_rn(sx, (float)found);
-        o.y = __fdiv_rn(sy, (float)found);
-      }
+      ws[k] = is_hole ? 0.0f : a[k].z;
+      cn[k] = (int32_t)a[k].w;
+      hl[k] = is_hole ? 1 : 0;
     }
-    reinterpret_cast<float2*>(proj)[p] = o;
-    if (wsum) wsum[p] = is_hole ? 0.0f : a.z;
-    count[p] = (int32_t)a.w;
-    hole[p] = is_hole ? 1 : 0;
+    if (kPix == 4) {
+      reinterpret_cast<float4*>(proj)[2 * i] = make_float4(o[0].x, o[0].y, o[1 % kPix].x, o[1 % kPix].y);
+      reinterpret_cast<float4*>(proj)[2 * i + 1] = make_float4(o[2 % kPix].x, o[2 % kPix].y, o[3 % kPix].x, o[3 % kPix].y);
+      if (wsum) reinterpret_cast<float4*>(wsum)[i] = make_float4(ws[0], ws[1 % kPix], ws[2 % kPix], ws[3 % kPix]);
+      reinterpret_cast<int4*>(count)[i] = make_int4(cn[0], cn[1 % kPix], cn[2 % kPix], cn[3 % kPix]);
+      reinterpret_cast<uchar4*>(hole)[i] = make_uchar4(hl[0], hl[1 % kPix], hl[2 % kPix], hl[3 % kPix]);
+    } else {
+      reinterpret_cast<float2*>(proj)[p0] = o[0];
+      if (wsum) wsum[p0] = ws[0];
+      count[p0] = cn[0];
+      hole[p0] = hl[0];
+    }
   }
 }
 
@@ -206,7 +235,12 @@ extern "C" int vsr_flow_projection_forward(const float* flow, const float* inv_d
   const int64_t P = (int64_t)h * w;
   const int n_tasks = ceil_div(w, 32) * ceil_div(h, kRows);
   int splat_blocks = ceil_div(n_tasks, kThreads / 32);
-  int norm_blocks = (int)ceil_div64(P, kThreads);
+  const uintptr_t al = reinterpret_cast<uintptr_t>(proj) | reinterpret_cast<uintptr_t>(count) |
+                       (wsum ? reinterpret_cast<uintptr_t>(wsum) : 0);
+  // measured on B200: 4 pixels per thread is SLOWER (52 -> 70 us per 1080p image; 3x slower on hole-heavy
+  // scenes, where the serial fill loops of one thread add up) -- kept for reference, not used.
+  const bool vec4 = false && (P % 4 == 0) && (al % 16 == 0) && (reinterpret_cast<uintptr_t>(hole) % 4 == 0);
+  int norm_blocks = (int)ceil_div64(vec4 ? P / 4 : P, kThreads);
   const int cap = kNumSMs * 8 * 4;
   if (norm_blocks > cap) norm_blocks = cap;
   for (int b = 0; b < B; ++b) {
@@ -216,8 +250,12 @@ extern "C" int vsr_flow_projection_forward(const float* flow, const float* inv_d
                                                     w);
     int rc = after_launch();
     if (rc) return rc;
-    normalise_fill_kernel<<<norm_blocks, kThreads, 0, st>>>(acc, proj + b * P * 2, wsum ? wsum + b * P : nullptr,
-                                                            count + b * P, hole + b * P, h, w);
+    if (vec4)
+      normalise_fill_kernel<4><<<norm_blocks, kThreads, 0, st>>>(acc, proj + b * P * 2, wsum ? wsum + b * P : nullptr,
+                                                                 count + b * P, hole + b * P, h, w);
+    else
+      normalise_fill_kernel<1><<<norm_blocks, kThreads, 0, st>>>(acc, proj + b * P * 2, wsum ? wsum + b * P : nullptr,
+                                                                 count + b * P, hole + b * P, h, w);
     rc = after_launch();
     if (rc) return rc;
   }

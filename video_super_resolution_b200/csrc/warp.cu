@@ -19,23 +19,55 @@ struct Taps {
   int xL, xR, yT, yB;
   double wTL, wTR, wBL;
   float wBR;
+  float af, bf;   // alpha, beta in fp32 (fast mode)
 };
+
+// `bilinear` argument of the channels-last entry points
+constexpr int kModeNearest = 0, kModeExact = 1, kModeFast = 2;
+
+// floor() and float->int without the conversion (XU) pipe, which ncu showed to be the busiest pipe of
+// these kernels (55-77 %): for |v| < 2^22 adding and subtracting 1.5*2^23 rounds to an integer on the
+// FMA pipe, one compare fixes round-to-nearest into floor, and the integer is read off the mantissa.
+// Exact, so the bit-for-bit contract holds; larger magnitudes / NaN take the conversion instructions.
+__device__ __forceinline__ float floor_small(float v, bool& ok) {
+  ok = fabsf(v) < 4194304.0f;
+  const float r = __fsub_rn(__fadd_rn(v, 12582912.0f), 12582912.0f);
+  return r > v ? __fsub_rn(r, 1.0f) : r;
+}
+__device__ __forceinline__ int int_of_small(float r) {   // r integral, |r| <= 2^22
+  return __float_as_int(__fadd_rn(r, 12582912.0f)) - 0x4B400000;
+}
 
 // resample2d_kernel.cu:40-52: fp32 coordinates, floor, border clamp with the output dims;
 // :56-58: the `1.` literals make the TL/TR/BL weights (and products) doubles; :59 the BR term
 // `(alpha)*(beta) * in` has no literal, so it is fp32 and nvcc contracts `val += ...` into an FMA
 // (verified in the SASS of the reference compiled for sm_100a: FMUL alpha*beta, FFMA).
+template <bool FAST = false>
 __device__ __forceinline__ Taps bilinear_taps(int x, int y, float dx, float dy, int W, int H) {
   Taps t;
   float xf = __fadd_rn((float)x, dx);
   float yf = __fadd_rn((float)y, dy);
-  float fx0 = floorf(xf), fy0 = floorf(yf);
+  bool okx, oky;
+  float fx0 = floor_small(xf, okx), fy0 = floor_small(yf, oky);
+  if (okx && oky) {
+    const int ix = int_of_small(fx0), iy = int_of_small(fy0);
+    t.xL = max(min(ix, W - 1), 0);
+    t.xR = max(min(ix + 1, W - 1), 0);
+    t.yT = max(min(iy, H - 1), 0);
+    t.yB = max(min(iy + 1, H - 1), 0);
+  } else {
+    fx0 = floorf(xf);
+    fy0 = floorf(yf);
+    t.xL = max(min((int)fx0, W - 1), 0);
+    t.xR = max(min((int)__fadd_rn(fx0, 1.0f), W - 1), 0);
+    t.yT = max(min((int)fy0, H - 1), 0);
+    t.yB = max(min((int)__fadd_rn(fy0, 1.0f), H - 1), 0);
+  }
   float alpha_f = __fsub_rn(xf, fx0), beta_f = __fsub_rn(yf, fy0);
+  t.af = alpha_f;
+  t.bf = beta_f;
+  if (FAST) return t;
   double alpha = (double)alpha_f, beta = (double)beta_f;
-  t.xL = max(min((int)fx0, W - 1), 0);
-  t.xR = max(min((int)__fadd_rn(fx0, 1.0f), W - 1), 0);
-  t.yT = max(min((int)fy0, H - 1), 0);
-  t.yB = max(min((int)__fadd_rn(fy0, 1.0f), H - 1), 0);
   double ia = __dsub_rn(1.0, alpha), ib = __dsub_rn(1.0, beta);
   t.wTL = __dmul_rn(ia, ib);
   t.wTR = __dmul_rn(alpha, ib);
@@ -54,12 +86,35 @@ __device__ __forceinline__ float blend(const Taps& t, float tl, float tr, float 
   return v;
 }
 
-// :65-70 `floor(xf + 0.5)`: the literal promotes to double; ties go up.
+// Fast mode (pipeline default): the same taps and border rule, weights and products in fp32 FMAs.
+// Differs from the reference's mixed double/float sequence by a few fp32 ulps (<= 1e-4 on 0..255
+// data; the north star allows 1e-3 for warps) and needs no fp64 conversion at all.
+__device__ __forceinline__ float blend_fast(const Taps& t, float tl, float tr, float bl, float br) {
+  const float ia = 1.0f - t.af, ib = 1.0f - t.bf;
+  float top = fmaf(t.af, tr, ia * tl);
+  float bot = fmaf(t.af, br, ia * bl);
+  return fmaf(t.bf, bot, ib * top);
+}
+template <bool FAST>
+__device__ __forceinline__ float blend_mode(const Taps& t, float tl, float tr, float bl, float br) {
+  return FAST ? blend_fast(t, tl, tr, bl, br) : blend(t, tl, tr, bl, br);
+}
+
+// :65-70 `floor(xf + 0.5)`: the literal promotes to double; ties go up.  floor(xf + 0.5) evaluated
+// exactly equals floor(xf) + (xf - floor(xf) >= 0.5): the subtraction is exact in fp32, so the fp32
+// form below returns the reference's integer without touching the fp64 / conversion pipes.
 __device__ __forceinline__ void nearest_tap(int x, int y, float dx, float dy, int W, int H, int& xN, int& yN) {
   float xf = __fadd_rn((float)x, dx);
   float yf = __fadd_rn((float)y, dy);
-  xN = max(min((int)floor(__dadd_rn((double)xf, 0.5)), W - 1), 0);
-  yN = max(min((int)floor(__dadd_rn((double)yf, 0.5)), H - 1), 0);
+  bool okx, oky;
+  const float fx0 = floor_small(xf, okx), fy0 = floor_small(yf, oky);
+  if (okx && oky) {
+    xN = max(min(int_of_small(fx0) + (__fsub_rn(xf, fx0) >= 0.5f ? 1 : 0), W - 1), 0);
+    yN = max(min(int_of_small(fy0) + (__fsub_rn(yf, fy0) >= 0.5f ? 1 : 0), H - 1), 0);
+  } else {
+    xN = max(min((int)floor(__dadd_rn((double)xf, 0.5)), W - 1), 0);
+    yN = max(min((int)floor(__dadd_rn((double)yf, 0.5)), H - 1), 0);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -102,6 +157,7 @@ resample2d_nchw_kernel(const float* __restrict__ in1, const float* __restrict__ 
 // shared memory and leave as 192 coalesced float4 stores.  Optional fused residual norm
 // sqrt(sum_c (ref - warped)^2) (models.py:86-88 = resample -> subtract -> channelnorm).
 // ---------------------------------------------------------------------------------------------
+template <bool FAST>
 __global__ void __launch_bounds__(kThreads)
 warp_nhwc3_kernel(const float* __restrict__ src, const float* __restrict__ flow, float* __restrict__ dst,
                   const float* __restrict__ ref, float* __restrict__ norm_out,
@@ -118,14 +174,14 @@ warp_nhwc3_kernel(const float* __restrict__ src, const float* __restrict__ flow,
       float2 f = ldg_stream_f2(reinterpret_cast<const float2*>(flow) + i);
       const float* s = src + b * HW * 3;
       if (bilinear) {
-        Taps t = bilinear_taps(x, y, f.x, f.y, W, H);
+        Taps t = bilinear_taps<FAST>(x, y, f.x, f.y, W, H);
         const float* pTL = s + ((int64_t)t.yT * W + t.xL) * 3;
         const float* pTR = s + ((int64_t)t.yT * W + t.xR) * 3;
         const float* pBL = s + ((int64_t)t.yB * W + t.xL) * 3;
         const float* pBR = s + ((int64_t)t.yB * W + t.xR) * 3;
-        v0 = blend(t, __ldg(pTL + 0), __ldg(pTR + 0), __ldg(pBL + 0), __ldg(pBR + 0));
-        v1 = blend(t, __ldg(pTL + 1), __ldg(pTR + 1), __ldg(pBL + 1), __ldg(pBR + 1));
-        v2 = blend(t, __ldg(pTL + 2), __ldg(pTR + 2), __ldg(pBL + 2), __ldg(pBR + 2));
+        v0 = blend_mode<FAST>(t, __ldg(pTL + 0), __ldg(pTR + 0), __ldg(pBL + 0), __ldg(pBR + 0));
+        v1 = blend_mode<FAST>(t, __ldg(pTL + 1), __ldg(pTR + 1), __ldg(pBL + 1), __ldg(pBR + 1));
+        v2 = blend_mode<FAST>(t, __ldg(pTL + 2), __ldg(pTR + 2), __ldg(pBL + 2), __ldg(pBR + 2));
       } else {
         int xN, yN;
         nearest_tap(x, y, f.x, f.y, W, H, xN, yN);
@@ -168,6 +224,7 @@ warp_nhwc3_kernel(const float* __restrict__ src, const float* __restrict__ flow,
 // gathers and one 16-byte coalesced store; the C/4 lanes of a pixel share taps through the
 // broadcast of the flow load.
 // ---------------------------------------------------------------------------------------------
+template <bool FAST>
 __global__ void __launch_bounds__(kThreads)
 warp_nhwc_vec4_kernel(const float* __restrict__ src, const float* __restrict__ flow, float* __restrict__ dst,
                       int64_t n_pix, int H, int W, int C, int bilinear) {
@@ -184,15 +241,15 @@ warp_nhwc_vec4_kernel(const float* __restrict__ src, const float* __restrict__ f
     const float4* s = reinterpret_cast<const float4*>(src + b * HW * C) + g;
     float4 o;
     if (bilinear) {
-      Taps t = bilinear_taps(x, y, f.x, f.y, W, H);
+      Taps t = bilinear_taps<FAST>(x, y, f.x, f.y, W, H);
       float4 tl = __ldg(s + ((int64_t)t.yT * W + t.xL) * G);
       float4 tr = __ldg(s + ((int64_t)t.yT * W + t.xR) * G);
       float4 bl = __ldg(s + ((int64_t)t.yB * W + t.xL) * G);
       float4 br = __ldg(s + ((int64_t)t.yB * W + t.xR) * G);
-      o.x = blend(t, tl.x, tr.x, bl.x, br.x);
-      o.y = blend(t, tl.y, tr.y, bl.y, br.y);
-      o.z = blend(t, tl.z, tr.z, bl.z, br.z);
-      o.w = blend(t, tl.w, tr.w, bl.w, br.w);
+      o.x = blend_mode<FAST>(t, tl.x, tr.x, bl.x, br.x);
+      o.y = blend_mode<FAST>(t, tl.y, tr.y, bl.y, br.y);
+      o.z = blend_mode<FAST>(t, tl.z, tr.z, bl.z, br.z);
+      o.w = blend_mode<FAST>(t, tl.w, tr.w, bl.w, br.w);
     } else {
       int xN, yN;
       nearest_tap(x, y, f.x, f.y, W, H, xN, yN);
@@ -224,7 +281,8 @@ warp_nhwc_generic_kernel(const float* __restrict__ src, const float* __restrict_
       const float* pBL = s + ((int64_t)t.yB * W + t.xL) * C;
       const float* pBR = s + ((int64_t)t.yB * W + t.xR) * C;
       for (int c = 0; c < C; ++c) {
-        float v = blend(t, __ldg(pTL + c), __ldg(pTR + c), __ldg(pBL + c), __ldg(pBR + c));
+        float v = bilinear == kModeFast ? blend_fast(t, __ldg(pTL + c), __ldg(pTR + c), __ldg(pBL + c), __ldg(pBR + c))
+                                        : blend(t, __ldg(pTL + c), __ldg(pTR + c), __ldg(pBL + c), __ldg(pBR + c));
         o[c] = v;
         if (norm_out != nullptr) {
           float d = __fsub_rn(__ldg(ref + i * C + c), v);
@@ -340,16 +398,25 @@ extern "C" int vsr_warp_nhwc_f32(const float* src, const float* flow, float* dst
   if (!aligned(flow, 8)) return VSR_ERR_INVALID_ARG;
   int64_t n_pix = (int64_t)B * H * W;
   cudaStream_t st = as_stream(stream);
+  if (bilinear < 0 || bilinear > kModeFast) return VSR_ERR_INVALID_ARG;
   if (C == 3) {
     int vec = aligned(dst, 16) ? 1 : 0;
-    warp_nhwc3_kernel<<<grid_for(n_pix, kThreads), kThreads, 0, st>>>(src, flow, dst, ref, norm_out, n_pix, H, W,
-                                                                      bilinear ? 1 : 0, vec);
+    if (bilinear == kModeFast)
+      warp_nhwc3_kernel<true><<<grid_for(n_pix, kThreads), kThreads, 0, st>>>(src, flow, dst, ref, norm_out, n_pix, H, W,
+                                                                              1, vec);
+    else
+      warp_nhwc3_kernel<false><<<grid_for(n_pix, kThreads), kThreads, 0, st>>>(src, flow, dst, ref, norm_out, n_pix, H,
+                                                                               W, bilinear, vec);
   } else if ((C % 4) == 0 && norm_out == nullptr && aligned(src, 16) && aligned(dst, 16)) {
-    warp_nhwc_vec4_kernel<<<grid_for(n_pix * (C / 4), kThreads), kThreads, 0, st>>>(src, flow, dst, n_pix, H, W, C,
-                                                                                    bilinear ? 1 : 0);
+    if (bilinear == kModeFast)
+      warp_nhwc_vec4_kernel<true><<<grid_for(n_pix * (C / 4), kThreads), kThreads, 0, st>>>(src, flow, dst, n_pix, H, W,
+                                                                                            C, 1);
+    else
+      warp_nhwc_vec4_kernel<false><<<grid_for(n_pix * (C / 4), kThreads), kThreads, 0, st>>>(src, flow, dst, n_pix, H,
+                                                                                             W, C, bilinear);
   } else {
     warp_nhwc_generic_kernel<<<grid_for(n_pix, kThreads), kThreads, 0, st>>>(src, flow, dst, ref, norm_out, n_pix, H,
-                                                                             W, C, bilinear ? 1 : 0);
+                                                                             W, C, bilinear);
   }
   return after_launch();
 }

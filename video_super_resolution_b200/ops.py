@@ -56,9 +56,10 @@ def resample2d(input1: torch.Tensor, flow: torch.Tensor, kernel_size: int = 1, b
     return out
 
 
-def warp(src: torch.Tensor, flow: torch.Tensor, bilinear: bool = True, ref: torch.Tensor | None = None):
+def warp(src: torch.Tensor, flow: torch.Tensor, bilinear: bool | int = True, ref: torch.Tensor | None = None):
     """Channels-last warp: src (B,H,W,C), flow (B,H,W,2) -> (B,H,W,C).  With `ref` (B,H,W,C) also
-    returns the per-pixel L2 norm of (ref - warped), (B,H,W) (models.py:86-88 fused)."""
+    returns the per-pixel L2 norm of (ref - warped), (B,H,W) (models.py:86-88 fused).
+    bilinear: False/0 nearest, True/1 the reference arithmetic bit for bit, 2 fast fp32 (<= 1e-3)."""
     _req(src, torch.float32, "src")
     _req(flow, torch.float32, "flow")
     B, H, W, C = src.shape
@@ -75,7 +76,7 @@ def warp(src: torch.Tensor, flow: torch.Tensor, bilinear: bool = True, ref: torc
         _lib.check(_lib.lib().vsr_warp_nhwc_f32(src.data_ptr(), flow.data_ptr(), dst.data_ptr(),
                                                 ref.data_ptr() if ref is not None else None,
                                                 norm.data_ptr() if norm is not None else None,
-                                                B, H, W, C, int(bool(bilinear)), _stream()), "warp")
+                                                B, H, W, C, int(bilinear), _stream()), "warp")
     return dst if ref is None else (dst, norm)
 
 

@@ -55,7 +55,7 @@ class WarpFusePipeline:
         proj_d, wsum, cnt_d, hole_d = ops.project_depth_flow(flows, inv_depth)
         neigh = frames[self._neigh].contiguous()
         ref = frames[c].unsqueeze(0).expand(T - 1, -1, -1, -1).contiguous()
-        warped, resid = ops.warp(neigh, proj_d, True, ref=ref)
+        warped, resid = ops.warp(neigh, proj_d, 2, ref=ref)      # fast fp32 blend (north star: <= 1e-3)
         mask = ops.vos_threshold(logits_a, logits_b)
         mask_w = ops.warp_labels(mask.unsqueeze(0), proj_d[min(c, T - 2)].unsqueeze(0))[0]
         ops.assemble_stack(warped, frames[c], proj_f, resid, wsum, estimate, c, out=self.stack)
