@@ -46,6 +46,18 @@ def test_pointwise_layer(rows, K):
     _close(got, want, f"pointwise rows={rows} K={K}")
 
 
+@pytest.mark.parametrize("slope", [0.0, 1.0, 1.7, -0.3])
+def test_pointwise_prelu_slope_forms(slope):
+    """The packed-BF16 PReLU picks max/min/general forms by the (per-layer) slope."""
+    g = torch.Generator().manual_seed(3)
+    x = _bf(torch.randn((777, 64), generator=g))
+    w = _bf(torch.randn((32, 64), generator=g) / 8).float()
+    b = torch.randn(32, generator=g) * 0.1
+    got = hk.pointwise(x.to(DEV), w, b, slope)
+    want = F.prelu(x.float() @ w.t() + b, torch.tensor([slope]))
+    _close(got, want, f"pointwise slope={slope}")
+
+
 @pytest.mark.parametrize("B,h,w", [(1, 8, 16), (2, 5, 7), (1, 19, 33)])
 @pytest.mark.parametrize("block", [False, True])
 def test_deconv_layer(B, h, w, block):

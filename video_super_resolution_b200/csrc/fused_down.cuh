@@ -49,7 +49,9 @@ struct alignas(64) FusedDownParams {
   int32_t tiles_x, tiles_y, batch;
   int32_t lr_h, lr_w;
   int32_t prefetch_ahead;             // L2 prefetch distance in half-tiles
-  int32_t debug;                      // bring-up knob: bit0 = do not issue the phase-A MMAs
+  int32_t debug;                      // timing experiments (results become wrong): bit0 skip phase-A MMAs, bit1 skip
+                                      // the TMEM reads + conversion of phase A, bit2 skip the final TMEM reads/stores,
+                                      // bit3 skip phase-B MMAs
   const float* tran_bias;             // [32] biases + [1] PReLU slope of the downtran
   float* part;                        // (B, h, w, 4 slots, 32) fp32 partial sums (see final epilogue)
 };
@@ -220,6 +222,10 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    // One thread runs the whole role (no warp-wide waits / __syncwarp per box): timing experiments
+    // showed this thread's instruction stream to be co-critical with HBM (each box costs it a barrier
+    // wait, four MMA issues and a commit), so descriptors are pre-built and only offsets are added.
+    if (lane == 0) {
     constexpr uint32_t idesc_a = make_idesc(32);
     constexpr uint32_t idesc_b = make_idesc(128);
     if (HAS_TRAN) mbar_wait(w_full, 0);
@@ -228,6 +234,12 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
     uint32_t phase = 0;
     uint32_t n_a[2] = {0, 0}, n_b[2] = {0, 0}, n_h = 0, n_wd = 0;
     int tb = 0;
+    // matrix descriptors: the start-address field is bits [0,14) in 16-byte units, so an offset of
+    // `off` bytes inside the same buffer is a plain add of off >> 4
+    const uint64_t dA = make_smem_desc<128>(smem_u32(s_a));
+    const uint64_t dWt = make_smem_desc<64>(smem_u32(s_wt));
+    const uint64_t dH = make_smem_desc<128>(smem_u32(s_h));
+    const uint64_t dWd = make_smem_desc<128>(smem_u32(s_wd));
 
     // phase A of sub-position group g: D_A[g&1] = sum_j A(s, j) * Wt_j^T for the 4 sub-positions
     auto issue_a = [&](int g) {
@@ -238,57 +250,50 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
         for (int j = 0; j < p.nsrc; ++j) {
           mbar_wait(&full_bar[s], phase);
           tc_fence_after();
-          if (lane == 0) {
-            const uint32_t a_addr = smem_u32(s_a + s * kStageBytes);
-            const uint32_t b_addr = smem_u32(s_wt + j * kWtChunkBytes);
-            if (!(p.debug & 1))
-#pragma unroll
-            for (int sl2 = 0; sl2 < 2; ++sl2) {
-              const uint32_t d = tmem_base + (uint32_t)(buf * 128 + (pair * 2 + sl2) * 32);
-#pragma unroll
-              for (int k = 0; k < 2; ++k)
-                umma_bf16(d, make_smem_desc<128>(a_addr + sl2 * 64 + k * 32), make_smem_desc<64>(b_addr + k * 32),
-                          idesc_a, (uint32_t)((j | k) != 0));
-            }
-            umma_commit(&empty_bar[s]);
+          const uint64_t a0 = dA + (uint64_t)((s * kStageBytes) >> 4);
+          const uint64_t b0 = dWt + (uint64_t)((j * kWtChunkBytes) >> 4);
+          const uint32_t d0 = tmem_base + (uint32_t)(buf * 128 + pair * 64);
+          if (!(p.debug & 1)) {
+            const uint32_t acc = (uint32_t)(j != 0);
+            umma_bf16(d0, a0, b0, idesc_a, acc);
+            umma_bf16(d0, a0 + 2, b0 + 2, idesc_a, 1u);
+            umma_bf16(d0 + 32, a0 + 4, b0, idesc_a, acc);
+            umma_bf16(d0 + 32, a0 + 6, b0 + 2, idesc_a, 1u);
           }
-          __syncwarp();
+          umma_commit(&empty_bar[s]);
           if (++s == p.num_stages) { s = 0; phase ^= 1; }
         }
-      if (lane == 0) umma_commit(&da_full[buf]);
-      __syncwarp();
+      umma_commit(&da_full[buf]);
       ++n_a[buf];
     };
     // phase B of group g: D_B[tb] += H_g * Wd_g^T
     auto issue_b = [&](int g) {
-      uint32_t a_addr;
+      uint64_t a0;
       if (HAS_TRAN) {
         mbar_wait(h_full, n_h & 1);
-        a_addr = smem_u32(s_h);
+        a0 = dH;
       } else {
         mbar_wait(&full_bar[s], phase);
-        a_addr = smem_u32(s_a + s * kStageBytes);
+        a0 = dA + (uint64_t)((s * kStageBytes) >> 4);
       }
       if (g == 0) mbar_wait(&db_empty[tb], (n_b[tb] & 1) ^ 1);
       const int wslot = n_wd & 1;
       mbar_wait(&wd_full[wslot], (n_wd >> 1) & 1);
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t d = tmem_base + kDB + (uint32_t)(tb * 128);
+      const uint32_t d = tmem_base + kDB + (uint32_t)(tb * 128);
+      const uint64_t b0 = dWd + (uint64_t)((wslot * kWdGroupBytes) >> 4);
+      if (!(p.debug & 8)) {
 #pragma unroll
-        for (int kc = 0; kc < 2; ++kc) {
-          const uint32_t b_addr = smem_u32(s_wd + wslot * kWdGroupBytes + kc * 16384);
+        for (int kc = 0; kc < 2; ++kc)
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(d, make_smem_desc<128>(a_addr + kc * 16384 + k * 32), make_smem_desc<128>(b_addr + k * 32),
-                      idesc_b, (uint32_t)((g | kc | k) != 0));
-        }
-        umma_commit(&wd_empty[wslot]);
-        if (HAS_TRAN) umma_commit(h_empty);
-        else umma_commit(&empty_bar[s]);
-        if (g == 3) umma_commit(&db_full[tb]);
+            umma_bf16(d, a0 + (uint64_t)(kc * 1024 + k * 2), b0 + (uint64_t)(kc * 1024 + k * 2), idesc_b,
+                      (uint32_t)((g | kc | k) != 0));
       }
-      __syncwarp();
+      umma_commit(&wd_empty[wslot]);
+      if (HAS_TRAN) umma_commit(h_empty);
+      else umma_commit(&empty_bar[s]);
+      if (g == 3) umma_commit(&db_full[tb]);
       ++n_wd;
       if (HAS_TRAN) ++n_h;
       else if (++s == p.num_stages) { s = 0; phase ^= 1; }
@@ -308,6 +313,7 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
       } else {
         for (int g = 0; g < 4; ++g) issue_b(g);
       }
+    }
     }
   } else if (warp == kFusedWdWarp) {
     // ===================== conv-weight streamer =====================
@@ -336,8 +342,7 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t m_a[2] = {0, 0}, m_b[2] = {0, 0}, m_h = 0;
     int tb = 0;
-    const float slope = HAS_TRAN ? s_bias[32] : 1.0f;
-    const __nv_bfloat162 slope2 = __floats2bfloat162_rn(slope, slope);
+    const PreluCfg pc = make_prelu(HAS_TRAN ? s_bias[32] : 1.0f, 1);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       int x0, y0, b;
       tile_coord(tile, x0, y0, b);
@@ -350,7 +355,11 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
           mbar_wait(&da_full[buf], m_a[buf] & 1);
           tc_fence_after();
           uint32_t o[16];
-          {
+          if (p.debug & 2) {
+            zero16(o);
+            tc_fence_before();
+            mbar_arrive(&da_empty[buf]);
+          } else {
             uint32_t v[32];
             tmem_ld32(lane_base + (uint32_t)(buf * 128 + sub * 32), v);
             tmem_ld_wait();
@@ -359,7 +368,8 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
             const int s16 = g * 4 + sub, ry = s16 >> 2, rx = s16 & 3;
             const bool ring = (Yb == 0 && ry < 2) || (Yb == p.lr_h && ry >= 2) || (Xb == 0 && rx < 2) ||
                               (Xb == p.lr_w && rx >= 2);
-            convert32(v, s_bias, slope2, in_tensor && !ring, o);
+            if (in_tensor && !ring) convert32(v, s_bias, pc, o);
+            else zero16(o);
           }
           ++m_a[buf];
           mbar_wait(h_empty, (m_h & 1) ^ 1);
@@ -384,7 +394,10 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
       //                                                   (only pixels with X % 16 == 15 have one)
       mbar_wait(&db_full[tb], m_b[tb] & 1);
       tc_fence_after();
-      {
+      if (p.debug & 4) {
+        tc_fence_before();
+        mbar_arrive(&db_empty[tb]);
+      } else {
         uint32_t v[4][8];
 #pragma unroll
         for (int t = 0; t < 4; ++t) tmem_ld8(lane_base + kDB + (uint32_t)(tb * 128 + t * 32 + sub * 8), v[t]);

@@ -25,7 +25,7 @@ namespace vsr {
 constexpr int kTileM = 128;          // UMMA M
 constexpr int kMaxChunks = 72;       // K chunks per tile (downconv: 32 with CK=64, 64 with CK=32)
 constexpr int kMaxSources = 6;       // concatenated A sources (downtran of group 5)
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 16;
 constexpr int kIgemmThreads = 192;   // 6 warps: producer, MMA, 4 epilogue (EPI_ROWS / EPI_CONV_OUT)
 constexpr int kDeconvEpiWarps = 16;  // EPI_DECONV: 4 warps per TMEM lane quarter, 2 sub-positions each
 constexpr int kDeconvThreads = 64 + 32 * kDeconvEpiWarps;
@@ -47,6 +47,7 @@ struct Chunk {
 struct alignas(64) IgemmParams {
   CUtensorMap a_maps[kMaxSources];
   CUtensorMap b_map;
+  CUtensorMap out_map;         // EPI_DECONV block layout: 4-D (64 el, 8 sub-position pairs, w+1, (h+1)*B), box (64,1,16,1), 128B swizzle
   Chunk chunks[kMaxChunks];
   int32_t num_chunks;
   int32_t num_stages;
@@ -115,6 +116,17 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+
+// TMA store: shared (128B-swizzled tile) -> global, completion tracked by the thread's bulk groups
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -189,26 +201,49 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 __device__ __forceinline__ float prelu(float v, float slope, int act) { return (act && v < 0.0f) ? v * slope : v; }
-// Two activations at once: round to BF16, then PReLU in packed BF16 (max(x,0) + slope*min(x,0), one
-// rounding of the product) -- 2 instructions per element instead of 4.5.  slope2 = (1,1) is identity.
-__device__ __forceinline__ uint32_t prelu_pack(float a, float b, __nv_bfloat162 slope2) {
+// Two activations at once: round to BF16, then PReLU in packed BF16.  For a slope in [0,1]
+// PReLU(x) = max(x, slope*x); for a slope > 1 it is min(x, slope*x); a negative slope needs the
+// general form max(x,0) + slope*min(x,0).  The slope is uniform per layer, so the form is chosen
+// once per kernel (`mode`) and the common case costs 2 packed instructions per pair.
+struct PreluCfg {
+  __nv_bfloat162 slope2;
+  int mode;   // 0: max(x, s*x)   1: min(x, s*x)   2: general   3: identity
+};
+__device__ __forceinline__ PreluCfg make_prelu(float slope, int act) {
+  PreluCfg c;
+  c.slope2 = __floats2bfloat162_rn(slope, slope);
+  c.mode = !act ? 3 : (slope >= 0.0f && slope <= 1.0f) ? 0 : (slope > 1.0f ? 1 : 2);
+  return c;
+}
+__device__ __forceinline__ uint32_t prelu_pack(float a, float b, const PreluCfg& c) {
   const __nv_bfloat162 x = __floats2bfloat162_rn(a, b);
-  const __nv_bfloat162 z = __floats2bfloat162_rn(0.0f, 0.0f);
-  const __nv_bfloat162 r = __hfma2(__hmin2(x, z), slope2, __hmax2(x, z));
+  __nv_bfloat162 r;
+  if (c.mode == 0) {
+    r = __hmax2(x, __hmul2(x, c.slope2));
+  } else if (c.mode == 3) {
+    r = x;
+  } else if (c.mode == 1) {
+    r = __hmin2(x, __hmul2(x, c.slope2));
+  } else {
+    const __nv_bfloat162 z = __floats2bfloat162_rn(0.0f, 0.0f);
+    r = __hfma2(__hmin2(x, z), c.slope2, __hmax2(x, z));
+  }
   return *reinterpret_cast<const uint32_t*>(&r);
 }
 // 32 accumulator columns -> 16 packed BF16 pairs with bias (fp32 add) and PReLU
-__device__ __forceinline__ void convert32(const uint32_t (&v)[32], const float* bias, __nv_bfloat162 slope2, bool keep,
+__device__ __forceinline__ void convert32(const uint32_t (&v)[32], const float* bias, const PreluCfg& c,
                                           uint32_t (&o)[16]) {
   const float4* b4 = reinterpret_cast<const float4*>(bias);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const float4 bb = b4[j];
-    const uint32_t lo = prelu_pack(__uint_as_float(v[4 * j]) + bb.x, __uint_as_float(v[4 * j + 1]) + bb.y, slope2);
-    const uint32_t hi = prelu_pack(__uint_as_float(v[4 * j + 2]) + bb.z, __uint_as_float(v[4 * j + 3]) + bb.w, slope2);
-    o[2 * j] = keep ? lo : 0u;
-    o[2 * j + 1] = keep ? hi : 0u;
+    o[2 * j] = prelu_pack(__uint_as_float(v[4 * j]) + bb.x, __uint_as_float(v[4 * j + 1]) + bb.y, c);
+    o[2 * j + 1] = prelu_pack(__uint_as_float(v[4 * j + 2]) + bb.z, __uint_as_float(v[4 * j + 3]) + bb.w, c);
   }
+}
+__device__ __forceinline__ void zero16(uint32_t (&o)[16]) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) o[j] = 0u;
 }
 
 struct TileCoord {
@@ -317,36 +352,34 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = make_idesc(BN);
-    mbar_wait(b_full, 0);
-    tc_fence_after();
-    int s = 0;
-    uint32_t phase = 0;
-    int as = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      mbar_wait(&tmem_empty[as], acc_phase ^ 1);
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN);
+      mbar_wait(b_full, 0);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
-      for (int kc = 0; kc < p.num_chunks; ++kc) {
-        mbar_wait(&full_bar[s], phase);
+      int s = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t acc_phase = 0;
+      const uint64_t dA = make_smem_desc<kSwz>(smem_u32(smem_a));
+      const uint64_t dB = make_smem_desc<kSwz>(smem_u32(smem_b));
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[as], acc_phase ^ 1);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_addr = smem_u32(smem_a + s * kABytes);
-          const uint32_t b_addr = smem_u32(smem_b + kc * kBBytes);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        for (int kc = 0; kc < p.num_chunks; ++kc) {
+          mbar_wait(&full_bar[s], phase);
+          tc_fence_after();
+          const uint64_t a0 = dA + (uint64_t)((s * kABytes) >> 4);
+          const uint64_t b0 = dB + (uint64_t)((kc * kBBytes) >> 4);
 #pragma unroll
-          for (int k = 0; k < CK / 16; ++k) {
-            umma_bf16(d_tmem, make_smem_desc<kSwz>(a_addr + k * 32), make_smem_desc<kSwz>(b_addr + k * 32), idesc,
-                      (uint32_t)((kc | k) != 0));
-          }
+          for (int k = 0; k < CK / 16; ++k) umma_bf16(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, (uint32_t)((kc | k) != 0));
           umma_commit(&empty_bar[s]);                      // frees the A slot when these MMAs retire
           if (kc == p.num_chunks - 1) umma_commit(&tmem_full[as]);
+          if (++s == p.num_stages) { s = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++s == p.num_stages) { s = 0; phase ^= 1; }
+        if (++as == 2) { as = 0; acc_phase ^= 1; }
       }
-      if (++as == 2) { as = 0; acc_phase ^= 1; }
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
@@ -380,8 +413,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
           valid = (y < p.out_h) && (x < p.out_w);
           dst = reinterpret_cast<uint8_t*>(p.out) + (((int64_t)t.b * p.out_h + y) * p.out_w + x) * p.out_pitch + p.out_off;
         }
-        const float slope = p.act ? s_bias[p.bias_n] : 1.0f;
-        const __nv_bfloat162 slope2 = __floats2bfloat162_rn(slope, slope);
+        const PreluCfg pc = make_prelu(s_bias[p.bias_n], p.act);
 #pragma unroll 1
         for (int cg = 0; cg < BN / 32; ++cg) {
           uint32_t v[32];
@@ -393,7 +425,8 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
           }
           if (valid) {
             uint32_t o[16];
-            convert32(v, s_bias + cg * 32, slope2, !zero, o);
+            if (zero) zero16(o);
+            else convert32(v, s_bias + cg * 32, pc, o);
             uint4* d4 = reinterpret_cast<uint4*>(dst + cg * 64);
 #pragma unroll
             for (int j = 0; j < 4; ++j) d4[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
@@ -405,8 +438,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
         const int Y = t.y0 + (row >> 4), X = t.x0 + (row & 15);     // deconv tiles are 16 x 8 blocks
         const bool valid = (Y <= p.lr_h) && (X <= p.lr_w);
         const int H = 4 * p.lr_h, W = 4 * p.lr_w;
-        const float slope = s_bias[p.bias_n];
-        const __nv_bfloat162 slope2 = __floats2bfloat162_rn(slope, slope);
+        const PreluCfg pc = make_prelu(s_bias[p.bias_n], 1);
         const int sub = (warp - 2) >> 2;             // which pair of sub-positions this warp converts
         if (p.deconv_nhwc) {
 #pragma unroll 1
@@ -424,7 +456,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
             const int Yt = 4 * Y + ry - 2, Xt = 4 * X + rx - 2;       // true HR coordinates
             if (valid && (Yt >= 0) && (Yt < H) && (Xt >= 0) && (Xt < W)) {
               uint32_t o[16];
-              convert32(v, s_bias, slope2, true, o);
+              convert32(v, s_bias, pc, o);
               uint4* d4 = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) + (((int64_t)t.b * H + Yt) * W + Xt) * 64);
 #pragma unroll
               for (int j = 0; j < 4; ++j) d4[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
@@ -432,9 +464,13 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
           }
         } else {
           // Block layout: this warp owns 128 contiguous bytes (2 sub-positions x 32 ch) of each of its
-          // 32 block rows.  Stage them in shared memory (16-byte pieces XOR-swizzled by the row: both
-          // phases are bank-conflict free), then store 4 rows per instruction as full 128-byte lines.
+          // 32 block rows.  It stages them in shared memory as a [32 rows x 128 B] tile in the canonical
+          // 128B-swizzle pattern and hands the tile to the TMA engine: two bulk tensor stores (one per
+          // block row of 16 blocks) write full 128-byte lines, clip at the tensor edge, and cost the LSU
+          // nothing (the first version read the tile back with LDS and stored with STG: L1TEX 70 % busy).
           uint8_t* stg = s_stage + (warp - 2) * (32 * 128);
+          if (lane == 0) tma_store_wait_read();       // previous tile's stores have read the staging tile
+          __syncwarp();
 #pragma unroll
           for (int c2 = 0; c2 < 2; ++c2) {
             const int cg = sub * 2 + c2;
@@ -450,29 +486,26 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
             const int Yt = 4 * Y + ry - 2, Xt = 4 * X + rx - 2;
             const bool inside = (Yt >= 0) && (Yt < H) && (Xt >= 0) && (Xt < W);   // else: zero ring
             uint32_t o[16];
-            convert32(v, s_bias, slope2, inside, o);
+            if (inside) convert32(v, s_bias, pc, o);   // ring positions (tile border only) stay zero
+            else zero16(o);
+            uint8_t* srow = stg + lane * 128;
+            const int sw = lane & 7;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int piece = c2 * 4 + j;
-              *reinterpret_cast<uint4*>(stg + lane * 128 + ((piece ^ (lane & 7)) << 4)) =
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(srow + (((c2 * 4 + j) ^ sw) << 4)) =
                   make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-            }
           }
+          fence_async_smem();
           __syncwarp();
-          const int pr = lane >> 3, pc = lane & 7;
+          if (lane == 0) {
 #pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int r = it * 4 + pr;
-            const int R = q * 32 + r;
-            const int Yr = t.y0 + (R >> 4), Xr = t.x0 + (R & 15);
-            if (Yr <= p.lr_h && Xr <= p.lr_w) {
-              const uint4 val = *reinterpret_cast<const uint4*>(stg + r * 128 + ((pc ^ (r & 7)) << 4));
-              const int64_t blk = ((int64_t)t.b * (p.lr_h + 1) + Yr) * (p.lr_w + 1) + Xr;
-              uint8_t* dst = reinterpret_cast<uint8_t*>(p.out) + blk * 1024 + (t.n_tile * 8 + sub * 2) * 64 + pc * 16;
-              *reinterpret_cast<uint4*>(dst) = val;
+            for (int half = 0; half < 2; ++half) {
+              const int Yr = t.y0 + 2 * q + half;
+              if (Yr <= p.lr_h)
+                tma_store_4d(&p.out_map, stg + half * 2048, 0, t.n_tile * 4 + sub, t.x0, t.b * (p.lr_h + 1) + Yr);
             }
+            tma_store_commit();
           }
-          __syncwarp();
         }
       } else {  // EPI_CONV_OUT
         const int Y = t.y0 + (row >> 5), X = t.x0 + (row & 31);     // conv_out tiles are 32 x 4
@@ -506,6 +539,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
     }
   }
 
+  if (MODE == EPI_DECONV && warp >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {

@@ -253,7 +253,7 @@ int build_deconv(Layer& L, const void* x, int B, int h, int w, const void* w_dev
     p.chunks[t].c0 = 0;
   }
   p.num_chunks = 4;
-  p.num_stages = 4;
+  p.num_stages = 11;    // ~3 tiles of lookahead: with 4 (= one tile) every tile paid a full load latency
   p.n_tiles = 2;
   p.tiles_x = ceil_div(w + 1, kTW);
   p.tiles_y = ceil_div(h + 1, kTH);
@@ -267,6 +267,18 @@ int build_deconv(Layer& L, const void* x, int B, int h, int w, const void* w_dev
   p.lr_h = h;
   p.lr_w = w;
   p.deconv_nhwc = nhwc;
+  if (!nhwc) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return VSR_ERR_STATE;
+    cuuint64_t dims[4] = {64, 8, (cuuint64_t)(w + 1), (cuuint64_t)(h + 1) * B};
+    cuuint64_t strides[3] = {128, 1024, (cuuint64_t)1024 * (w + 1)};
+    cuuint32_t box[4] = {64, 1, 16, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&p.out_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return VSR_ERR_CUDA_BASE + 999;
+  }
   finish_layer(L, 1);
   const double lrpx = (double)B * h * w;
   L.kclass = KC_DECONV;
@@ -424,7 +436,7 @@ int build_conv_out(Layer& L, const void* xhr, int B, int h, int w, const void* w
     p.chunks[t].c0 = 0;
   }
   p.num_chunks = 9;
-  p.num_stages = 6;
+  p.num_stages = 12;
   p.n_tiles = 1;
   p.tiles_x = ceil_div(W, tw);
   p.tiles_y = ceil_div(H, th);
