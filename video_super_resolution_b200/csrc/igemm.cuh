@@ -29,11 +29,13 @@ constexpr int kMaxStages = 16;
 constexpr int kIgemmThreads = 192;   // 6 warps: producer, MMA, 4 epilogue (EPI_ROWS / EPI_CONV_OUT)
 constexpr int kDeconvEpiWarps = 16;  // EPI_DECONV: 4 warps per TMEM lane quarter, 2 sub-positions each
 constexpr int kDeconvThreads = 64 + 32 * kDeconvEpiWarps;
+constexpr int kConvOutPitch = 33;                          // floats per row of the tap-partial exchange buffer
+constexpr int kConvOutStageBytes = 2 * 128 * kConvOutPitch * 4;
 
 enum EpiMode : int {
   EPI_ROWS = 0,        // BN=32: 64-byte BF16 row per pixel at out + row*pitch + off
   EPI_DECONV = 1,      // BN=256 (one half of the 16 sub-positions): HR block layout or plain NHWC HR
-  EPI_CONV_OUT = 2,    // BN=16 (3 real): fp32 planar output + bilinear skip + mean shifts
+  EPI_CONV_OUT = 2,    // BN=32 (27 real = 9 taps x 3): output-shift 3x3 conv, fp32 planar output + skip + mean shifts
 };
 
 struct Chunk {
@@ -53,7 +55,8 @@ struct alignas(64) IgemmParams {
   int32_t num_stages;
   // tile grid: total tiles = n_tiles * tiles_x * tiles_y * batch, n fastest
   int32_t n_tiles, tiles_x, tiles_y, batch;
-  int32_t tile_w, tile_h;      // tile_w * tile_h == 128
+  int32_t tile_w, tile_h;      // tile stride in pixels (== tile size except EPI_CONV_OUT, whose 16x8 tiles overlap)
+  int32_t org_x, org_y;        // origin of tile (0,0)
   // epilogue
   const float* bias;           // [bias_n] fp32 biases, then extras: [bias_n] = PReLU slope,
                                // EPI_CONV_OUT: [bias_n+1..+3] = sub_mean bias, [bias_n+4..+6] = add_mean bias
@@ -253,9 +256,9 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile)
   TileCoord t;
   t.n_tile = tile % p.n_tiles;
   int r = tile / p.n_tiles;
-  t.x0 = (r % p.tiles_x) * p.tile_w;
+  t.x0 = (r % p.tiles_x) * p.tile_w + p.org_x;
   r /= p.tiles_x;
-  t.y0 = (r % p.tiles_y) * p.tile_h;
+  t.y0 = (r % p.tiles_y) * p.tile_h + p.org_y;
   t.b = r / p.tiles_y;
   return t;
 }
@@ -508,14 +511,36 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
           }
         }
       } else {  // EPI_CONV_OUT
-        const int Y = t.y0 + (row >> 5), X = t.x0 + (row & 31);     // conv_out tiles are 32 x 4
-        const bool valid = (Y < p.out_h) && (X < p.out_w);
-        uint32_t v[16];
-        tmem_ld16(taddr, v);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(&tmem_empty[as]);
-        if (valid) {
+        // 3x3 conv in "output-shift" form: row = INPUT pixel (xi, yi) of a 16x8 tile whose origin is
+        // (x0, y0) = 14*tx-1, 6*ty-1; D[row, (ky*3+kx)*3 + o] = sum_c in[row, c] * W[o, c, ky, kx] is the
+        // contribution of this pixel to output (y - ky + 1, x - kx + 1).  Every input pixel is loaded
+        // once per tile (1.5x overlap) instead of once per tap (9x); the 27 partials are exchanged
+        // through shared memory and the 14x6 interior pixels gather their 9 neighbours.
+        float* S = reinterpret_cast<float*>(s_stage) + (as * 128) * kConvOutPitch;
+        {
+          uint32_t v[32];
+          tmem_ld32(taddr, v);
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(&tmem_empty[as]);
+          float* srow = S + row * kConvOutPitch;
+#pragma unroll
+          for (int j = 0; j < 27; ++j) srow[j] = __uint_as_float(v[j]);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");     // the 4 epilogue warps only
+        const int xi = row & 15, yi = row >> 4;
+        const int X = t.x0 + xi, Y = t.y0 + yi;
+        if (xi >= 1 && xi <= 14 && yi >= 1 && yi <= 6 && X < p.out_w && Y < p.out_h) {
+          float acc[3] = {s_bias[0], s_bias[1], s_bias[2]};
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              const float* q = S + ((yi + ky - 1) * 16 + (xi + kx - 1)) * kConvOutPitch + (ky * 3 + kx) * 3;
+              acc[0] += q[0];
+              acc[1] += q[1];
+              acc[2] += q[2];
+            }
           // bilinear x4 skip, align_corners=False (SRProjectionModule.py:136; ATen
           // upsample_bilinear2d: src = (dst+0.5)/4 - 0.5 clamped at 0), on sub_mean(x)
           const int h = p.lr_h, w = p.lr_w;
@@ -527,11 +552,11 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
             const float* src = p.skip_src + ((int64_t)t.b * 3 + c) * h * w;
-            float v00 = __ldg(src + y0i * w + x0i) + s_bias[p.bias_n + 1 + c], v01 = __ldg(src + y0i * w + x1i) + s_bias[p.bias_n + 1 + c];
-            float v10 = __ldg(src + y1i * w + x0i) + s_bias[p.bias_n + 1 + c], v11 = __ldg(src + y1i * w + x1i) + s_bias[p.bias_n + 1 + c];
+            const float sb = s_bias[p.bias_n + 1 + c];
+            float v00 = __ldg(src + y0i * w + x0i) + sb, v01 = __ldg(src + y0i * w + x1i) + sb;
+            float v10 = __ldg(src + y1i * w + x0i) + sb, v11 = __ldg(src + y1i * w + x1i) + sb;
             float skip = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
-            float r = skip + (__uint_as_float(v[c]) + s_bias[c]);
-            out[(((int64_t)t.b * 3 + c) * p.out_h + Y) * p.out_w + X] = r + s_bias[p.bias_n + 4 + c];
+            out[(((int64_t)t.b * 3 + c) * p.out_h + Y) * p.out_w + X] = skip + acc[c] + s_bias[p.bias_n + 4 + c];
           }
         }
       }

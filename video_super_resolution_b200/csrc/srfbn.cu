@@ -152,7 +152,7 @@ int launch_layer(const Layer& L, cudaStream_t st) {
     case V_PW128: return launch_variant<EPI_ROWS, 32, 128>(L, st);
     case V_DECONV: return launch_variant<EPI_DECONV, 32, 256>(L, st);
     case V_DOWN: return launch_variant<EPI_ROWS, 64, 32>(L, st);
-    case V_CONVOUT: return launch_variant<EPI_CONV_OUT, 32, 16>(L, st);
+    case V_CONVOUT: return launch_variant<EPI_CONV_OUT, 32, 32>(L, st);
     default: return VSR_ERR_INVALID_ARG;
   }
 }
@@ -163,7 +163,7 @@ size_t variant_smem(int variant, int chunks, int stages) {
     case V_PW128: return igemm_smem_bytes<32, 128>(chunks, stages);
     case V_DECONV: return igemm_smem_bytes<32, 256>(chunks, stages, kDeconvStageBytes);
     case V_DOWN: return igemm_smem_bytes<64, 32>(chunks, stages);
-    default: return igemm_smem_bytes<32, 16>(chunks, stages);
+    default: return igemm_smem_bytes<32, 32>(chunks, stages, kConvOutStageBytes);
   }
 }
 
@@ -424,25 +424,23 @@ int build_conv_out(Layer& L, const void* xhr, int B, int h, int w, const void* w
   L.variant = V_CONVOUT;
   IgemmParams& p = L.p;
   const int H = 4 * h, W = 4 * w;
-  const int tw = 32, th = 4;
-  int rc = make_act_map(&p.a_maps[0], xhr, kNF, W, H, B, 32, tw, th);
+  int rc = make_act_map(&p.a_maps[0], xhr, kNF, W, H, B, 32, 16, 8);
   if (rc) return rc;
-  rc = make_w_map(&p.b_map, w_dev, 9 * kNF, 16, 32, 16);
+  rc = make_w_map(&p.b_map, w_dev, kNF, 32, 32, 32);
   if (rc) return rc;
-  for (int t = 0; t < 9; ++t) {
-    p.chunks[t].map = 0;
-    p.chunks[t].dy = (int8_t)(t / 3 - 1);
-    p.chunks[t].dx = (int8_t)(t % 3 - 1);
-    p.chunks[t].c0 = 0;
-  }
-  p.num_chunks = 9;
-  p.num_stages = 12;
+  p.chunks[0].map = 0;
+  p.chunks[0].dx = p.chunks[0].dy = 0;
+  p.chunks[0].c0 = 0;
+  p.num_chunks = 1;
+  p.num_stages = 3;                    // per-tile latency chain (TMEM -> smem exchange -> gather) is hidden by CTAs/SM
   p.n_tiles = 1;
-  p.tiles_x = ceil_div(W, tw);
-  p.tiles_y = ceil_div(H, th);
+  p.tile_w = 14;                       // 16x8 input tiles produce 14x6 outputs
+  p.tile_h = 6;
+  p.org_x = -1;
+  p.org_y = -1;
+  p.tiles_x = ceil_div(W, 14);
+  p.tiles_y = ceil_div(H, 6);
   p.batch = B;
-  p.tile_w = tw;
-  p.tile_h = th;
   p.bias = bias_dev;
   p.bias_n = 16;
   p.act = 0;
@@ -451,7 +449,7 @@ int build_conv_out(Layer& L, const void* xhr, int B, int h, int w, const void* w
   p.out_w = W;
   p.lr_h = h;
   p.lr_w = w;
-  finish_layer(L, 2);
+  finish_layer(L, 3);
   const double hrpx = (double)B * H * W;
   L.kclass = KC_CONV_OUT;
   L.flops = hrpx * 2.0 * 288 * 3;
@@ -512,12 +510,12 @@ void pack_downconv_fused(const float* w, uint16_t* dst) {
           dst[(t * 32 + o) * 512 + s * 32 + c] = f2bf(w[((o * 32 + c) * 8 + ky) * 8 + kx]);
         }
 }
-// conv_out (3,32,3,3) -> [16][288], k = (ky*3+kx)*32 + c, rows 3..15 zero
+// conv_out (3,32,3,3) for the output-shift form -> [32 = (ky*3+kx)*3 + o][32 = c], rows 27..31 zero
 void pack_conv_out(const float* w, uint16_t* dst) {
-  memset(dst, 0, 16 * 288 * 2);
-  for (int o = 0; o < 3; ++o)
-    for (int t = 0; t < 9; ++t)
-      for (int c = 0; c < 32; ++c) dst[o * 288 + t * 32 + c] = f2bf(w[(o * 32 + c) * 9 + t]);
+  memset(dst, 0, 32 * 32 * 2);
+  for (int t = 0; t < 9; ++t)
+    for (int o = 0; o < 3; ++o)
+      for (int c = 0; c < 32; ++c) dst[(t * 3 + o) * 32 + c] = f2bf(w[(o * 32 + c) * 9 + t]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -640,7 +638,7 @@ static void layout_weights(vsr_srfbn_plan* pl) {
   for (int i = 0; i < 6; ++i) put(W_DOWN0 + i, 128, 512, 33);
   put(W_COMPRESS_OUT, 32, 192, 33);
   put(W_OUT, 512, 128, 33);
-  put(W_CONV_OUT, 16, 288, 16 + 7);
+  put(W_CONV_OUT, 32, 32, 16 + 7);
   pl->fc_off = off;
   off = align_up(off + (size_t)(32 * pl->cfg.num_maps + 65) * 4, 256);
   pl->misc_off = off;
