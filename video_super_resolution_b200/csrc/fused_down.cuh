@@ -49,6 +49,7 @@ struct alignas(64) FusedDownParams {
   int32_t tiles_x, tiles_y, batch;
   int32_t lr_h, lr_w;
   int32_t prefetch_ahead;             // L2 prefetch distance in half-tiles
+  int32_t wd_resident;                // 1: all 128 KB of conv weights stay in shared memory; 0: 2-deep ring per group
   int32_t debug;                      // timing experiments (results become wrong): bit0 skip phase-A MMAs, bit1 skip
                                       // the TMEM reads + conversion of phase A, bit2 skip the final TMEM reads/stores,
                                       // bit3 skip phase-B MMAs
@@ -87,10 +88,11 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
 }
 
 template <bool HAS_TRAN>
-inline size_t fused_down_smem_bytes(int nsrc, int num_stages) {
+inline size_t fused_down_smem_bytes(int nsrc, int num_stages, int wd_resident) {
   size_t wt = HAS_TRAN ? ((size_t)nsrc * kWtChunkBytes + 1023) / 1024 * 1024 : 0;
   size_t stage = HAS_TRAN ? 16384 : 2 * 16384;
-  return 1024 + kWdRingBytes + wt + (HAS_TRAN ? kHBytes : 0) + (size_t)num_stages * stage + 1024;
+  return 1024 + (wd_resident ? 4 * kWdGroupBytes : kWdRingBytes) + wt + (HAS_TRAN ? kHBytes : 0) +
+         (size_t)num_stages * stage + 1024;
 }
 
 template <bool HAS_TRAN>
@@ -103,7 +105,7 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* s_wd = smem;
-  uint8_t* s_wt = s_wd + kWdRingBytes;
+  uint8_t* s_wt = s_wd + (p.wd_resident ? 4 * kWdGroupBytes : kWdRingBytes);
   const int wt_region = HAS_TRAN ? ((p.nsrc * kWtChunkBytes + 1023) / 1024 * 1024) : 0;
   uint8_t* s_h = s_wt + wt_region;
   uint8_t* s_a = s_h + (HAS_TRAN ? kHBytes : 0);
@@ -277,8 +279,9 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
         a0 = dA + (uint64_t)((s * kStageBytes) >> 4);
       }
       if (g == 0) mbar_wait(&db_empty[tb], (n_b[tb] & 1) ^ 1);
-      const int wslot = n_wd & 1;
-      mbar_wait(&wd_full[wslot], (n_wd >> 1) & 1);
+      const int wslot = p.wd_resident ? g : (int)(n_wd & 1);
+      if (!p.wd_resident) mbar_wait(&wd_full[wslot], (n_wd >> 1) & 1);
+      else if (n_wd == 0) mbar_wait(&wd_full[0], 0);      // one-time load of all four groups
       tc_fence_after();
       const uint32_t d = tmem_base + kDB + (uint32_t)(tb * 128);
       const uint64_t b0 = dWd + (uint64_t)((wslot * kWdGroupBytes) >> 4);
@@ -290,7 +293,7 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
             umma_bf16(d, a0 + (uint64_t)(kc * 1024 + k * 2), b0 + (uint64_t)(kc * 1024 + k * 2), idesc_b,
                       (uint32_t)((g | kc | k) != 0));
       }
-      umma_commit(&wd_empty[wslot]);
+      if (!p.wd_resident) umma_commit(&wd_empty[wslot]);
       if (HAS_TRAN) umma_commit(h_empty);
       else umma_commit(&empty_bar[s]);
       if (g == 3) umma_commit(&db_full[tb]);
@@ -320,7 +323,10 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
     // every tile needs the 128 KB of 8x8-s4 weights once, 32 KB per sub-position group; all SMs
     // stream the same bytes, so these are L2 hits.  A 2-deep ring instead of a resident copy frees
     // 64 KB of shared memory for the activation pipeline (HBM latency hiding).
-    if (lane == 0) {
+    if (lane == 0 && p.wd_resident) {
+      mbar_expect_tx(&wd_full[0], 4 * kWdGroupBytes);
+      for (int kc = 0; kc < 8; ++kc) tma_load_2d(s_wd + kc * 16384, &p.wd_map, &wd_full[0], kc * 64, 0);
+    } else if (lane == 0) {
       uint32_t n_wd = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x)
         for (int g = 0; g < 4; ++g) {

@@ -390,10 +390,18 @@ int build_fused_down(Layer& L, const void* const* hr, int nsrc, int B, int h, in
   }
   f.tran_bias = tran_bias_dev;
   f.part = part;
-  while (f.num_stages > 2 && (tran ? fused_down_smem_bytes<true>(nsrc, f.num_stages)
-                                   : fused_down_smem_bytes<false>(nsrc, f.num_stages)) > 227 * 1024)
+  {
+    // measured on B200 (C2 shape, nsrc = 6): weights resident + 3 x 16 KB activation stages 3.73 ms,
+    // weights streamed per group from L2 + 7 stages 3.22 ms -> streaming is the default
+    const char* e = getenv("VSR_FUSED_WD_RESIDENT");
+    f.wd_resident = e ? atoi(e) : 0;
+    if (f.wd_resident) f.num_stages = tran ? 3 : 2;
+  }
+  while (f.num_stages > 2 && (tran ? fused_down_smem_bytes<true>(nsrc, f.num_stages, f.wd_resident)
+                                   : fused_down_smem_bytes<false>(nsrc, f.num_stages, f.wd_resident)) > 227 * 1024)
     --f.num_stages;
-  L.smem = tran ? fused_down_smem_bytes<true>(nsrc, f.num_stages) : fused_down_smem_bytes<false>(nsrc, f.num_stages);
+  L.smem = tran ? fused_down_smem_bytes<true>(nsrc, f.num_stages, f.wd_resident)
+                : fused_down_smem_bytes<false>(nsrc, f.num_stages, f.wd_resident);
   int64_t total = (int64_t)f.tiles_x * f.tiles_y * B;
   L.grid = (int)(total < kNumSMs ? total : kNumSMs);
   const double lrpx = (double)B * h * w;
