@@ -219,9 +219,7 @@ int vsr_srfbn_debug_premix(const vsr_srfbn_plan* plan, float* out_maps, vsr_stre
  * (SURVEY.md Appendix C).  All pointers device.  `act`: 1 = PReLU(slope), 0 = none.
  *   pointwise: y[r, 0:32] = act(sum_k x[r, k] * w[n, k] + b[n]),  x (rows, K) bf16, K%32==0, K<=224
  *   deconv   : ConvTranspose2d(32,32,8,4,2): x (B,h,w,32) bf16 -> y (B,4h,4w,32) bf16 (block_layout=0)
- *              or the HR block layout (B,h+1,w+1,16,32) (block_layout=1)
- *   downconv : Conv2d(32,32,8,4,2):          x in the HR block layout (B,h+1,w+1,16,32) bf16
- *              -> y (B,h,w,32) bf16
+ *              or the HR block layout (B,8,h+1,w+1,64) (block_layout=1)
  * w/b in the reference (torch) layouts, fp32, HOST memory. */
 int vsr_test_pointwise(const void* x_bf16, int64_t rows, int K, const float* w_host,
                        const float* b_host, float slope, int act, void* y_bf16,
@@ -229,14 +227,12 @@ int vsr_test_pointwise(const void* x_bf16, int64_t rows, int K, const float* w_h
 int vsr_test_deconv(const void* x_bf16, int B, int h, int w, const float* w_host,
                     const float* b_host, float slope, int block_layout, void* y_bf16,
                     void* workspace, size_t workspace_bytes, vsr_stream_t stream);
-int vsr_test_downconv(const void* x_bf16, int B, int h, int w, const float* w_host,
-                      const float* b_host, float slope, void* y_bf16,
-                      void* workspace, size_t workspace_bytes, vsr_stream_t stream);
 size_t vsr_test_workspace_bytes(int B, int h, int w);
 /*   fused_down: the kernel the plan uses for the HR half of a feedback group
  *              (SRProjectionModule.py:70-80): PReLU(Conv1x1 over nsrc concatenated HR maps) ->
- *              Conv2d(32,32,8,4,2) -> PReLU.  hr: (nsrc,B,h+1,w+1,16,32) bf16 block layout; nsrc==1
- *              skips the 1x1 (group 0).  wt (32,32*nsrc), wd (32,32,8,8) fp32 host.  y (B,h,w,32) bf16.
+ *              Conv2d(32,32,8,4,2) -> PReLU.  hr: (nsrc,B,8,h+1,w+1,64) bf16 block layout; nsrc==1
+ *              skips the 1x1 (group 0: the strided conv alone).  wt (32,32*nsrc), wd (32,32,8,8) fp32
+ *              host.  y (B,h,w,32) bf16.
  *              workspace: vsr_test_workspace_bytes + B*h*w*512 bytes. */
 int vsr_test_fused_down(const void* hr_bf16, int nsrc, int B, int h, int w, const float* wt_host,
                         const float* bt_host, float slope_t, const float* wd_host, const float* bd_host,

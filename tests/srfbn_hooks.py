@@ -12,16 +12,22 @@ def _fp(t):
 
 
 def to_block(x):
-    """(B,4h,4w,C) plain NHWC -> HR block layout (B,h+1,w+1,16,C): origin shifted by (-2,-2), zero ring."""
+    """(B,4h,4w,C) plain NHWC -> HR block layout (B,8,h+1,w+1,2*C): blocks of 4x4 pixels whose origin is
+    shifted by (-2,-2) (zero ring outside the image), stored as 8 planes of sub-position pairs
+    (s = ry*4+rx, pair = s>>1): element [b, pair, Yb, Xb, (s&1)*C + c]."""
     B, H, W, C = x.shape
     xp = torch.nn.functional.pad(x, (0, 0, 2, 2, 2, 2))
-    xp = xp.view(B, H // 4 + 1, 4, W // 4 + 1, 4, C).permute(0, 1, 3, 2, 4, 5)
-    return xp.reshape(B, H // 4 + 1, W // 4 + 1, 16, C).contiguous()
+    xp = xp.view(B, H // 4 + 1, 4, W // 4 + 1, 4, C)                 # b, Yb, ry, Xb, rx, c
+    xp = xp.permute(0, 2, 4, 1, 3, 5)                                 # b, ry, rx, Yb, Xb, c
+    xp = xp.reshape(B, 8, 2, H // 4 + 1, W // 4 + 1, C)               # b, pair, s&1, Yb, Xb, c
+    return xp.permute(0, 1, 3, 4, 2, 5).reshape(B, 8, H // 4 + 1, W // 4 + 1, 2 * C).contiguous()
 
 
 def from_block(xb):
-    B, hb, wb, _, C = xb.shape
-    x = xb.view(B, hb, wb, 4, 4, C).permute(0, 1, 3, 2, 4, 5).reshape(B, hb * 4, wb * 4, C)
+    B, _, hb, wb, C2 = xb.shape
+    C = C2 // 2
+    x = xb.view(B, 8, hb, wb, 2, C).permute(0, 1, 4, 2, 3, 5).reshape(B, 4, 4, hb, wb, C)   # b, ry, rx, Yb, Xb, c
+    x = x.permute(0, 3, 1, 4, 2, 5).reshape(B, hb * 4, wb * 4, C)
     return x[:, 2:-2, 2:-2].contiguous()
 
 
@@ -46,7 +52,7 @@ def pointwise(x_bf16, w, b, slope, act=True):
 def deconv(x_bf16, w, b, slope, block_layout=False):
     """x (B,h,w,32) bf16; w (32,32,8,8) ConvTranspose layout -> (B,4h,4w,32) or block layout."""
     B, h, wd, _ = x_bf16.shape
-    shape = (B, h + 1, wd + 1, 16, 32) if block_layout else (B, 4 * h, 4 * wd, 32)
+    shape = (B, 8, h + 1, wd + 1, 64) if block_layout else (B, 4 * h, 4 * wd, 32)
     y = torch.full(shape, float("nan"), dtype=torch.bfloat16, device=x_bf16.device)
     ws = _ws(x_bf16.device)
     w = w.contiguous().float()
@@ -57,23 +63,9 @@ def deconv(x_bf16, w, b, slope, block_layout=False):
     return y
 
 
-def downconv(xb_bf16, w, b, slope):
-    """xb (B,h+1,w+1,16,32) bf16 block layout; w (32,32,8,8) Conv2d layout -> (B,h,w,32) bf16."""
-    B, hb, wb = xb_bf16.shape[:3]
-    h, wd = hb - 1, wb - 1
-    y = torch.full((B, h, wd, 32), float("nan"), dtype=torch.bfloat16, device=xb_bf16.device)
-    ws = _ws(xb_bf16.device)
-    w = w.contiguous().float()
-    b = b.contiguous().float()
-    _lib.check(_lib.lib().vsr_test_downconv(xb_bf16.data_ptr(), B, h, wd, _fp(w), _fp(b), float(slope),
-                                            y.data_ptr(), ws.data_ptr(), ws.numel(),
-                                            torch.cuda.current_stream().cuda_stream), "test_downconv")
-    return y
-
-
 def fused_down(hr_bf16, wt, bt, slope_t, wd, bd, slope_d):
-    """hr (nsrc,B,h+1,w+1,16,32) bf16 block layout; wt (32,32*nsrc)|None; wd (32,32,8,8) -> (B,h,w,32) bf16."""
-    nsrc, B, hb, wb = hr_bf16.shape[:4]
+    """hr (nsrc,B,8,h+1,w+1,64) bf16 block layout; wt (32,32*nsrc)|None; wd (32,32,8,8) -> (B,h,w,32) bf16."""
+    nsrc, B, _, hb, wb = hr_bf16.shape[:5]
     h, wd_ = hb - 1, wb - 1
     dev = hr_bf16.device
     y = torch.full((B, h, wd_, 32), float("nan"), dtype=torch.bfloat16, device=dev)

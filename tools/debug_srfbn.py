@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 CASES = ["fused:1:1:8:16", "fused:2:1:8:16", "fused:3:2:5:7", "fused:6:1:19:33", "deconv:1:19:33:1", "pw:128:32", "pw:1000:64", "pw:4173:192", "deconv:1:8:16:0", "deconv:2:5:7:0", "deconv:1:8:16:1",
-         "down:1:8:16", "down:2:5:7", "full:8:16:16:3", "full:20:24:40:3"]
+         "full:8:16:16:3", "full:20:24:40:3"]
 
 
 def stats(name, got, want):
@@ -54,15 +54,6 @@ def run_case(case):
             got = hk.from_block(got)
         err = stats(case, got, want)
         print("  err by (y%4,x%4):", [[round(err[:, ry::4, rx::4].max().item(), 3) for rx in range(4)] for ry in range(4)])
-    elif parts[0] == "down":
-        B, h, w = map(int, parts[1:])
-        x = torch.randn((B, 4 * h, 4 * w, 32), generator=g).bfloat16()
-        wt = (torch.randn((32, 32, 8, 8), generator=g) / 45).bfloat16().float()
-        b = torch.randn(32, generator=g) * 0.1
-        got = hk.downconv(hk.to_block(x).to(dev), wt, b, 0.15)
-        want = F.prelu(F.conv2d(x.float().permute(0, 3, 1, 2), wt, b, stride=4, padding=2),
-                       torch.tensor([0.15])).permute(0, 2, 3, 1)
-        stats(case, got, want)
     elif parts[0] == "fused":
         nsrc, B, h, w = map(int, parts[1:])
         hr = torch.randn((nsrc, B, 4 * h, 4 * w, 32), generator=g).bfloat16()

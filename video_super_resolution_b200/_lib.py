@@ -75,7 +75,6 @@ SIGNATURES = {
     "vsr_srfbn_debug_premix": (c_int, [c_void_p, c_void_p, c_void_p]),
     "vsr_test_pointwise": (c_int, [c_void_p, c_i64, c_int, c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vsr_test_deconv": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
-    "vsr_test_downconv": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vsr_test_fused_down": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
                                     c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vsr_test_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),

@@ -40,8 +40,8 @@ constexpr int kWtChunkBytes = 32 * 32 * 2;   // one 32x32 downtran slice (64-byt
 constexpr int kHBytes = 128 * 128 * 2;       // phase-B A operand of one sub-position group
 
 struct alignas(64) FusedDownParams {
-  CUtensorMap hr_maps[kMaxSources];   // HAS_TRAN: 4-D (512, w+1, h+1, B), box (64,16,8,1) = 2 sub-positions, 128B swizzle
-  CUtensorMap h0_map;                 // !HAS_TRAN: 4-D (512, w+1, h+1, B), box (64,16,8,1), 128B swizzle
+  CUtensorMap hr_maps[kMaxSources];   // HAS_TRAN: 4-D (64, w+1, h+1, 8*B) pair planes, box (64,16,8,1) = 2 sub-positions, 128B swizzle
+  CUtensorMap h0_map;                 // !HAS_TRAN: the same view of hr[0]
   CUtensorMap wt_map;                 // 2-D (32*nsrc, 32), box (32,32), 64B swizzle
   CUtensorMap wd_map;                 // 2-D (512, 128), box (64,128), 128B swizzle
   int32_t nsrc;
@@ -179,9 +179,9 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
         tile_coord(tile, px0, py0, pb);
         if (HAS_TRAN) {
           for (int sp = half * 8; sp < half * 8 + 8; sp += 2)
-            for (int j = 0; j < p.nsrc; ++j) tma_prefetch_4d(&p.hr_maps[j], sp * 32, px0, py0, pb);
+            for (int j = 0; j < p.nsrc; ++j) tma_prefetch_4d(&p.hr_maps[j], 0, px0, py0, pb * 8 + (sp >> 1));
         } else {
-          for (int c = half * 256; c < half * 256 + 256; c += 64) tma_prefetch_4d(&p.h0_map, c, px0, py0, pb);
+          for (int pr = half * 4; pr < half * 4 + 4; ++pr) tma_prefetch_4d(&p.h0_map, 0, px0, py0, pb * 8 + pr);
         }
       };
       {
@@ -206,7 +206,7 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
               for (int j = 0; j < p.nsrc; ++j) {
                 mbar_wait(&empty_bar[s], phase ^ 1);
                 mbar_expect_tx(&full_bar[s], kStageBytes);
-                tma_load_4d(s_a + s * kStageBytes, &p.hr_maps[j], &full_bar[s], sp * 32, x0, y0, b);
+                tma_load_4d(s_a + s * kStageBytes, &p.hr_maps[j], &full_bar[s], 0, x0, y0, b * 8 + (sp >> 1));
                 if (++s == p.num_stages) { s = 0; phase ^= 1; }
               }
             }
@@ -214,8 +214,8 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
             for (int g = half * 2; g < half * 2 + 2; ++g) {
               mbar_wait(&empty_bar[s], phase ^ 1);
               mbar_expect_tx(&full_bar[s], kStageBytes);
-              tma_load_4d(s_a + s * kStageBytes, &p.h0_map, &full_bar[s], g * 128, x0, y0, b);
-              tma_load_4d(s_a + s * kStageBytes + 16384, &p.h0_map, &full_bar[s], g * 128 + 64, x0, y0, b);
+              tma_load_4d(s_a + s * kStageBytes, &p.h0_map, &full_bar[s], 0, x0, y0, b * 8 + 2 * g);
+              tma_load_4d(s_a + s * kStageBytes + 16384, &p.h0_map, &full_bar[s], 0, x0, y0, b * 8 + 2 * g + 1);
               if (++s == p.num_stages) { s = 0; phase ^= 1; }
             }
           }

@@ -49,7 +49,7 @@ struct Chunk {
 struct alignas(64) IgemmParams {
   CUtensorMap a_maps[kMaxSources];
   CUtensorMap b_map;
-  CUtensorMap out_map;         // EPI_DECONV block layout: 4-D (64 el, 8 sub-position pairs, w+1, (h+1)*B), box (64,1,16,1), 128B swizzle
+  CUtensorMap out_map;         // EPI_DECONV block layout: 4-D (64 el, w+1, h+1, 8 pairs * B), box (64,16,2,1), 128B swizzle
   Chunk chunks[kMaxChunks];
   int32_t num_chunks;
   int32_t num_stages;
@@ -468,8 +468,8 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
         } else {
           // Block layout: this warp owns 128 contiguous bytes (2 sub-positions x 32 ch) of each of its
           // 32 block rows.  It stages them in shared memory as a [32 rows x 128 B] tile in the canonical
-          // 128B-swizzle pattern and hands the tile to the TMA engine: two bulk tensor stores (one per
-          // block row of 16 blocks) write full 128-byte lines, clip at the tensor edge, and cost the LSU
+          // 128B-swizzle pattern and hands the tile to the TMA engine: one bulk tensor store writes two
+          // contiguous 2 KB runs of the pair's plane, clips at the tensor edge, and costs the LSU
           // nothing (the first version read the tile back with LDS and stored with STG: L1TEX 70 % busy).
           uint8_t* stg = s_stage + (warp - 2) * (32 * 128);
           if (lane == 0) tma_store_wait_read();       // previous tile's stores have read the staging tile
@@ -501,12 +501,10 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
           fence_async_smem();
           __syncwarp();
           if (lane == 0) {
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              const int Yr = t.y0 + 2 * q + half;
-              if (Yr <= p.lr_h)
-                tma_store_4d(&p.out_map, stg + half * 2048, 0, t.n_tile * 4 + sub, t.x0, t.b * (p.lr_h + 1) + Yr);
-            }
+            // one box = this warp's 2 block rows x 16 blocks of one sub-position-pair plane; rows or
+            // columns beyond the tensor edge are clipped by the TMA unit
+            if (t.y0 + 2 * q <= p.lr_h)
+              tma_store_4d(&p.out_map, stg, 0, t.x0, t.y0 + 2 * q, t.b * 8 + t.n_tile * 4 + sub);
             tma_store_commit();
           }
         }

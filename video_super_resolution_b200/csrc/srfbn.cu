@@ -89,7 +89,7 @@ int make_w_map(CUtensorMap* m, const void* base, int64_t K, int64_t N, int ck, i
 // ------------------------------------------------------------------------------------------------
 // kernel variants
 // ------------------------------------------------------------------------------------------------
-enum Variant : int { V_PW32 = 0, V_PW128, V_DECONV, V_DOWN, V_CONVOUT, V_FUSED_TRAN, V_FUSED_PLAIN, V_FINALIZE, V_COUNT };
+enum Variant : int { V_PW32 = 0, V_PW128, V_DECONV, V_CONVOUT, V_FUSED_TRAN, V_FUSED_PLAIN, V_FINALIZE, V_COUNT };
 
 // kernel classes for the per-launch accounting bench.py reads (vsr_srfbn_profile_*)
 static_assert(VSR_SRFBN_KERNEL_CLASSES == 10, "header constant");
@@ -151,7 +151,6 @@ int launch_layer(const Layer& L, cudaStream_t st) {
     case V_PW32: return launch_variant<EPI_ROWS, 32, 32>(L, st);
     case V_PW128: return launch_variant<EPI_ROWS, 32, 128>(L, st);
     case V_DECONV: return launch_variant<EPI_DECONV, 32, 256>(L, st);
-    case V_DOWN: return launch_variant<EPI_ROWS, 64, 32>(L, st);
     case V_CONVOUT: return launch_variant<EPI_CONV_OUT, 32, 32>(L, st);
     default: return VSR_ERR_INVALID_ARG;
   }
@@ -162,7 +161,6 @@ size_t variant_smem(int variant, int chunks, int stages) {
     case V_PW32: return igemm_smem_bytes<32, 32>(chunks, stages);
     case V_PW128: return igemm_smem_bytes<32, 128>(chunks, stages);
     case V_DECONV: return igemm_smem_bytes<32, 256>(chunks, stages, kDeconvStageBytes);
-    case V_DOWN: return igemm_smem_bytes<64, 32>(chunks, stages);
     default: return igemm_smem_bytes<32, 32>(chunks, stages, kConvOutStageBytes);
   }
 }
@@ -270,9 +268,9 @@ int build_deconv(Layer& L, const void* x, int B, int h, int w, const void* w_dev
   if (!nhwc) {
     EncodeTiledFn enc = encode_fn();
     if (!enc) return VSR_ERR_STATE;
-    cuuint64_t dims[4] = {64, 8, (cuuint64_t)(w + 1), (cuuint64_t)(h + 1) * B};
-    cuuint64_t strides[3] = {128, 1024, (cuuint64_t)1024 * (w + 1)};
-    cuuint32_t box[4] = {64, 1, 16, 1};
+    cuuint64_t dims[4] = {64, (cuuint64_t)(w + 1), (cuuint64_t)(h + 1), (cuuint64_t)8 * B};
+    cuuint64_t strides[3] = {128, (cuuint64_t)128 * (w + 1), (cuuint64_t)128 * (w + 1) * (h + 1)};
+    cuuint32_t box[4] = {64, 16, 2, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = enc(&p.out_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -287,65 +285,6 @@ int build_deconv(Layer& L, const void* x, int B, int h, int w, const void* w_dev
   return VSR_OK;
 }
 
-// Conv2d(32,32,8,4,2) on the HR block layout: (B,h+1,w+1,512) -> (B,h,w,32)
-int build_downconv(Layer& L, const void* xb, int B, int h, int w, const void* w_dev, const float* bias_dev,
-                   void* out) {
-  memset(&L, 0, sizeof(L));
-  L.variant = V_DOWN;
-  IgemmParams& p = L.p;
-  int rc = make_act_map(&p.a_maps[0], xb, 512, w + 1, h + 1, B, 64, kTW, kTH);
-  if (rc) return rc;
-  rc = make_w_map(&p.b_map, w_dev, 2048, kNF, 64, kNF);
-  if (rc) return rc;
-  int nc = 0;
-  for (int t = 0; t < 4; ++t)
-    for (int q = 0; q < 8; ++q, ++nc) {
-      p.chunks[nc].map = 0;
-      p.chunks[nc].dy = (int8_t)(t >> 1);
-      p.chunks[nc].dx = (int8_t)(t & 1);
-      p.chunks[nc].c0 = q * 64;
-    }
-  p.num_chunks = nc;
-  p.num_stages = 4;
-  p.n_tiles = 1;
-  p.tiles_x = ceil_div(w, kTW);
-  p.tiles_y = ceil_div(h, kTH);
-  p.batch = B;
-  p.tile_w = kTW;
-  p.tile_h = kTH;
-  p.bias = bias_dev;
-  p.bias_n = kNF;
-  p.act = 1;
-  p.out = out;
-  p.out_pitch = kNF * 2;
-  p.out_off = 0;
-  p.flat_rows = 0;
-  p.out_h = h;
-  p.out_w = w;
-  p.lr_h = h;
-  p.lr_w = w;
-  finish_layer(L, 1);
-  const double lrpx = (double)B * h * w;
-  L.kclass = KC_DOWNCONV;
-  L.flops = lrpx * 131072.0;
-  L.bytes = lrpx * 64.0 * 17.0;
-  return VSR_OK;
-}
-
-// HR block layout viewed as (c, s, Xb, Yb, map): one sub-position of a 16x8 block tile per box
-int make_hr5d_map(CUtensorMap* m, const void* base, int h, int w, int B) {
-  EncodeTiledFn enc = encode_fn();
-  if (!enc) return VSR_ERR_STATE;
-  cuuint64_t dims[5] = {32, 16, (cuuint64_t)(w + 1), (cuuint64_t)(h + 1), (cuuint64_t)B};
-  cuuint64_t strides[4] = {64, 1024, (cuuint64_t)1024 * (w + 1), (cuuint64_t)1024 * (w + 1) * (h + 1)};
-  cuuint32_t box[5] = {32, 2, 16, 8, 1};
-  cuuint32_t es[5] = {1, 1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? VSR_OK : VSR_ERR_CUDA_BASE + 999;
-}
-
 // downtran (1x1 over hr[0..nsrc-1], nsrc >= 2) + PReLU + Conv2d(32,32,8,4,2) pre-activation sums -> acc;
 // nsrc == 1: the conv alone on hr[0].  hr[j]: HR block layout (B,h+1,w+1,16,32); acc (B,h,w,32) fp32.
 int build_fused_down(Layer& L, const void* const* hr, int nsrc, int B, int h, int w, const void* wt_dev,
@@ -358,13 +297,13 @@ int build_fused_down(Layer& L, const void* const* hr, int nsrc, int B, int h, in
   int rc;
   if (tran) {
     for (int j = 0; j < nsrc; ++j) {
-      rc = make_act_map(&f.hr_maps[j], hr[j], 512, w + 1, h + 1, B, 64, 16, 8);
+      rc = make_act_map(&f.hr_maps[j], hr[j], 64, w + 1, h + 1, 8 * B, 64, 16, 8);   // (el, Xb, Yb, pair plane)
       if (rc) return rc;
     }
     rc = make_w_map(&f.wt_map, wt_dev, 32 * nsrc, 32, 32, 32);
     if (rc) return rc;
   } else {
-    rc = make_act_map(&f.h0_map, hr[0], 512, w + 1, h + 1, B, 64, 16, 8);
+    rc = make_act_map(&f.h0_map, hr[0], 64, w + 1, h + 1, 8 * B, 64, 16, 8);
     if (rc) return rc;
   }
   rc = make_w_map(&f.wd_map, wd_dev, 512, 128, 64, 128);
@@ -495,16 +434,6 @@ void pack_deconv(const float* w, uint16_t* dst) {
           int ry = s >> 2, rx = s & 3, dy = (t >> 1) - 1, dx = (t & 1) - 1;
           int ky = ry - 4 * dy, kx = rx - 4 * dx;
           dst[(s * 32 + o) * 128 + t * 32 + c] = f2bf(w[((c * 32 + o) * 8 + ky) * 8 + kx]);
-        }
-}
-// Conv2d weight (o, c, 8, 8) s4 p2 -> [32][2048], k = ((dy*2+dx)*16 + s)*32 + c, ky = 4dy+ry, kx = 4dx+rx
-void pack_downconv(const float* w, uint16_t* dst) {
-  for (int o = 0; o < 32; ++o)
-    for (int t = 0; t < 4; ++t)
-      for (int s = 0; s < 16; ++s)
-        for (int c = 0; c < 32; ++c) {
-          int ky = 4 * (t >> 1) + (s >> 2), kx = 4 * (t & 1) + (s & 3);
-          dst[o * 2048 + (t * 16 + s) * 32 + c] = f2bf(w[((o * 32 + c) * 8 + ky) * 8 + kx]);
         }
 }
 // Conv2d weight (o, c, 8, 8) s4 p2 for the fused kernel's output-shift form -> [128 = t*32+o][512 = s*32+c],
@@ -1004,32 +933,6 @@ extern "C" int vsr_test_deconv(const void* x_bf16, int B, int h, int w, const fl
   if (rc) return rc;
   Layer L;
   rc = build_deconv(L, x_bf16, B, h, w, ws, reinterpret_cast<const float*>(ws + 256 * 1024), y_bf16, block_layout ? 0 : 1);
-  if (rc) return rc;
-  rc = launch_layer(L, st);
-  if (rc) return rc;
-  return cuda_status(cudaStreamSynchronize(st));
-}
-
-// x is passed already in the HR block layout (B,h+1,w+1,16,32); tests build it with torch
-// (pad by 2, unfold 4x4), which keeps the hook allocation-free.
-extern "C" int vsr_test_downconv(const void* x_bf16, int B, int h, int w, const float* w_host, const float* b_host,
-                                 float slope, void* y_bf16, void* workspace, size_t workspace_bytes,
-                                 vsr_stream_t stream) {
-  if (!x_bf16 || !w_host || !b_host || !y_bf16 || !workspace || B <= 0 || h <= 0 || w <= 0) return VSR_ERR_INVALID_ARG;
-  if (workspace_bytes < vsr_test_workspace_bytes(B, h, w)) return VSR_ERR_WORKSPACE;
-  cudaStream_t st = as_stream(stream);
-  std::vector<uint16_t> wp((size_t)32 * 2048);
-  pack_downconv(w_host, wp.data());
-  float bias[33];
-  memcpy(bias, b_host, 32 * 4);
-  bias[32] = slope;
-  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
-  int rc = upload(ws, wp.data(), wp.size() * 2, st);
-  if (rc) return rc;
-  rc = upload(ws + 256 * 1024, bias, sizeof(bias), st);
-  if (rc) return rc;
-  Layer L;
-  rc = build_downconv(L, x_bf16, B, h, w, ws, reinterpret_cast<const float*>(ws + 256 * 1024), y_bf16);
   if (rc) return rc;
   rc = launch_layer(L, st);
   if (rc) return rc;
