@@ -20,9 +20,9 @@ for _ in range(2):
     ops.project_flow(f)
     ops.project_flow(f, inv)
     ops.project_flow(fr, inv)
-    ops.warp(src, f)
-    ops.warp(src, f, True, ref=src)
+    ops.warp(src, f, 2)
+    ops.warp(src, f, 2, ref=src)
     ops.warp_labels(lab, f)
-    ops.warp(feat, f[:1])
+    ops.warp(feat, f[:1], 2)
 torch.cuda.synchronize()
 print("ok")

@@ -30,6 +30,45 @@ constexpr int kNumSMs = 148;  // B200
 __host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Division by a runtime constant without the ~100-instruction 64-bit divide (ncu: the pixel index ->
+// (b, y, x) decode was the bulk of the warp kernels' instructions).  Valid for n < 2^32.
+struct FastDiv {
+  uint32_t mul, shr, d;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d;
+  uint32_t shr = 0;
+  while ((1ull << shr) < d) ++shr;
+  f.shr = shr;
+  f.mul = (uint32_t)((((1ull << 32) * ((1ull << shr) - d)) / d) + 1);
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
+  return (uint32_t)(((uint64_t)__umulhi(n, f.mul) + n) >> f.shr);
+}
+// pixel index -> (b, y, x) for a (B, H, W) raster
+struct PixDecode {
+  FastDiv w, hw;
+  uint32_t W, HW;
+};
+inline PixDecode make_pixdecode(int H, int W) {
+  PixDecode d;
+  d.w = make_fastdiv((uint32_t)W);
+  d.hw = make_fastdiv((uint32_t)H * (uint32_t)W);
+  d.W = (uint32_t)W;
+  d.HW = (uint32_t)H * (uint32_t)W;
+  return d;
+}
+__device__ __forceinline__ void decode_pix(uint32_t i, const PixDecode& d, int& b, int& y, int& x) {
+  const uint32_t bb = fdiv(i, d.hw);
+  const uint32_t r = i - bb * d.HW;
+  const uint32_t yy = fdiv(r, d.w);
+  b = (int)bb;
+  y = (int)yy;
+  x = (int)(r - yy * d.W);
+}
+
 // streaming (read-once) loads / write-once stores: keep them out of L1
 __device__ __forceinline__ float2 ldg_stream_f2(const float2* p) {
   float2 r;

@@ -123,13 +123,12 @@ __device__ __forceinline__ void nearest_tap(int x, int y, float dx, float dy, in
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
 resample2d_nchw_kernel(const float* __restrict__ in1, const float* __restrict__ flow, float* __restrict__ out,
-                       int B, int C, int H, int W, int bilinear) {
+                       int B, int C, int H, int W, int bilinear, const PixDecode pd) {
   const int64_t HW = (int64_t)H * W;
   const int64_t n = (int64_t)B * HW;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    int x = (int)(i % W);
-    int y = (int)((i / W) % H);
-    int b = (int)(i / HW);
+    int x, y, b;
+    decode_pix((uint32_t)i, pd, b, y, x);
     const float* fl = flow + (int64_t)b * 2 * HW + (int64_t)y * W + x;
     float dx = __ldg(fl), dy = __ldg(fl + HW);
     const float* src = in1 + (int64_t)b * C * HW;
@@ -161,16 +160,16 @@ template <bool FAST>
 __global__ void __launch_bounds__(kThreads)
 warp_nhwc3_kernel(const float* __restrict__ src, const float* __restrict__ flow, float* __restrict__ dst,
                   const float* __restrict__ ref, float* __restrict__ norm_out,
-                  int64_t n_pix, int H, int W, int bilinear, int vec_store) {
+                  int64_t n_pix, int H, int W, int bilinear, int vec_store, const PixDecode pd) {
   __shared__ __align__(16) float stage[kThreads * 3];
   const int64_t HW = (int64_t)H * W;
   for (int64_t base = (int64_t)blockIdx.x * kThreads; base < n_pix; base += (int64_t)gridDim.x * kThreads) {
     int64_t i = base + threadIdx.x;
     float v0 = 0.f, v1 = 0.f, v2 = 0.f;
     if (i < n_pix) {
-      int x = (int)(i % W);
-      int y = (int)((i / W) % H);
-      int64_t b = i / HW;
+      int x, y, bi;
+      decode_pix((uint32_t)i, pd, bi, y, x);
+      const int64_t b = bi;
       float2 f = ldg_stream_f2(reinterpret_cast<const float2*>(flow) + i);
       const float* s = src + b * HW * 3;
       if (bilinear) {
@@ -227,16 +226,16 @@ warp_nhwc3_kernel(const float* __restrict__ src, const float* __restrict__ flow,
 template <bool FAST>
 __global__ void __launch_bounds__(kThreads)
 warp_nhwc_vec4_kernel(const float* __restrict__ src, const float* __restrict__ flow, float* __restrict__ dst,
-                      int64_t n_pix, int H, int W, int C, int bilinear) {
+                      int64_t n_pix, int H, int W, int C, int bilinear, const PixDecode pd, const FastDiv gd) {
   const int G = C >> 2;
   const int64_t HW = (int64_t)H * W;
   const int64_t n = n_pix * G;
   for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
-    int64_t i = j / G;
+    const int64_t i = fdiv((uint32_t)j, gd);
     int g = (int)(j - i * G);
-    int x = (int)(i % W);
-    int y = (int)((i / W) % H);
-    int64_t b = i / HW;
+    int x, y, bi;
+    decode_pix((uint32_t)i, pd, bi, y, x);
+    const int64_t b = bi;
     float2 f = __ldg(reinterpret_cast<const float2*>(flow) + i);
     const float4* s = reinterpret_cast<const float4*>(src + b * HW * C) + g;
     float4 o;
@@ -264,12 +263,12 @@ warp_nhwc_vec4_kernel(const float* __restrict__ src, const float* __restrict__ f
 __global__ void __launch_bounds__(kThreads)
 warp_nhwc_generic_kernel(const float* __restrict__ src, const float* __restrict__ flow, float* __restrict__ dst,
                          const float* __restrict__ ref, float* __restrict__ norm_out,
-                         int64_t n_pix, int H, int W, int C, int bilinear) {
+                         int64_t n_pix, int H, int W, int C, int bilinear, const PixDecode pd) {
   const int64_t HW = (int64_t)H * W;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pix; i += (int64_t)gridDim.x * blockDim.x) {
-    int x = (int)(i % W);
-    int y = (int)((i / W) % H);
-    int64_t b = i / HW;
+    int x, y, bi;
+    decode_pix((uint32_t)i, pd, bi, y, x);
+    const int64_t b = bi;
     float2 f = __ldg(reinterpret_cast<const float2*>(flow) + i);
     const float* s = src + b * HW * C;
     float* o = dst + i * C;
@@ -312,7 +311,7 @@ warp_nhwc_generic_kernel(const float* __restrict__ src, const float* __restrict_
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
 warp_labels_kernel(const uint8_t* __restrict__ labels, const float* __restrict__ flow, uint8_t* __restrict__ dst,
-                   int64_t n_pix, int H, int W, int vec) {
+                   int64_t n_pix, int H, int W, int vec, const PixDecode pd) {
   const int64_t HW = (int64_t)H * W;
   const int64_t n4 = vec ? n_pix / 4 : 0;
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (int64_t)gridDim.x * blockDim.x) {
@@ -324,9 +323,9 @@ warp_labels_kernel(const uint8_t* __restrict__ labels, const float* __restrict__
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       int64_t i = q * 4 + k;
-      int x = (int)(i % W);
-      int y = (int)((i / W) % H);
-      int64_t b = i / HW;
+      int x, y, bi;
+      decode_pix((uint32_t)i, pd, bi, y, x);
+      const int64_t b = bi;
       int xN, yN;
       nearest_tap(x, y, fxs[k], fys[k], W, H, xN, yN);
       packed |= (uint32_t)__ldg(labels + b * HW + (int64_t)yN * W + xN) << (8 * k);
@@ -336,9 +335,9 @@ warp_labels_kernel(const uint8_t* __restrict__ labels, const float* __restrict__
   // scalar tail (and the whole range when the buffers are not 16/4-byte aligned)
   for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pix;
        i += (int64_t)gridDim.x * blockDim.x) {
-    int x = (int)(i % W);
-    int y = (int)((i / W) % H);
-    int64_t b = i / HW;
+    int x, y, bi;
+    decode_pix((uint32_t)i, pd, bi, y, x);
+    const int64_t b = bi;
     float2 f = __ldg(reinterpret_cast<const float2*>(flow) + i);
     int xN, yN;
     nearest_tap(x, y, f.x, f.y, W, H, xN, yN);
@@ -387,7 +386,7 @@ extern "C" int vsr_resample2d_forward(const float* input1, const float* flow, fl
   if (kernel_size != 1) return VSR_ERR_UNSUPPORTED;  // resample2d.py:44: the only value ever used
   int64_t n = (int64_t)B * H * W;
   resample2d_nchw_kernel<<<grid_for(n, kThreads), kThreads, 0, as_stream(stream)>>>(input1, flow, output, B, C, H, W,
-                                                                                   bilinear ? 1 : 0);
+                                                                                   bilinear ? 1 : 0, make_pixdecode(H, W));
   return after_launch();
 }
 
@@ -399,24 +398,28 @@ extern "C" int vsr_warp_nhwc_f32(const float* src, const float* flow, float* dst
   int64_t n_pix = (int64_t)B * H * W;
   cudaStream_t st = as_stream(stream);
   if (bilinear < 0 || bilinear > kModeFast) return VSR_ERR_INVALID_ARG;
+  if ((int64_t)B * H * W * ((C % 4) == 0 ? C / 4 : 1) >= ((int64_t)1 << 32)) return VSR_ERR_UNSUPPORTED;   // 32-bit index decode
+  const PixDecode pd = make_pixdecode(H, W);
   if (C == 3) {
+    // (a 4-pixels-per-thread variant without the shared-memory staging measured SLOWER on B200, 195 vs
+    //  172 us for 8 x 1080p: neighbouring lanes' gathers end up 48 B apart and touch 4x more lines per load)
     int vec = aligned(dst, 16) ? 1 : 0;
     if (bilinear == kModeFast)
       warp_nhwc3_kernel<true><<<grid_for(n_pix, kThreads), kThreads, 0, st>>>(src, flow, dst, ref, norm_out, n_pix, H, W,
-                                                                              1, vec);
+                                                                              1, vec, pd);
     else
       warp_nhwc3_kernel<false><<<grid_for(n_pix, kThreads), kThreads, 0, st>>>(src, flow, dst, ref, norm_out, n_pix, H,
-                                                                               W, bilinear, vec);
+                                                                               W, bilinear, vec, pd);
   } else if ((C % 4) == 0 && norm_out == nullptr && aligned(src, 16) && aligned(dst, 16)) {
     if (bilinear == kModeFast)
       warp_nhwc_vec4_kernel<true><<<grid_for(n_pix * (C / 4), kThreads), kThreads, 0, st>>>(src, flow, dst, n_pix, H, W,
-                                                                                            C, 1);
+                                                                                            C, 1, pd, make_fastdiv((uint32_t)(C / 4)));
     else
       warp_nhwc_vec4_kernel<false><<<grid_for(n_pix * (C / 4), kThreads), kThreads, 0, st>>>(src, flow, dst, n_pix, H,
-                                                                                             W, C, bilinear);
+                                                                                             W, C, bilinear, pd, make_fastdiv((uint32_t)(C / 4)));
   } else {
     warp_nhwc_generic_kernel<<<grid_for(n_pix, kThreads), kThreads, 0, st>>>(src, flow, dst, ref, norm_out, n_pix, H,
-                                                                             W, C, bilinear);
+                                                                             W, C, bilinear, pd);
   }
   return after_launch();
 }
@@ -428,7 +431,7 @@ extern "C" int vsr_warp_labels_u8(const uint8_t* labels, const float* flow, uint
   int64_t n_pix = (int64_t)B * H * W;
   int vec = (aligned(flow, 16) && aligned(dst, 4)) ? 1 : 0;
   warp_labels_kernel<<<grid_for(ceil_div64(n_pix, 4), kThreads), kThreads, 0, as_stream(stream)>>>(labels, flow, dst,
-                                                                                                  n_pix, H, W, vec);
+                                                                                                  n_pix, H, W, vec, make_pixdecode(H, W));
   return after_launch();
 }
 
