@@ -77,6 +77,20 @@ int vsr_warp_labels_u8(const uint8_t* labels, const float* flow, uint8_t* dst,
 int vsr_channelnorm_forward(const float* input, float* output, int B, int C, int H, int W,
                             int norm_deg, vsr_stream_t stream);
 
+/* Backward passes of the two autograd Functions.
+ * ref: resample2d_cuda.cc:14-26 `resample2d_cuda_backward(input1, input2, gradOutput, gradInput1,
+ * gradInput2, kernel_size, bilinear)` -> resample2d_kernel.cu:75-198,244-323; channelnorm_cuda.cc
+ * `channelnorm_cuda_backward(input1, output, gradOutput, gradInput1, norm_deg)` ->
+ * channelnorm_kernel.cu:64-96.  All tensors NCHW f32 contiguous.  grad_input1 must be ZERO on entry
+ * (the reference's caller allocates it with .zero_(), resample2d.py:32): the 4-tap scatter adds into
+ * it with atomics, so it is deterministic only up to fp32 summation order; grad_input2 and the
+ * channel-norm gradient are bit-identical to the reference binary. */
+int vsr_resample2d_backward(const float* input1, const float* flow, const float* grad_output,
+                            float* grad_input1, float* grad_input2,
+                            int B, int C, int H, int W, int kernel_size, int bilinear, vsr_stream_t stream);
+int vsr_channelnorm_backward(const float* input, const float* output, const float* grad_output,
+                             float* grad_input, int B, int C, int H, int W, int norm_deg, vsr_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * a1 / a2: flow projection (forward splat + count + normalise + hole fill), SURVEY.md App. B.
  * ref surface: FlowProjectionModule.forward (FlowProjectionModule.py:18-33) and

@@ -50,6 +50,10 @@ def lib():
         _lib.or_vos_threshold.restype = None
         _lib.or_mask_fill.argtypes = [_f32p, _u8p, _f32p, I, L]
         _lib.or_mask_fill.restype = None
+        _lib.or_resample2d_backward.argtypes = [_f32p] * 5 + [I, I, I, I]
+        _lib.or_resample2d_backward.restype = None
+        _lib.or_channelnorm_backward.argtypes = [_f32p] * 4 + [I, I, L]
+        _lib.or_channelnorm_backward.restype = None
     return _lib
 
 
@@ -135,6 +139,30 @@ def channelnorm_nhwc(x):
     out = np.zeros((B, H, W), np.float32)
     lib().or_channelnorm(_p(x, _f32p), _p(out, _f32p), B, C, H, W, H * W * C, 1, W * C, C)
     return out
+
+
+def resample2d_backward(input1, flow, grad_output):
+    """(grad_input1, grad_input2), NCHW.  ref: resample2d_kernel.cu:75-198, resample2d.py:25-39."""
+    input1 = _c(input1, np.float32)
+    flow = _c(flow, np.float32)
+    grad_output = _c(grad_output, np.float32)
+    B, C, H, W = input1.shape
+    g1 = np.zeros_like(input1)
+    g2 = np.zeros_like(flow)
+    lib().or_resample2d_backward(_p(input1, _f32p), _p(flow, _f32p), _p(grad_output, _f32p), _p(g1, _f32p), _p(g2, _f32p),
+                                 B, C, H, W)
+    return g1, g2
+
+
+def channelnorm_backward(x, out, grad_output):
+    """ref: channelnorm_kernel.cu:64-96."""
+    x = _c(x, np.float32)
+    out = _c(out, np.float32)
+    grad_output = _c(grad_output, np.float32)
+    B, C, H, W = x.shape
+    g = np.zeros_like(x)
+    lib().or_channelnorm_backward(_p(x, _f32p), _p(out, _f32p), _p(grad_output, _f32p), _p(g, _f32p), B, C, H * W)
+    return g
 
 
 def flow_projection(flow, inv_depth=None, threads=1):

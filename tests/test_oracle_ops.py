@@ -110,3 +110,40 @@ def test_flow_projection_nan_flow_is_skipped():
     flow[0, 1, 1, 0] = np.nan
     _, _, count, _ = orc.flow_projection(flow)
     assert count.sum() == 4 * 8
+
+
+def test_backward_oracles_against_torch_autograd():
+    """CPU: the backward restatements vs torch autograd of an equivalent differentiable formulation
+    (positive coordinates only, where the reference's int() truncation equals floor)."""
+    import torch
+    from oracle import oracle as orc
+    g = torch.Generator().manual_seed(0)
+    B, C, H, W = 1, 3, 12, 16
+    img = torch.rand((B, C, H, W), generator=g, dtype=torch.float64)
+    flow = torch.rand((B, 2, H, W), generator=g, dtype=torch.float64) * 1.5 + 0.1     # keeps x+dx > 0
+    flow[:, 0, :, -3:] = 0.25
+    flow[:, 1, -3:, :] = 0.25                                                          # stay inside: no clamping
+    gout = torch.randn((B, C, H, W), generator=g, dtype=torch.float64)
+    imgt = img.clone().requires_grad_(True)
+    ft = flow.clone().requires_grad_(True)
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float64), torch.arange(W, dtype=torch.float64), indexing="ij")
+    xf, yf = xs + ft[:, 0], ys + ft[:, 1]
+    x0, y0 = xf.detach().floor(), yf.detach().floor()
+    a, b = xf - x0, yf - y0
+    x0i, y0i = x0.long().clamp(0, W - 1), y0.long().clamp(0, H - 1)
+    x1i, y1i = (x0i + 1).clamp(0, W - 1), (y0i + 1).clamp(0, H - 1)
+
+    def tap(yy, xx):
+        return imgt[0][:, yy[0], xx[0]]
+
+    out = (1 - a) * (1 - b) * tap(y0i, x0i) + a * (1 - b) * tap(y0i, x1i) + (1 - a) * b * tap(y1i, x0i) + a * b * tap(y1i, x1i)
+    (out * gout[0]).sum().backward()
+    g1, g2 = orc.resample2d_backward(img.float().numpy(), flow.float().numpy(), gout.float().numpy())
+    assert np.abs(g1 - imgt.grad.numpy()).max() < 1e-4
+    assert np.abs(g2 - ft.grad.numpy()).max() < 1e-4
+    x = torch.randn((2, 3, 5, 7), generator=g, dtype=torch.float64).requires_grad_(True)
+    n = (x * x).sum(1, keepdim=True).sqrt()
+    go = torch.randn(n.shape, generator=g, dtype=torch.float64)
+    (n * go).sum().backward()
+    got = orc.channelnorm_backward(x.detach().float().numpy(), n.detach().float().numpy(), go.float().numpy())
+    assert np.abs(got - x.grad.numpy()).max() < 1e-5

@@ -443,3 +443,143 @@ extern "C" int vsr_channelnorm_forward(const float* input, float* output, int B,
   channelnorm_nchw_kernel<<<grid_for(n, kThreads), kThreads, 0, as_stream(stream)>>>(input, output, B, C, H, W);
   return after_launch();
 }
+
+// ---------------------------------------------------------------------------------------------
+// Backward passes: complete the autograd Function surfaces.
+//   ref: resample2d_kernel.cu:75-125 (gradient w.r.t. input1: 4-tap scatter with atomicAdd),
+//        :127-198 (gradient w.r.t. the flow), channelnorm_kernel.cu:64-96.
+// The reference's quirks are kept: the scatter's fractional parts use int() truncation, not floor
+// (:105-106), its taps use floor (:111-114), `bilinear` is ignored, kernel_size must be 1.
+// ---------------------------------------------------------------------------------------------
+namespace vsr {
+namespace {
+
+__device__ __forceinline__ void red_add_f32(float* addr, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+
+// One thread per (b, y, x): taps and weights once, then the channel loop (the reference spends one
+// thread per (b, c, y, x) and recomputes them C times).
+__global__ void __launch_bounds__(kThreads)
+resample2d_backward_input1_kernel(const float* __restrict__ flow, const float* __restrict__ gout, float* __restrict__ gin1,
+                                  int B, int C, int H, int W, const PixDecode pd) {
+  const int64_t HW = (int64_t)H * W;
+  const int64_t n = (int64_t)B * HW;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int x, y, b;
+    decode_pix((uint32_t)i, pd, b, y, x);
+    const float* fl = flow + (int64_t)b * 2 * HW + (int64_t)y * W + x;
+    const float dx = __ldg(fl), dy = __ldg(fl + HW);
+    const float xf = __fadd_rn((float)x, dx), yf = __fadd_rn((float)y, dy);
+    const float alpha = __fsub_rn(xf, (float)__float2int_rz(xf));     // :105 int(), not floor
+    const float beta = __fsub_rn(yf, (float)__float2int_rz(yf));      // :106
+    const int xL = max(min((int)floorf(xf), W - 1), 0);
+    const int xR = max(min((int)__fadd_rn(floorf(xf), 1.0f), W - 1), 0);
+    const int yT = max(min((int)floorf(yf), H - 1), 0);
+    const int yB = max(min((int)__fadd_rn(floorf(yf), 1.0f), H - 1), 0);
+    const float ia = __fsub_rn(1.0f, alpha), ib = __fsub_rn(1.0f, beta);
+    const float wTL = __fmul_rn(ia, ib), wTR = __fmul_rn(alpha, ib), wBL = __fmul_rn(ia, beta), wBR = __fmul_rn(alpha, beta);
+    const int64_t oTL = (int64_t)yT * W + xL, oTR = (int64_t)yT * W + xR, oBL = (int64_t)yB * W + xL, oBR = (int64_t)yB * W + xR;
+    for (int c = 0; c < C; ++c) {
+      const float g = __ldg(gout + ((int64_t)b * C + c) * HW + (int64_t)y * W + x);
+      float* plane = gin1 + ((int64_t)b * C + c) * HW;
+      red_add_f32(plane + oTL, __fmul_rn(wTL, g));
+      red_add_f32(plane + oTR, __fmul_rn(wTR, g));
+      red_add_f32(plane + oBL, __fmul_rn(wBL, g));
+      red_add_f32(plane + oBR, __fmul_rn(wBR, g));
+    }
+  }
+}
+
+// One thread per (b, y, x) computes both flow-gradient channels (the reference: one thread per
+// channel, each re-reading the C taps).  The accumulation order and the FMA contraction of
+// `output += gamma * g * in` are the reference binary's, so the result is bit-identical.
+__global__ void __launch_bounds__(kThreads)
+resample2d_backward_input2_kernel(const float* __restrict__ in1, const float* __restrict__ flow,
+                                  const float* __restrict__ gout, float* __restrict__ gin2, int B, int C, int H, int W,
+                                  const PixDecode pd) {
+  const int64_t HW = (int64_t)H * W;
+  const int64_t n = (int64_t)B * HW;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int x, y, b;
+    decode_pix((uint32_t)i, pd, b, y, x);
+    const float* fl = flow + (int64_t)b * 2 * HW + (int64_t)y * W + x;
+    const float dx = __ldg(fl), dy = __ldg(fl + HW);
+    const float xf = __fadd_rn((float)x, dx), yf = __fadd_rn((float)y, dy);
+    const float fx0 = floorf(xf), fy0 = floorf(yf);
+    const int xL = max(min((int)fx0, W - 1), 0);
+    const int xR = max(min((int)__fadd_rn(fx0, 1.0f), W - 1), 0);
+    const int yT = max(min((int)fy0, H - 1), 0);
+    const int yB = max(min((int)__fadd_rn(fy0, 1.0f), H - 1), 0);
+    const float gx = __fsub_rn(1.0f, __fsub_rn(yf, fy0));   // channel 0 (dx): gamma = 1 - (yf - floor(yf)), :179
+    const float gy = __fsub_rn(1.0f, __fsub_rn(xf, fx0));   // channel 1 (dy): gamma = 1 - (xf - floor(xf)), :166
+    const float igx = __fsub_rn(1.0f, gx), igy = __fsub_rn(1.0f, gy);
+    const int64_t oTL = (int64_t)yT * W + xL, oTR = (int64_t)yT * W + xR, oBL = (int64_t)yB * W + xL, oBR = (int64_t)yB * W + xR;
+    float out0 = 0.0f, out1 = 0.0f;
+    for (int ch = 0; ch < C; ++ch) {
+      const float g = __ldg(gout + ((int64_t)b * C + ch) * HW + (int64_t)y * W + x);
+      const float* p = in1 + ((int64_t)b * C + ch) * HW;
+      const float tl = __ldg(p + oTL), tr = __ldg(p + oTR), bl = __ldg(p + oBL), br = __ldg(p + oBR);
+      // c % 2 == 0 (:178-189): +g*TR -g*TL +(1-g)*BR -(1-g)*BL
+      const float a0 = __fmul_rn(gx, g), b0 = __fmul_rn(igx, g);
+      out0 = fmaf(a0, tr, out0);
+      out0 = fmaf(-a0, tl, out0);
+      out0 = fmaf(b0, br, out0);
+      out0 = fmaf(-b0, bl, out0);
+      // c % 2 == 1 (:165-176): +g*BL -g*TL +(1-g)*BR -(1-g)*TR
+      const float a1 = __fmul_rn(gy, g), b1 = __fmul_rn(igy, g);
+      out1 = fmaf(a1, bl, out1);
+      out1 = fmaf(-a1, tl, out1);
+      out1 = fmaf(b1, br, out1);
+      out1 = fmaf(-b1, tr, out1);
+    }
+    float* o = gin2 + (int64_t)b * 2 * HW + (int64_t)y * W + x;
+    o[0] = out0;
+    o[HW] = out1;
+  }
+}
+
+// channelnorm_kernel.cu:64-96: val = float(g * x) / (double(out) + 1e-9), rounded to fp32
+__global__ void __launch_bounds__(kThreads)
+channelnorm_backward_kernel(const float* __restrict__ in, const float* __restrict__ out, const float* __restrict__ gout,
+                            float* __restrict__ gin, int C, int64_t HW, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / (C * HW);
+    const int64_t p = i % HW;
+    const int64_t oi = b * HW + p;
+    const float num = __fmul_rn(__ldg(gout + oi), __ldg(in + i));
+    gin[i] = __double2float_rn(__ddiv_rn((double)num, __dadd_rn((double)__ldg(out + oi), 1e-9)));
+  }
+}
+
+}  // namespace
+}  // namespace vsr
+
+extern "C" int vsr_resample2d_backward(const float* input1, const float* flow, const float* grad_output,
+                                       float* grad_input1, float* grad_input2, int B, int C, int H, int W,
+                                       int kernel_size, int bilinear, vsr_stream_t stream) {
+  (void)bilinear;  // the reference's backward ignores it as well (resample2d_kernel.cu:75-198)
+  if (!input1 || !flow || !grad_output || !grad_input1 || !grad_input2 || B <= 0 || C <= 0 || H <= 0 || W <= 0)
+    return VSR_ERR_INVALID_ARG;
+  if (kernel_size != 1) return VSR_ERR_UNSUPPORTED;
+  if ((int64_t)B * H * W >= ((int64_t)1 << 32)) return VSR_ERR_UNSUPPORTED;
+  const int64_t n = (int64_t)B * H * W;
+  const PixDecode pd = make_pixdecode(H, W);
+  cudaStream_t st = as_stream(stream);
+  resample2d_backward_input1_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(flow, grad_output, grad_input1, B, C, H, W, pd);
+  int rc = after_launch();
+  if (rc) return rc;
+  resample2d_backward_input2_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(input1, flow, grad_output, grad_input2, B, C, H,
+                                                                               W, pd);
+  return after_launch();
+}
+
+extern "C" int vsr_channelnorm_backward(const float* input, const float* output, const float* grad_output,
+                                        float* grad_input, int B, int C, int H, int W, int norm_deg, vsr_stream_t stream) {
+  (void)norm_deg;
+  if (!input || !output || !grad_output || !grad_input || B <= 0 || C <= 0 || H <= 0 || W <= 0) return VSR_ERR_INVALID_ARG;
+  const int64_t HW = (int64_t)H * W, n = (int64_t)B * C * HW;
+  channelnorm_backward_kernel<<<grid_for(n, kThreads), kThreads, 0, as_stream(stream)>>>(input, output, grad_output,
+                                                                                        grad_input, C, HW, n);
+  return after_launch();
+}

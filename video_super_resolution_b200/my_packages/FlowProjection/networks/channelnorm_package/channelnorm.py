@@ -1,7 +1,7 @@
 """ChannelNorm -- the reference's autograd Function / Module surface
 (my_packages/FlowProjection/networks/channelnorm_package/channelnorm.py:6-39) over the B200 kernel.
 x (B,C,H,W) -> (B,1,H,W) = sqrt(sum_c x^2); `norm_deg` is accepted and ignored exactly as the
-reference kernel does (channelnorm_kernel.cu:53-59).  Forward only (hot path runs under no_grad)."""
+reference kernel does (channelnorm_kernel.cu:53-59); backward = g*x/(out+1e-9) (:64-96)."""
 from torch.autograd import Function
 from torch.nn.modules.module import Module
 
@@ -13,11 +13,14 @@ class ChannelNormFunction(Function):
     def forward(ctx, input1, norm_deg=2):
         assert input1.is_contiguous()
         ctx.norm_deg = norm_deg
-        return ops.channelnorm(input1, norm_deg)
+        output = ops.channelnorm(input1, norm_deg)
+        ctx.save_for_backward(input1, output)
+        return output
 
     @staticmethod
     def backward(ctx, grad_output):
-        raise NotImplementedError("ChannelNorm backward is outside the B200 hot path (SURVEY.md 8f, rank 2)")
+        input1, output = ctx.saved_tensors
+        return ops.channelnorm_backward(input1, output, grad_output.contiguous(), ctx.norm_deg), None
 
 
 class ChannelNorm(Module):

@@ -6,8 +6,8 @@
 
 input1 (B,C,H,W), input2 = flow (B,2,H,W), both contiguous fp32 CUDA (the reference asserts
 contiguity, :10-11).  The forward arithmetic is the reference kernel's, bit for bit
-(csrc/warp.cu).  Every hot-path use is under no_grad (network/video_super_resolution.py:24);
-backward is not part of the B200 path and raises.
+(csrc/warp.cu); backward is the reference's too (4-tap scatter with int() truncated fractions for
+input1, bit-identical flow gradient; resample2d_kernel.cu:75-198).
 """
 from torch.autograd import Function
 from torch.nn.modules.module import Module
@@ -20,13 +20,17 @@ class Resample2dFunction(Function):
     def forward(ctx, input1, input2, kernel_size=1, bilinear=True):
         assert input1.is_contiguous()
         assert input2.is_contiguous()
+        ctx.save_for_backward(input1, input2)
         ctx.kernel_size = kernel_size
         ctx.bilinear = bilinear
         return ops.resample2d(input1, input2, kernel_size, bilinear)
 
     @staticmethod
     def backward(ctx, grad_output):
-        raise NotImplementedError("Resample2d backward is outside the B200 hot path (SURVEY.md 8f, rank 2)")
+        grad_output = grad_output.contiguous()
+        input1, input2 = ctx.saved_tensors
+        g1, g2 = ops.resample2d_backward(input1, input2, grad_output, ctx.kernel_size, ctx.bilinear)
+        return g1, g2, None, None
 
 
 class Resample2d(Module):

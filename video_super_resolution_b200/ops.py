@@ -56,6 +56,37 @@ def resample2d(input1: torch.Tensor, flow: torch.Tensor, kernel_size: int = 1, b
     return out
 
 
+def resample2d_backward(input1: torch.Tensor, flow: torch.Tensor, grad_output: torch.Tensor, kernel_size: int = 1,
+                        bilinear: bool = True):
+    """(grad_input1, grad_input2) of Resample2d.  ref: Resample2dFunction.backward (resample2d.py:25-39)."""
+    for t, n in ((input1, "input1"), (flow, "input2"), (grad_output, "grad_output")):
+        _req(t, torch.float32, n)
+    B, C, H, W = grad_output.shape
+    if tuple(input1.shape) != (B, C, H, W) or tuple(flow.shape) != (B, 2, H, W):
+        raise ValueError("resample2d_backward: input1/grad_output (B,C,H,W) and flow (B,2,H,W) must agree")
+    g1 = torch.zeros_like(input1)                     # the scatter accumulates into it (resample2d.py:32)
+    g2 = torch.empty_like(flow)
+    with torch.cuda.device(input1.device):
+        _lib.check(_lib.lib().vsr_resample2d_backward(input1.data_ptr(), flow.data_ptr(), grad_output.data_ptr(),
+                                                      g1.data_ptr(), g2.data_ptr(), B, C, H, W, int(kernel_size),
+                                                      int(bool(bilinear)), _stream()), "resample2d_backward")
+    return g1, g2
+
+
+def channelnorm_backward(x: torch.Tensor, out: torch.Tensor, grad_output: torch.Tensor, norm_deg: int = 2):
+    """ref: ChannelNormFunction.backward (channelnorm.py:20-29)."""
+    for t, n in ((x, "input1"), (out, "output"), (grad_output, "grad_output")):
+        _req(t, torch.float32, n)
+    B, C, H, W = x.shape
+    if tuple(out.shape) != (B, 1, H, W) or tuple(grad_output.shape) != (B, 1, H, W):
+        raise ValueError("channelnorm_backward: output / grad_output must be (B,1,H,W)")
+    g = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().vsr_channelnorm_backward(x.data_ptr(), out.data_ptr(), grad_output.data_ptr(), g.data_ptr(),
+                                                       B, C, H, W, int(norm_deg), _stream()), "channelnorm_backward")
+    return g
+
+
 def warp(src: torch.Tensor, flow: torch.Tensor, bilinear: bool | int = True, ref: torch.Tensor | None = None):
     """Channels-last warp: src (B,H,W,C), flow (B,H,W,2) -> (B,H,W,C).  With `ref` (B,H,W,C) also
     returns the per-pixel L2 norm of (ref - warped), (B,H,W) (models.py:86-88 fused).
