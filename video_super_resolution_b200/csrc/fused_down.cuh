@@ -32,7 +32,8 @@ namespace vsr {
 
 constexpr int kFusedEpiWarps = 16;   // 4 per TMEM lane quarter: one sub-position / one tap each
 constexpr int kFusedWdWarp = 2 + kFusedEpiWarps;             // last warp: streams the conv weights
-constexpr int kFusedThreads = 32 * (kFusedWdWarp + 1);
+constexpr int kFusedBWarp = kFusedWdWarp + 1;                // issues the phase-B MMAs (HAS_TRAN)
+constexpr int kFusedThreads = 32 * (kFusedBWarp + 1);
 constexpr int kFusedMaxStages = 16;
 constexpr int kWdGroupBytes = 128 * 128 * 2; // 8x8-s4 weights of one sub-position group: 2 chunks [128 n][64 k]
 constexpr int kWdRingBytes = 2 * kWdGroupBytes;  // streamed per group from L2 through a 2-deep ring
@@ -222,15 +223,15 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 || (HAS_TRAN && warp == kFusedBWarp)) {
+    // ===================== MMA issuers =====================
     // One thread runs the whole role (no warp-wide waits / __syncwarp per box): timing experiments
     // showed this thread's instruction stream to be co-critical with HBM (each box costs it a barrier
     // wait, four MMA issues and a commit), so descriptors are pre-built and only offsets are added.
     if (lane == 0) {
     constexpr uint32_t idesc_a = make_idesc(32);
     constexpr uint32_t idesc_b = make_idesc(128);
-    if (HAS_TRAN) mbar_wait(w_full, 0);
+    if (HAS_TRAN && warp == 1) mbar_wait(w_full, 0);
     tc_fence_after();
     int s = 0;
     uint32_t phase = 0;
@@ -303,16 +304,16 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
       if (g == 3) { ++n_b[tb]; tb ^= 1; }
     };
 
+    // HAS_TRAN: this thread issues phase A only; phase B has its own issuing thread (warp kFusedBWarp), so
+    // that waiting for the converted tile / the weights never holds up the consumption of TMA stages.
+    // tcgen05.commit tracks the MMAs of the issuing thread, so each thread signals exactly its own work.
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       if (HAS_TRAN) {
-        issue_a(0);
-        issue_a(1);
-        issue_b(0);
-        issue_a(2);
-        issue_b(1);
-        issue_a(3);
-        issue_b(2);
-        issue_b(3);
+        if (warp == 1) {
+          for (int g = 0; g < 4; ++g) issue_a(g);
+        } else {
+          for (int g = 0; g < 4; ++g) issue_b(g);
+        }
       } else {
         for (int g = 0; g < 4; ++g) issue_b(g);
       }
@@ -338,7 +339,7 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
           ++n_wd;
         }
     }
-  } else {
+  } else if (warp >= 2 && warp < 2 + kFusedEpiWarps) {
     // ===================== epilogue warps 2..17 =====================
     // warp -> TMEM lane quarter q = warp % 4 (hardware rule) and sub = which of the 4 column groups
     // (phase A: sub-position within the group; final: tap) this warp handles
