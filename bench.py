@@ -298,6 +298,19 @@ def run_b200(args, rank, world, local_rank):
         ach = d["bytes"] / d["ms"] / 1e6
         roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
                 "traffic": None}
+    # DRAM bytes per launch of that kernel class from the committed ncu capture of the same shapes
+    # (profiles/traffic_r01f.json: dram__bytes_read.sum + dram__bytes_write.sum, one pass, C2 size)
+    try:
+        pat = {"fused_downtran_conv8x8s4": "fused_down_kernel", "deconv8x8s4": "igemm_kernel<1, 32, 256>",
+               "pointwise_lr": "igemm_kernel<0, 32, 32>", "finalize_lr": "finalize_lr_kernel",
+               "conv_out3x3": "igemm_kernel<2, 32, 32>", "conv_in_gemm": "igemm_kernel<0, 32, 128>",
+               "fc_fuse": "fc_fuse_kernel", "im2col": "im2col_kernel"}[dom]
+        tr = [t["dram_read_bytes"] + t["dram_write_bytes"]
+              for t in json.load(open(os.path.join(ROOT, "profiles", "traffic_r01f.json"))) if pat in t["kernel"]]
+        roof["traffic"] = sum(tr) / len(tr) if tr else None
+        roof["traffic_source"] = "profiles/traffic_r01f.json (ncu, same shapes, average over the class's launches)"
+    except Exception:
+        pass
     roof.update({"kernel": dom, "launches_per_step": d["launches"], "avg_launch_ms": d["ms"] / d["launches"],
                  "algorithmic_per_launch": {"flops": d["flops"] / d["launches"], "bytes": d["bytes"] / d["launches"]},
                  "peak_source": peaks["source"] + " (sustained bf16 / copy GB/s)", "share_of_step": d["ms"] / (ms_total / args.steps)})
