@@ -91,6 +91,22 @@ int vsr_resample2d_backward(const float* input1, const float* flow, const float*
 int vsr_channelnorm_backward(const float* input, const float* output, const float* grad_output,
                              float* grad_input, int B, int C, int H, int W, int norm_deg, vsr_stream_t stream);
 
+/* FlowNetC cost volume (outside the warp-and-fuse hot path).
+ * ref: correlation_cuda.cc:10-86 `correlation_forward_cuda(input1, input2, rInput1, rInput2, output,
+ * pad_size, kernel_size, max_displacement, stride1, stride2, corr_type_multiply)` ->
+ * correlation_cuda_kernel.cu:46-147.  input1/input2 (B,C,H,W) f32 NCHW; output (B, D*D, outH, outW)
+ * f32 with D = 2*(max_displacement/stride2)+1 and outH/outW from vsr_correlation_output_shape (the
+ * reference resizes `output` itself; here the caller allocates, as everywhere in this ABI).  No
+ * padded NHWC copies (`rInput1/2`) are needed.  fp32 results agree with the reference to fp32
+ * summation order (tested <= 1e-5 relative).  Positions outside the image are zeros for any pad_size;
+ * the reference is only defined for pad_size >= max_displacement + (kernel_size-1)/2 (with less it
+ * indexes outside its padded copies). */
+int vsr_correlation_output_shape(int C, int H, int W, int pad_size, int kernel_size, int max_displacement,
+                                 int stride1, int stride2, int* out_channels, int* out_h, int* out_w);
+int vsr_correlation_forward(const float* input1, const float* input2, float* output, int B, int C, int H, int W,
+                            int pad_size, int kernel_size, int max_displacement, int stride1, int stride2,
+                            int corr_multiply, vsr_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * a1 / a2: flow projection (forward splat + count + normalise + hole fill), SURVEY.md App. B.
  * ref surface: FlowProjectionModule.forward (FlowProjectionModule.py:18-33) and

@@ -5,6 +5,7 @@ the GPU box with the tree).  TEST INFRASTRUCTURE ONLY -- the product never loads
 
 Sources are compiled where they lie under /root/reference (nothing is copied into the repo):
   resample2d_cuda   resample2d_cuda.cc + resample2d_kernel.cu        -- unmodified
+  correlation_cuda  correlation_cuda.cc + correlation_cuda_kernel.cu -- same one-token fix as channelnorm
   channelnorm_cuda  channelnorm_cuda.cc + channelnorm_kernel.cu      -- the kernel file needs the
                     one-token fix `.type()` -> `.scalar_type()` (AT_DISPATCH on
                     DeprecatedTypeProperties no longer compiles with torch 2.x,
@@ -45,6 +46,13 @@ def build():
         with open(patched, "w") as f:
             f.write(re.sub(r"\.type\(\)", ".scalar_type()", src))
         jobs.append(("channelnorm_cuda", [os.path.join(d, "channelnorm_cuda.cc"), patched], [d]))
+        d = os.path.join(REF, "correlation_package")
+        patched = os.path.join(tmp, "correlation_cuda_kernel.cu")
+        with open(os.path.join(d, "correlation_cuda_kernel.cu")) as f:
+            src = f.read()
+        with open(patched, "w") as f:
+            f.write(re.sub(r"\.type\(\)", ".scalar_type()", src))
+        jobs.append(("correlation_cuda", [os.path.join(d, "correlation_cuda.cc"), patched], [d]))
         for name, sources, inc in jobs:
             bdir = os.path.join(tmp, "b_" + name)
             os.makedirs(bdir)

@@ -54,6 +54,8 @@ def lib():
         _lib.or_resample2d_backward.restype = None
         _lib.or_channelnorm_backward.argtypes = [_f32p] * 4 + [I, I, L]
         _lib.or_channelnorm_backward.restype = None
+        _lib.or_correlation.argtypes = [_f32p] * 3 + [I] * 11
+        _lib.or_correlation.restype = None
     return _lib
 
 
@@ -163,6 +165,21 @@ def channelnorm_backward(x, out, grad_output):
     g = np.zeros_like(x)
     lib().or_channelnorm_backward(_p(x, _f32p), _p(out, _f32p), _p(grad_output, _f32p), _p(g, _f32p), B, C, H * W)
     return g
+
+
+def correlation(input1, input2, pad_size=3, kernel_size=3, max_displacement=20, stride1=1, stride2=2):
+    """FlowNetC cost volume, NCHW.  ref: correlation_cuda.cc:25-42, correlation_cuda_kernel.cu:73-147."""
+    input1 = _c(input1, np.float32)
+    input2 = _c(input2, np.float32)
+    B, C, H, W = input1.shape
+    border = (kernel_size - 1) // 2 + max_displacement
+    outH = -(-(H + 2 * pad_size - 2 * border) // stride1)
+    outW = -(-(W + 2 * pad_size - 2 * border) // stride1)
+    D = 2 * (max_displacement // stride2) + 1
+    out = np.zeros((B, D * D, outH, outW), np.float32)
+    lib().or_correlation(_p(input1, _f32p), _p(input2, _f32p), _p(out, _f32p), B, C, H, W, pad_size, kernel_size,
+                         max_displacement, stride1, stride2, outH, outW)
+    return out
 
 
 def flow_projection(flow, inv_depth=None, threads=1):

@@ -147,3 +147,26 @@ def test_backward_oracles_against_torch_autograd():
     (n * go).sum().backward()
     got = orc.channelnorm_backward(x.detach().float().numpy(), n.detach().float().numpy(), go.float().numpy())
     assert np.abs(got - x.grad.numpy()).max() < 1e-5
+
+
+def test_correlation_oracle_against_direct_numpy():
+    """CPU: or_correlation vs a direct numpy evaluation of the definition (correlation_cuda_kernel.cu:73-147)."""
+    from oracle import oracle as orc
+    rng = np.random.default_rng(3)
+    B, C, H, W, pad, k, md, s1, s2 = 1, 5, 9, 11, 4, 1, 4, 1, 2
+    a = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    b = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    got = orc.correlation(a, b, pad, k, md, s1, s2)
+    R = md // s2
+    D = 2 * R + 1
+    assert got.shape == (B, D * D, H, W)
+    ap = np.pad(a, ((0, 0), (0, 0), (pad, pad), (pad, pad)))
+    bp = np.pad(b, ((0, 0), (0, 0), (pad, pad), (pad, pad)))
+    for tj in range(-R, R + 1):
+        for ti in range(-R, R + 1):
+            ref = np.zeros((H, W))
+            for y in range(H):
+                for x in range(W):
+                    y1, x1 = y + md, x + md
+                    ref[y, x] = (ap[0, :, y1, x1].astype(np.float64) * bp[0, :, y1 + tj * s2, x1 + ti * s2]).sum() / C
+            assert np.abs(got[0, (tj + R) * D + ti + R] - ref).max() < 1e-5

@@ -118,3 +118,29 @@ def test_autograd_function_surfaces_backward():
         f2[0, 0, 10, 10] += eps
         num = (ChannelNorm()(Resample2d()(img.detach(), f2)).sum() - y.detach().sum()) / eps
     assert abs(num.item() - flow.grad[0, 0, 10, 10].item()) <= 0.05 * abs(num.item()) + 0.5
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(shape=(1, 64, 24, 40), pad=20, k=1, md=20, s1=1, s2=2),      # FlowNetC (FlowNetC.py:22), fewer channels
+    dict(shape=(2, 256, 16, 24), pad=20, k=1, md=20, s1=1, s2=2),     # FlowNetC channels
+    dict(shape=(1, 16, 20, 28), pad=5, k=3, md=4, s1=1, s2=1),        # 3x3 kernel window (pad >= md + 1: with a
+                                                                      # smaller pad the reference reads outside its padded copy)
+    dict(shape=(1, 8, 21, 37), pad=4, k=1, md=4, s1=2, s2=2),         # strided outputs
+])
+def test_reference_correlation_equals_oracle_and_product(cfg):
+    """correlation_cuda.forward of the reference binary (correlation_cuda_kernel.cu:46-147) vs oracle vs product;
+    fp32 summation order differs (32 strided partials + shuffle tree there), so compare to 1e-5 relative."""
+    ref = _ref("correlation_cuda")
+    g = torch.Generator().manual_seed(cfg["shape"][1])
+    a = torch.randn(cfg["shape"], generator=g).to(DEV)
+    b = torch.randn(cfg["shape"], generator=g).to(DEV)
+    r1, r2, out = a.new_empty(0), a.new_empty(0), a.new_empty(0)                # correlation.py:22-24
+    ref.forward(a, b, r1, r2, out, cfg["pad"], cfg["k"], cfg["md"], cfg["s1"], cfg["s2"], 1)
+    torch.cuda.synchronize()
+    want = out.cpu().numpy()
+    got = ops.correlation(a, b, cfg["pad"], cfg["k"], cfg["md"], cfg["s1"], cfg["s2"], 1)
+    assert tuple(got.shape) == want.shape
+    tol = 1e-5 * max(1.0, float(np.abs(want).max()))
+    assert np.abs(got.cpu().numpy() - want).max() <= tol
+    orc_out = orc.correlation(a.cpu().numpy(), b.cpu().numpy(), cfg["pad"], cfg["k"], cfg["md"], cfg["s1"], cfg["s2"])
+    assert np.abs(orc_out - want).max() <= tol

@@ -359,7 +359,7 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
 #pragma unroll 1
         for (int g = 0; g < 4; ++g) {
           const int buf = g & 1;
-          mbar_wait(&da_full[buf], m_a[buf] & 1);
+          mbar_wait_sleep(&da_full[buf], m_a[buf] & 1, (uint32_t)(p.debug >> 8));
           tc_fence_after();
           uint32_t o[16];
           if (p.debug & 2) {
@@ -399,7 +399,7 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
       // slot that has exactly one writer:  slot 2*dy   : tap (dy,0) + right neighbour's tap (dy,1)
       //                                     slot 2*dy+1 : tap (dy,1) arriving from the next tile
       //                                                   (only pixels with X % 16 == 15 have one)
-      mbar_wait(&db_full[tb], m_b[tb] & 1);
+      mbar_wait_sleep(&db_full[tb], m_b[tb] & 1, (uint32_t)(p.debug >> 8));
       tc_fence_after();
       if (p.debug & 4) {
         tc_fence_before();

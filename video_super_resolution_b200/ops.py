@@ -87,6 +87,27 @@ def channelnorm_backward(x: torch.Tensor, out: torch.Tensor, grad_output: torch.
     return g
 
 
+def correlation(input1: torch.Tensor, input2: torch.Tensor, pad_size: int = 3, kernel_size: int = 3,
+                max_displacement: int = 20, stride1: int = 1, stride2: int = 2, corr_multiply: int = 1) -> torch.Tensor:
+    """FlowNetC cost volume.  ref: CorrelationFunction.forward (correlation.py:9-30)."""
+    import ctypes
+    _req(input1, torch.float32, "input1")
+    _req(input2, torch.float32, "input2")
+    if input1.shape != input2.shape or input1.dim() != 4:
+        raise ValueError("correlation: two (B,C,H,W) tensors of the same shape expected")
+    B, C, H, W = input1.shape
+    oc, oh, ow = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    L = _lib.lib()
+    _lib.check(L.vsr_correlation_output_shape(C, H, W, pad_size, kernel_size, max_displacement, stride1, stride2,
+                                              ctypes.byref(oc), ctypes.byref(oh), ctypes.byref(ow)), "correlation shape")
+    out = torch.empty((B, oc.value, oh.value, ow.value), dtype=torch.float32, device=input1.device)
+    with torch.cuda.device(input1.device):
+        _lib.check(L.vsr_correlation_forward(input1.data_ptr(), input2.data_ptr(), out.data_ptr(), B, C, H, W, pad_size,
+                                             kernel_size, max_displacement, stride1, stride2, corr_multiply, _stream()),
+                   "correlation")
+    return out
+
+
 def warp(src: torch.Tensor, flow: torch.Tensor, bilinear: bool | int = True, ref: torch.Tensor | None = None):
     """Channels-last warp: src (B,H,W,C), flow (B,H,W,2) -> (B,H,W,C).  With `ref` (B,H,W,C) also
     returns the per-pixel L2 norm of (ref - warped), (B,H,W) (models.py:86-88 fused).
