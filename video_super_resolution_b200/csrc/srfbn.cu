@@ -503,7 +503,48 @@ fc_fuse_kernel(const float* __restrict__ maps, const float* __restrict__ fcw, fl
   const float* b0 = s_w + 32 * M;
   const float* w2 = b0 + 32;
   const float b2 = w2[32];
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+  // 4 consecutive outputs per thread: every weight read from shared memory feeds 4 FMAs (with one
+  // output per thread the kernel was bound by those LDS, not by the 12 B/pixel/map it streams)
+  const int64_t n4 = n >> 2;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (int64_t)gridDim.x * blockDim.x) {
+    float hid[4][32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float b = b0[j];
+      hid[0][j] = b; hid[1][j] = b; hid[2][j] = b; hid[3][j] = b;
+    }
+    for (int m0 = 0; m0 < M; m0 += 4) {
+      float4 vv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)       // four independent 16-byte loads in flight before the FMAs
+        vv[u] = (m0 + u < M) ? ldg_stream_f4(reinterpret_cast<const float4*>(maps + (int64_t)(m0 + u) * n) + q)
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (m0 + u < M) {
+          const float4 v = vv[u];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float w = w0[j * M + m0 + u];
+            hid[0][j] = fmaf(w, v.x, hid[0][j]);
+            hid[1][j] = fmaf(w, v.y, hid[1][j]);
+            hid[2][j] = fmaf(w, v.z, hid[2][j]);
+            hid[3][j] = fmaf(w, v.w, hid[3][j]);
+          }
+        }
+      }
+    }
+    float o[4] = {b2, b2, b2, b2};
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float w = w2[j];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[k] = fmaf(w, fmaxf(hid[k][j], 0.0f), o[k]);
+    }
+    reinterpret_cast<float4*>(y)[q] = make_float4(fmaxf(o[0], 0.0f), fmaxf(o[1], 0.0f), fmaxf(o[2], 0.0f), fmaxf(o[3], 0.0f));
+  }
+  // ragged tail (n is 48*h*w, a multiple of 4 for every LR size; kept for safety)
+  for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float hid[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) hid[j] = b0[j];
@@ -797,7 +838,7 @@ extern "C" int vsr_srfbn_forward(vsr_srfbn_plan* pl, const float* x, float* y, v
   mark();
   {
     const int64_t n = (int64_t)3 * 16 * c.h * c.w;
-    int64_t blocks = ceil_div64(n, 256);
+    int64_t blocks = ceil_div64(ceil_div64(n, 4), 256);
     if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
     fc_fuse_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const float*>(pl->ws + pl->o_premix),
                                                 reinterpret_cast<const float*>(pl->dev_w + pl->fc_off), y, c.num_maps, n);
