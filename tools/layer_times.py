@@ -36,7 +36,8 @@ def bw():
 
 
 def main():
-    bw()
+    if "--no-bw" not in sys.argv:
+        bw()
     M, h, w = 20, 270, 480
     torch.manual_seed(0)
     sr = SRProjectionModule(num_maps=M)
@@ -51,8 +52,14 @@ def main():
     ms = (ctypes.c_float * cap)()
     kc = (ctypes.c_int32 * cap)()
     n = L.vsr_srfbn_profile_launches(ent["plan"], ms, kc, cap)
+    tot = {}
     for i in range(n):
-        print(f"{i:4d} {L.vsr_srfbn_kernel_class_name(kc[i]).decode():28s} {ms[i] * 1e3:9.1f} us")
+        name = L.vsr_srfbn_kernel_class_name(kc[i]).decode()
+        tot[name] = tot.get(name, 0.0) + ms[i]
+        if "--summary" not in sys.argv:
+            print(f"{i:4d} {name:28s} {ms[i] * 1e3:9.1f} us")
+    for k, v in tot.items():
+        print(f"class {k:28s} {v:9.3f} ms")
     print("total", sum(ms[i] for i in range(n)), "ms")
 
 

@@ -52,6 +52,7 @@ struct alignas(64) IgemmParams {
   CUtensorMap out_map;         // EPI_DECONV block layout: 4-D (64 el, w+1, h+1, 8 pairs * B), box (64,16,2,1), 128B swizzle
   Chunk chunks[kMaxChunks];
   int32_t num_chunks;
+  int32_t cps;                 // K chunks per pipeline stage (one barrier round trip per stage, not per chunk)
   int32_t num_stages;
   // tile grid: total tiles = n_tiles * tiles_x * tiles_y * batch, n fastest
   int32_t n_tiles, tiles_x, tiles_y, batch;
@@ -70,6 +71,7 @@ struct alignas(64) IgemmParams {
   int32_t lr_h, lr_w;          // LR size (block-layout masks, deconv geometry)
   int32_t hrb_mask;            // EPI_ROWS flat over the HR block layout: zero the padding ring
   int32_t deconv_nhwc;         // EPI_DECONV: 1 = write plain NHWC HR instead of the block layout
+  int32_t debug;               // timing experiments (wrong results): bit0 no TMA stores, bit1 no TMEM reads/convert, bit2 no MMAs
   // EPI_CONV_OUT extras
   const float* skip_src;       // network input x (M,3,h,w) fp32
 };
@@ -318,7 +320,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
   const int b_region = ((p.num_chunks * kBBytes) + 1023) / 1024 * 1024;
   uint8_t* smem_b = smem;
   uint8_t* smem_a = smem + b_region;
-  uint8_t* tail = smem_a + p.num_stages * kABytes;
+  uint8_t* tail = smem_a + p.num_stages * p.cps * kABytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);          // [kMaxStages]
   uint64_t* empty_bar = full_bar + kMaxStages;                     // [kMaxStages]
   uint64_t* tmem_full = empty_bar + kMaxStages;                    // [2]
@@ -364,11 +366,15 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile(p, tile);
-        for (int kc = 0; kc < p.num_chunks; ++kc) {
+        for (int kc0 = 0; kc0 < p.num_chunks; kc0 += p.cps) {
+          const int nk = min(p.cps, p.num_chunks - kc0);
           mbar_wait(&empty_bar[s], phase ^ 1);
-          mbar_expect_tx(&full_bar[s], kABytes);
-          const Chunk c = p.chunks[kc];
-          tma_load_4d(smem_a + s * kABytes, &p.a_maps[c.map], &full_bar[s], c.c0, t.x0 + c.dx, t.y0 + c.dy, t.b);
+          mbar_expect_tx(&full_bar[s], (uint32_t)(nk * kABytes));
+          for (int j = 0; j < nk; ++j) {
+            const Chunk c = p.chunks[kc0 + j];
+            tma_load_4d(smem_a + (s * p.cps + j) * kABytes, &p.a_maps[c.map], &full_bar[s], c.c0, t.x0 + c.dx,
+                        t.y0 + c.dy, t.b);
+          }
           if (++s == p.num_stages) { s = 0; phase ^= 1; }
         }
       }
@@ -389,15 +395,20 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
         mbar_wait(&tmem_empty[as], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
-        for (int kc = 0; kc < p.num_chunks; ++kc) {
+        for (int kc0 = 0; kc0 < p.num_chunks; kc0 += p.cps) {
+          const int nk = min(p.cps, p.num_chunks - kc0);
           mbar_wait(&full_bar[s], phase);
           tc_fence_after();
-          const uint64_t a0 = dA + (uint64_t)((s * kABytes) >> 4);
-          const uint64_t b0 = dB + (uint64_t)((kc * kBBytes) >> 4);
+          for (int j = 0; j < nk; ++j) {
+            const int kc = kc0 + j;
+            const uint64_t a0 = dA + (uint64_t)(((s * p.cps + j) * kABytes) >> 4);
+            const uint64_t b0 = dB + (uint64_t)((kc * kBBytes) >> 4);
+            if (!(p.debug & 4))
 #pragma unroll
-          for (int k = 0; k < CK / 16; ++k) umma_bf16(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, (uint32_t)((kc | k) != 0));
-          umma_commit(&empty_bar[s]);                      // frees the A slot when these MMAs retire
-          if (kc == p.num_chunks - 1) umma_commit(&tmem_full[as]);
+            for (int k = 0; k < CK / 16; ++k) umma_bf16(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, (uint32_t)((kc | k) != 0));
+          }
+          umma_commit(&empty_bar[s]);                      // frees the stage when these MMAs retire
+          if (kc0 + nk >= p.num_chunks) umma_commit(&tmem_full[as]);
           if (++s == p.num_stages) { s = 0; phase ^= 1; }
         }
         if (++as == 2) { as = 0; acc_phase ^= 1; }
@@ -497,12 +508,18 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
           for (int c2 = 0; c2 < 2; ++c2) {
             const int cg = sub * 2 + c2;
             uint32_t v[32];
-            tmem_ld32(taddr + cg * 32, v);
-            tmem_ld_wait();
+            if (p.debug & 2) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = 0;
+            } else {
+              tmem_ld32(taddr + cg * 32, v);
+              tmem_ld_wait();
+            }
             if (c2 == 1) {
               tc_fence_before();
               mbar_arrive(&tmem_empty[as]);
             }
+            if (p.debug & 2) continue;
             const int s16 = t.n_tile * 8 + cg;
             const int ry = s16 >> 2, rx = s16 & 3;
             const int Yt = 4 * Y + ry - 2, Xt = 4 * X + rx - 2;
@@ -522,7 +539,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
           if (lane == 0) {
             // one box = this warp's 2 block rows x 16 blocks of one sub-position-pair plane; rows or
             // columns beyond the tensor edge are clipped by the TMA unit
-            if (t.y0 + 2 * q <= p.lr_h)
+            if (t.y0 + 2 * q <= p.lr_h && !(p.debug & 1))
               tma_store_4d(&p.out_map, stg, 0, t.x0, t.y0 + 2 * q, t.b * 8 + t.n_tile * 4 + sub);
             tma_store_commit();
           }

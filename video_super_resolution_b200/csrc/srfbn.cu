@@ -167,7 +167,8 @@ size_t variant_smem(int variant, int chunks, int stages) {
 
 void finish_layer(Layer& L, int ctas_per_sm) {
   IgemmParams& p = L.p;
-  L.smem = variant_smem(L.variant, p.num_chunks, p.num_stages);
+  if (p.cps < 1) p.cps = 1;
+  L.smem = variant_smem(L.variant, p.num_chunks, p.num_stages * p.cps);
   int64_t total = (int64_t)p.n_tiles * p.tiles_x * p.tiles_y * p.batch;
   int64_t g = (int64_t)kNumSMs * ctas_per_sm;
   if (g > total) g = total;
@@ -251,7 +252,8 @@ int build_deconv(Layer& L, const void* x, int B, int h, int w, const void* w_dev
     p.chunks[t].c0 = 0;
   }
   p.num_chunks = 4;
-  p.num_stages = 11;    // ~3 tiles of lookahead: with 4 (= one tile) every tile paid a full load latency
+  p.cps = 4;            // the 4 taps of a tile share one barrier round trip (the handshake loop of the issuing
+  p.num_stages = 2;     // threads, not the MMAs, is this kernel's floor: ~2000 cycles per tile with one per tap)
   p.n_tiles = 2;
   p.tiles_x = ceil_div(w + 1, kTW);
   p.tiles_y = ceil_div(h + 1, kTH);
@@ -265,6 +267,14 @@ int build_deconv(Layer& L, const void* x, int B, int h, int w, const void* w_dev
   p.lr_h = h;
   p.lr_w = w;
   p.deconv_nhwc = nhwc;
+  {
+    const char* e = getenv("VSR_DECONV_DEBUG");
+    p.debug = e ? atoi(e) : 0;
+    e = getenv("VSR_DECONV_CPS");        // tuning knobs: chunks per stage (1, 2 or 4) and ring depth
+    if (e && (atoi(e) == 1 || atoi(e) == 2 || atoi(e) == 4)) p.cps = atoi(e);
+    e = getenv("VSR_DECONV_STAGES");
+    if (e && atoi(e) >= 1 && atoi(e) * p.cps <= 12) p.num_stages = atoi(e);
+  }
   if (!nhwc) {
     EncodeTiledFn enc = encode_fn();
     if (!enc) return VSR_ERR_STATE;
