@@ -160,18 +160,19 @@ int vsr_estimate_slot(const float* hr, const uint8_t* mask, float* slot, int h, 
  *
  * A plan owns nothing on the device: weights live in a caller buffer that
  * vsr_srfbn_pack_weights fills, activations in a caller workspace.
- * Geometry: x4 only (k=8,s=4,p=2, SRProjectionModule.py:101-103), num_features=32,
- * num_groups=6, num_steps>=1, M stacked maps (reference: 8).
+ * Geometry: x4 (k=8,s=4,p=2, the reference's only one, SRProjectionModule.py:101-103) or x2
+ * (k=6,s=2,p=2, SRFBN's x2 geometry -- BASELINE config C4; the reference has no x2 code);
+ * num_features=32, num_groups=6, num_steps>=1, M stacked maps (reference: 8).
  * ---------------------------------------------------------------------------------------- */
 typedef struct vsr_srfbn_plan vsr_srfbn_plan;
 
 typedef struct vsr_srfbn_config {
   int32_t num_maps;      /* M: maps stacked along dim 0 (video_super_resolution.py:40), fc in-features */
-  int32_t h, w;          /* LR size; output is (4h, 4w)                                          */
+  int32_t h, w;          /* LR size; output is (upscale*h, upscale*w)                            */
   int32_t num_steps;     /* SRProjectionModule num_steps (default 3)                             */
   int32_t num_groups;    /* must be 6                                                            */
   int32_t num_features;  /* must be 32                                                           */
-  int32_t upscale;       /* must be 4                                                            */
+  int32_t upscale;       /* 4 or 2                                                               */
 } vsr_srfbn_config;
 
 /* Host-side weights in the reference's state-dict layout, fp32, host
@@ -188,10 +189,10 @@ typedef struct vsr_srfbn_weights {
   const float* compress_in_w;      /* (32,64,1,1)  */
   const float* compress_in_b;
   float compress_in_slope;
-  const float* up_w[6];            /* ConvTranspose (32 in,32 out,8,8) */
+  const float* up_w[6];            /* ConvTranspose (32 in,32 out,8,8); x2: (32,32,6,6) */
   const float* up_b[6];
   float up_slope[6];
-  const float* down_w[6];          /* Conv (32 out,32 in,8,8) */
+  const float* down_w[6];          /* Conv (32 out,32 in,8,8); x2: (32,32,6,6) */
   const float* down_b[6];
   float down_slope[6];
   const float* uptran_w[5];        /* (32,32*(i+2),1,1), i=0..4 */
@@ -203,7 +204,7 @@ typedef struct vsr_srfbn_weights {
   const float* compress_out_w;     /* (32,192,1,1) */
   const float* compress_out_b;
   float compress_out_slope;
-  const float* out_w;              /* ConvTranspose (32,32,8,8) */
+  const float* out_w;              /* ConvTranspose (32,32,8,8); x2: (32,32,6,6) */
   const float* out_b;
   float out_slope;
   const float* conv_out_w;         /* (3,32,3,3), no activation */
@@ -225,7 +226,7 @@ int vsr_srfbn_pack_weights(const vsr_srfbn_plan* plan, const vsr_srfbn_weights* 
 /* Binds device buffers (packed weights + workspace) and builds the TMA descriptors. */
 int vsr_srfbn_bind(vsr_srfbn_plan* plan, const void* dev_weights, void* dev_workspace,
                    size_t workspace_bytes);
-/* x: (M,3,h,w) f32 NCHW, 0..255 (video_super_resolution.py:40,62); y: (1,3,4h,4w) f32. */
+/* x: (M,3,h,w) f32 NCHW, 0..255 (video_super_resolution.py:40,62); y: (1,3,s*h,s*w) f32. */
 int vsr_srfbn_forward(vsr_srfbn_plan* plan, const float* x, float* y, vsr_stream_t stream);
 /* Per-launch accounting for bench.py: with profiling enabled, vsr_srfbn_forward brackets every
  * kernel launch with CUDA events on the caller's stream; vsr_srfbn_profile_read waits for the last
@@ -240,7 +241,7 @@ int vsr_srfbn_profile_read(vsr_srfbn_plan* plan, double* ms, int32_t* launches, 
  * launches (<0 on error) and fills at most `capacity` entries */
 int vsr_srfbn_profile_launches(vsr_srfbn_plan* plan, float* ms, int32_t* kclass, int32_t capacity);
 
-/* Test hook: per-map network output before the fc fuse, (M,3,4h,4w) f32 (SRProjectionModule.py:143);
+/* Test hook: per-map network output before the fc fuse, (M,3,s*h,s*w) f32 (SRProjectionModule.py:143);
  * valid after vsr_srfbn_forward on the same stream. */
 int vsr_srfbn_debug_premix(const vsr_srfbn_plan* plan, float* out_maps, vsr_stream_t stream);
 

@@ -21,10 +21,13 @@ import torch
 import torch.nn.functional as F
 
 RGB_MEAN = (0.4488, 0.4371, 0.4040)  # SRProjectionModule.py:105
+# (kernel, stride, padding) of the projection units: x4 is the reference's (SRProjectionModule.py:10-12,
+# 101-103); x2 is SRFBN's geometry, used for BASELINE config C4 (the reference has none)
+GEOMETRY = {4: (8, 4, 2), 2: (6, 2, 2)}
 
 
 def init_state_dict(num_maps: int = 8, num_features: int = 32, num_groups: int = 6,
-                    seed: int = 0, gain: float = 1.0) -> dict:
+                    seed: int = 0, gain: float = 1.0, upscale: int = 4) -> dict:
     """Random weights with the reference's default initialisers (nn.Conv2d / ConvTranspose2d /
     Linear defaults, PReLU 0.2, MeanShift fixed) and state-dict names.  `gain` scales every conv
     weight: with the default initialisers the signal decays by ~0.6x per layer and the conv branch
@@ -37,6 +40,7 @@ def init_state_dict(num_maps: int = 8, num_features: int = 32, num_groups: int =
     torch.manual_seed(int(torch.randint(0, 2 ** 31 - 1, (1,), generator=g)))
     try:
         nf = num_features
+        ksp = GEOMETRY[upscale]
         sd = {}
 
         def put(prefix, mod, act=True):
@@ -54,13 +58,13 @@ def init_state_dict(num_maps: int = 8, num_features: int = 32, num_groups: int =
         put("feat_in", nn.Conv2d(4 * nf, nf, 1))
         put("block.compress_in", nn.Conv2d(2 * nf, nf, 1))
         for i in range(num_groups):
-            put(f"block.upBlocks.{i}", nn.ConvTranspose2d(nf, nf, 8, 4, 2))
-            put(f"block.downBlocks.{i}", nn.Conv2d(nf, nf, 8, 4, 2))
+            put(f"block.upBlocks.{i}", nn.ConvTranspose2d(nf, nf, *ksp))
+            put(f"block.downBlocks.{i}", nn.Conv2d(nf, nf, *ksp))
             if i > 0:
                 put(f"block.uptranBlocks.{i - 1}", nn.Conv2d(nf * (i + 1), nf, 1))
                 put(f"block.downtranBlocks.{i - 1}", nn.Conv2d(nf * (i + 1), nf, 1))
         put("block.compress_out", nn.Conv2d(num_groups * nf, nf, 1))
-        put("out", nn.ConvTranspose2d(nf, nf, 8, 4, 2))
+        put("out", nn.ConvTranspose2d(nf, nf, *ksp))
         put("conv_out", nn.Conv2d(nf, 3, 3, padding=1), act=False)
         fc0 = nn.Linear(num_maps, 32)
         fc2 = nn.Linear(32, 1)
@@ -79,13 +83,14 @@ def _cba(x, sd, prefix, stride=1, padding=0, act=True):
     return F.prelu(y, sd[prefix + ".1.weight"]) if act else y
 
 
-def _dba(x, sd, prefix):
-    """DeconvBlock k8 s4 p2 -> PReLU.  ref: blocks.py:29-43, SRProjectionModule.py:22-24."""
-    y = F.conv_transpose2d(x, sd[prefix + ".0.weight"], sd[prefix + ".0.bias"], stride=4, padding=2)
+def _dba(x, sd, prefix, upscale=4):
+    """DeconvBlock k8 s4 p2 (x2: k6 s2 p2) -> PReLU.  ref: blocks.py:29-43, SRProjectionModule.py:22-24."""
+    _, st, pd = GEOMETRY[upscale]
+    y = F.conv_transpose2d(x, sd[prefix + ".0.weight"], sd[prefix + ".0.bias"], stride=st, padding=pd)
     return F.prelu(y, sd[prefix + ".1.weight"])
 
 
-def feedback_block(x, last_hidden, sd, num_groups=6):
+def feedback_block(x, last_hidden, sd, num_groups=6, upscale=4):
     """Intended FeedbackBlock dataflow (SRProjectionModule.py:44-90)."""
     x = _cba(torch.cat((x, last_hidden), 1), sd, "block.compress_in")          # :49-50
     lr = [x]
@@ -94,11 +99,11 @@ def feedback_block(x, last_hidden, sd, num_groups=6):
         ld_l = torch.cat(lr[: i + 1], 1)                                          # :55-59 (intended)
         if i > 0:
             ld_l = _cba(ld_l, sd, f"block.uptranBlocks.{i - 1}")                 # :62-63
-        hr.append(_dba(ld_l, sd, f"block.upBlocks.{i}"))                          # :64-65
+        hr.append(_dba(ld_l, sd, f"block.upBlocks.{i}", upscale))                      # :64-65
         ld_h = torch.cat(hr[: i + 1], 1)                                          # :70-74 (intended)
         if i > 0:
             ld_h = _cba(ld_h, sd, f"block.downtranBlocks.{i - 1}")               # :77-78
-        lr.append(_cba(ld_h, sd, f"block.downBlocks.{i}", stride=4, padding=2))   # :79-80
+        lr.append(_cba(ld_h, sd, f"block.downBlocks.{i}", stride=GEOMETRY[upscale][1], padding=2))   # :79-80
     out = _cba(torch.cat(lr[1:], 1), sd, "block.compress_out")                    # :87-88
     return out
 
@@ -113,9 +118,9 @@ def forward_maps(x, sd, num_steps=3, num_groups=6, upscale=4):
     hidden = x                                                                    # :45-48 first step
     h = None
     for _ in range(num_steps):
-        hidden = feedback_block(x, hidden, sd, num_groups)                        # :141, :89
+        hidden = feedback_block(x, hidden, sd, num_groups, upscale)                     # :141, :89
         h = hidden
-    y = F.conv2d(_dba(h, sd, "out"), sd["conv_out.0.weight"], sd["conv_out.0.bias"], padding=1)
+    y = F.conv2d(_dba(h, sd, "out", upscale), sd["conv_out.0.weight"], sd["conv_out.0.bias"], padding=1)
     y = inter + y                                                                 # :142
     y = F.conv2d(y, sd["add_mean.weight"], sd["add_mean.bias"])                   # :143
     return y

@@ -99,8 +99,39 @@ def test_c5_window_sharding_matches_single_run_at_shard_starts():
     assert not torch.equal(shards[1][0], whole[k1])               # ... which is a real difference
 
 
-def test_c4_geometry_is_rejected_loudly():
-    """C4 asks for 2x SR; the reference has no 2x geometry (SRProjectionModule.py:101-103) and neither
-    has this path: it must say so instead of producing something."""
+def test_c4_2x_4k_conv_stack_full_size_is_deterministic_and_tiling_consistent():
+    """C4 (2x, 1080x1920 -> 2160x3840, T=5 => M=14, one window per GPU): SRFBN's k6 s2 p2 geometry (the
+    reference has none).  Same two properties as C2: bit-identical reruns and equality with
+    a crop run that contains the receptive field.  ~89 GB of workspace: sized for the 180 GB part."""
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    M, h, w = 14, 1080, 1920
+    torch.manual_seed(0)
+    sr = SRProjectionModule(num_maps=M, upscale_factor=2)
+    with torch.no_grad():
+        for n, p in sr.named_parameters():
+            if n.endswith(".0.weight") and not n.startswith(("sub_mean", "add_mean")):
+                p.mul_(2.3)
+    x = (torch.rand((M, 3, h, w), generator=torch.Generator().manual_seed(1)) * 255).to(DEV)
+    y1 = sr(x)
+    y2 = sr(x)
+    assert y1.shape == (1, 3, 2 * h, 2 * w)
+    assert torch.isfinite(y1).all()
+    assert torch.equal(y1, y2)
+    # receptive field: 3 steps x 6 groups x (deconv +-1, conv +-2 LR px) + 3x3 convs < 64 LR pixels
+    y0, x0, ch, cw, m = 400, 800, 160, 224, 64
+    yc = sr(x[:, :, y0:y0 + ch, x0:x0 + cw].contiguous())
+    a = y1[:, :, 2 * (y0 + m):2 * (y0 + ch - m), 2 * (x0 + m):2 * (x0 + cw - m)]
+    b = yc[:, :, 2 * m:2 * (ch - m), 2 * m:2 * (cw - m)]
+    assert a.shape == b.shape and a.numel() > 0
+    assert (a - b).abs().max().item() <= 1e-2 * (a.abs().mean().item() + 1.0)
+    del sr, y1, y2, yc, x
+    gc.collect()
+    torch.cuda.empty_cache()
+
+
+def test_unsupported_geometry_is_rejected_loudly():
+    """x3 / x8 exist in SRFBN but neither in the reference nor in BASELINE's configs: say so."""
     with pytest.raises(NotImplementedError):
-        SRProjectionModule(upscale_factor=2)
+        SRProjectionModule(upscale_factor=3)

@@ -102,19 +102,24 @@ def _psnr(a, b):
     return 10 * math.log10(255.0 ** 2 / max(mse, 1e-20))
 
 
-@pytest.mark.parametrize("M,h,w,steps", [(8, 16, 16, 3), (3, 9, 21, 2), (20, 24, 40, 3)])
-def test_full_stack_against_oracle(M, h, w, steps):
-    sd = so.init_state_dict(num_maps=M, seed=M + h, gain=2.3)
+@pytest.mark.parametrize("M,h,w,steps,scale", [(8, 16, 16, 3, 4), (3, 9, 21, 2, 4), (20, 24, 40, 3, 4),
+                                                (8, 16, 16, 3, 2), (3, 9, 21, 2, 2), (14, 24, 40, 3, 2), (2, 37, 19, 1, 2)])
+def test_full_stack_against_oracle(M, h, w, steps, scale):
+    """x4 = the reference's geometry (k8 s4 p2); x2 = SRFBN's k6 s2 p2 (BASELINE config C4; layered kernels)."""
+    sd = so.init_state_dict(num_maps=M, seed=M + h, gain=2.3, upscale=scale)
     # make every slope distinct so a mixed-up layer shows
     gs = torch.Generator().manual_seed(99)
     for k in sd:
         if k.endswith(".1.weight"):
             sd[k] = torch.rand(1, generator=gs) * 0.4 + 0.05
-    mod = SRProjectionModule(num_steps=steps, num_maps=M)
+    mod = SRProjectionModule(num_steps=steps, num_maps=M, upscale_factor=scale)
     mod.load_state_dict(sd)
     x = torch.rand((M, 3, h, w), generator=torch.Generator().manual_seed(5)) * 255
     with torch.no_grad():
-        want_maps = so.forward_maps(x, sd, num_steps=steps)
+        want_maps = so.forward_maps(x, sd, num_steps=steps, upscale=scale)
+        # the parity test must not be blind: the conv branch (not only the bilinear skip) carries signal
+        skip = F.interpolate(x, scale_factor=scale, mode="bilinear", align_corners=False)
+        assert (want_maps - skip).abs().mean().item() > 0.05
         want = so.fc_fuse(want_maps, sd)
     got_maps = mod.premix(x.to(DEV)).cpu()
     got = mod(x.to(DEV)).cpu()

@@ -36,6 +36,7 @@ enum EpiMode : int {
   EPI_ROWS = 0,        // BN=32: 64-byte BF16 row per pixel at out + row*pitch + off
   EPI_DECONV = 1,      // BN=256 (one half of the 16 sub-positions): HR block layout or plain NHWC HR
   EPI_CONV_OUT = 2,    // BN=32 (27 real = 9 taps x 3): output-shift 3x3 conv, fp32 planar output + skip + mean shifts
+  EPI_DECONV2 = 3,     // BN=128 (4 sub-positions x 32): x2 transposed conv k6 s2 p2, plain NHWC HR output
 };
 
 struct Chunk {
@@ -74,6 +75,7 @@ struct alignas(64) IgemmParams {
   int32_t debug;               // timing experiments (wrong results): bit0 no TMA stores, bit1 no TMEM reads/convert, bit2 no MMAs
   // EPI_CONV_OUT extras
   const float* skip_src;       // network input x (M,3,h,w) fp32
+  float inv_scale;             // 1 / upscale factor of the bilinear skip (0.25 or 0.5)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -544,6 +546,32 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
             tma_store_commit();
           }
         }
+      } else if constexpr (MODE == EPI_DECONV2) {
+        // ConvTranspose2d k6 s2 p2 (SRFBN's x2 geometry): row = LR pixel (Y,X), the 3x3 LR taps are the
+        // K chunks, column group s = ry*2+rx is HR pixel (2Y+ry, 2X+rx): HR rows 2Y and 2Y+1 each get
+        // 128 contiguous bytes from this thread, consecutive lanes write consecutive 128-byte pieces.
+        const int Y = t.y0 + (row >> 4), X = t.x0 + (row & 15);
+        const bool valid = (Y < p.lr_h) && (X < p.lr_w);
+        const PreluCfg pc = make_prelu(s_bias[p.bias_n], 1);
+        const int64_t W2 = 2 * (int64_t)p.lr_w;
+        uint8_t* base = reinterpret_cast<uint8_t*>(p.out) + (((int64_t)t.b * 2 * p.lr_h + 2 * Y) * W2 + 2 * X) * 64;
+#pragma unroll 1
+        for (int cg = 0; cg < 4; ++cg) {
+          uint32_t v[32];
+          tmem_ld32(taddr + cg * 32, v);
+          tmem_ld_wait();
+          if (cg == 3) {
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[as]);
+          }
+          if (valid) {
+            uint32_t o[16];
+            convert32(v, s_bias, pc, o);
+            uint4* d4 = reinterpret_cast<uint4*>(base + ((cg >> 1) * W2 + (cg & 1)) * 64);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) d4[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          }
+        }
       } else {  // EPI_CONV_OUT
         // 3x3 conv in "output-shift" form: row = INPUT pixel (xi, yi) of a 16x8 tile whose origin is
         // (x0, y0) = 14*tx-1, 6*ty-1; D[row, (ky*3+kx)*3 + o] = sum_c in[row, c] * W[o, c, ky, kx] is the
@@ -575,10 +603,10 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
               acc[1] += q[1];
               acc[2] += q[2];
             }
-          // bilinear x4 skip, align_corners=False (SRProjectionModule.py:136; ATen
-          // upsample_bilinear2d: src = (dst+0.5)/4 - 0.5 clamped at 0), on sub_mean(x)
+          // bilinear xs skip, align_corners=False (SRProjectionModule.py:136; ATen
+          // upsample_bilinear2d: src = (dst+0.5)/s - 0.5 clamped at 0), on sub_mean(x)
           const int h = p.lr_h, w = p.lr_w;
-          float sy = fmaxf((Y + 0.5f) * 0.25f - 0.5f, 0.0f), sx = fmaxf((X + 0.5f) * 0.25f - 0.5f, 0.0f);
+          float sy = fmaxf((Y + 0.5f) * p.inv_scale - 0.5f, 0.0f), sx = fmaxf((X + 0.5f) * p.inv_scale - 0.5f, 0.0f);
           int y0i = (int)sy, x0i = (int)sx;
           int y1i = y0i + (y0i < h - 1 ? 1 : 0), x1i = x0i + (x0i < w - 1 ? 1 : 0);
           float ly = sy - y0i, lx = sx - x0i, hy = 1.0f - ly, hx = 1.0f - lx;

@@ -89,7 +89,7 @@ int make_w_map(CUtensorMap* m, const void* base, int64_t K, int64_t N, int ck, i
 // ------------------------------------------------------------------------------------------------
 // kernel variants
 // ------------------------------------------------------------------------------------------------
-enum Variant : int { V_PW32 = 0, V_PW128, V_DECONV, V_CONVOUT, V_FUSED_TRAN, V_FUSED_PLAIN, V_FINALIZE, V_COUNT };
+enum Variant : int { V_PW32 = 0, V_PW128, V_DECONV, V_CONVOUT, V_FUSED_TRAN, V_FUSED_PLAIN, V_FINALIZE, V_DECONV2, V_COUNT };
 
 // kernel classes for the per-launch accounting bench.py reads (vsr_srfbn_profile_*)
 static_assert(VSR_SRFBN_KERNEL_CLASSES == 10, "header constant");
@@ -152,6 +152,7 @@ int launch_layer(const Layer& L, cudaStream_t st) {
     case V_PW128: return launch_variant<EPI_ROWS, 32, 128>(L, st);
     case V_DECONV: return launch_variant<EPI_DECONV, 32, 256>(L, st);
     case V_CONVOUT: return launch_variant<EPI_CONV_OUT, 32, 32>(L, st);
+    case V_DECONV2: return launch_variant<EPI_DECONV2, 32, 128>(L, st);
     default: return VSR_ERR_INVALID_ARG;
   }
 }
@@ -159,7 +160,8 @@ int launch_layer(const Layer& L, cudaStream_t st) {
 size_t variant_smem(int variant, int chunks, int stages) {
   switch (variant) {
     case V_PW32: return igemm_smem_bytes<32, 32>(chunks, stages);
-    case V_PW128: return igemm_smem_bytes<32, 128>(chunks, stages);
+    case V_PW128:
+    case V_DECONV2: return igemm_smem_bytes<32, 128>(chunks, stages);
     case V_DECONV: return igemm_smem_bytes<32, 256>(chunks, stages, kDeconvStageBytes);
     default: return igemm_smem_bytes<32, 32>(chunks, stages, kConvOutStageBytes);
   }
@@ -295,6 +297,104 @@ int build_deconv(Layer& L, const void* x, int B, int h, int w, const void* w_dev
   return VSR_OK;
 }
 
+// ---- x2 geometry (SRFBN's k6 s2 p2; SURVEY.md 8 a6 / config C4: the reference hard-wires x4) -------------------
+// Layered path on plain NHWC HR features: transposed conv (3x3 LR taps, N = 4 sub-positions x 32), 1x1 downtran
+// over the concatenated HR maps, strided conv as a 36-tap implicit GEMM.
+
+// ConvTranspose2d(32,32,6,2,2): x (B,h,w,32) -> (B,2h,2w,32) NHWC
+int build_deconv2(Layer& L, const void* x, int B, int h, int w, const void* w_dev, const float* bias_dev, void* out) {
+  memset(&L, 0, sizeof(L));
+  L.variant = V_DECONV2;
+  IgemmParams& p = L.p;
+  int rc = make_act_map(&p.a_maps[0], x, kNF, w, h, B, 32, kTW, kTH);
+  if (rc) return rc;
+  rc = make_w_map(&p.b_map, w_dev, 9 * kNF, 128, 32, 128);
+  if (rc) return rc;
+  for (int t = 0; t < 9; ++t) {   // tap at LR (Y+dy, X+dx)
+    p.chunks[t].map = 0;
+    p.chunks[t].dy = (int8_t)(t / 3 - 1);
+    p.chunks[t].dx = (int8_t)(t % 3 - 1);
+    p.chunks[t].c0 = 0;
+  }
+  p.num_chunks = 9;
+  p.cps = 3;
+  p.num_stages = 3;
+  p.n_tiles = 1;
+  p.tiles_x = ceil_div(w, kTW);
+  p.tiles_y = ceil_div(h, kTH);
+  p.batch = B;
+  p.tile_w = kTW;
+  p.tile_h = kTH;
+  p.bias = bias_dev;
+  p.bias_n = kNF;
+  p.act = 1;
+  p.out = out;
+  p.lr_h = h;
+  p.lr_w = w;
+  finish_layer(L, 1);
+  const double lrpx = (double)B * h * w;
+  L.kclass = KC_DECONV;
+  L.flops = lrpx * 73728.0;             // 2 * 36 taps * 32 * 32 per LR pixel
+  L.bytes = lrpx * 64.0 * 5.0;
+  return VSR_OK;
+}
+
+// Conv2d(32,32,6,2,2) + PReLU: xhr (B,2h,2w,32) NHWC -> out (B,h,w,32).  Input pixel (2Y-2+ky, 2X-2+kx): the
+// row parity ky&1 selects one of two tensor maps over every other HR row (no element strides), the column parity
+// kx&1 the channel-offset half of a 64-element (pixel pair x channel) inner dimension; TMA zero fill is the padding.
+int build_downconv2(Layer& L, const void* xhr, int B, int h, int w, const void* w_dev, const float* bias_dev, void* out) {
+  memset(&L, 0, sizeof(L));
+  L.variant = V_PW32;
+  IgemmParams& p = L.p;
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return VSR_ERR_STATE;
+  for (int py = 0; py < 2; ++py) {
+    cuuint64_t dims[4] = {64, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)B};
+    cuuint64_t strides[3] = {128, (cuuint64_t)256 * w, (cuuint64_t)256 * w * h};
+    cuuint32_t box[4] = {32, (cuuint32_t)kTW, (cuuint32_t)kTH, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    void* base = const_cast<uint8_t*>(reinterpret_cast<const uint8_t*>(xhr)) + (size_t)py * 128 * w;
+    CUresult r = enc(&p.a_maps[py], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return VSR_ERR_CUDA_BASE + 999;
+  }
+  int rc = make_w_map(&p.b_map, w_dev, 36 * kNF, 32, 32, 32);
+  if (rc) return rc;
+  for (int ky = 0; ky < 6; ++ky)
+    for (int kx = 0; kx < 6; ++kx) {
+      Chunk& c = p.chunks[ky * 6 + kx];
+      c.map = (int8_t)(ky & 1);
+      c.dy = (int8_t)((ky >> 1) - 1);
+      c.dx = (int8_t)((kx >> 1) - 1);
+      c.c0 = (kx & 1) * 32;
+    }
+  p.num_chunks = 36;
+  p.cps = 4;
+  p.num_stages = 4;
+  p.n_tiles = 1;
+  p.tiles_x = ceil_div(w, kTW);
+  p.tiles_y = ceil_div(h, kTH);
+  p.batch = B;
+  p.tile_w = kTW;
+  p.tile_h = kTH;
+  p.bias = bias_dev;
+  p.bias_n = kNF;
+  p.act = 1;
+  p.out = out;
+  p.out_pitch = 64;
+  p.out_h = h;
+  p.out_w = w;
+  p.lr_h = h;
+  p.lr_w = w;
+  finish_layer(L, 1);
+  const double lrpx = (double)B * h * w;
+  L.kclass = KC_DOWNCONV;
+  L.flops = lrpx * 73728.0;
+  L.bytes = lrpx * 64.0 * 5.0;
+  return VSR_OK;
+}
+
 // downtran (1x1 over hr[0..nsrc-1], nsrc >= 2) + PReLU + Conv2d(32,32,8,4,2) pre-activation sums -> acc;
 // nsrc == 1: the conv alone on hr[0].  hr[j]: HR block layout (B,h+1,w+1,16,32); acc (B,h,w,32) fp32.
 int build_fused_down(Layer& L, const void* const* hr, int nsrc, int B, int h, int w, const void* wt_dev,
@@ -375,12 +475,13 @@ int build_finalize(Layer& L, float* acc, const float* bias_dev, void* out, int64
 }
 
 // conv_out 3x3 p1 32->3 at HR + bilinear skip + mean shifts, fp32 planar output (B,3,4h,4w)
-int build_conv_out(Layer& L, const void* xhr, int B, int h, int w, const void* w_dev, const float* bias_dev,
-                   float* out) {
+int build_conv_out(Layer& L, const void* xhr, int B, int h, int w, int scale, const void* w_dev,
+                   const float* bias_dev, float* out) {
   memset(&L, 0, sizeof(L));
   L.variant = V_CONVOUT;
   IgemmParams& p = L.p;
-  const int H = 4 * h, W = 4 * w;
+  const int H = scale * h, W = scale * w;
+  p.inv_scale = 1.0f / (float)scale;
   int rc = make_act_map(&p.a_maps[0], xhr, kNF, W, H, B, 32, 16, 8);
   if (rc) return rc;
   rc = make_w_map(&p.b_map, w_dev, kNF, 32, 32, 32);
@@ -410,7 +511,7 @@ int build_conv_out(Layer& L, const void* xhr, int B, int h, int w, const void* w
   const double hrpx = (double)B * H * W;
   L.kclass = KC_CONV_OUT;
   L.flops = hrpx * 2.0 * 288 * 3;
-  L.bytes = hrpx * (64.0 + 12.0) + hrpx / 16.0 * 12.0;
+  L.bytes = hrpx * (64.0 + 12.0) + hrpx / (scale * scale) * 12.0;
   return VSR_OK;
 }
 
@@ -456,6 +557,24 @@ void pack_downconv_fused(const float* w, uint16_t* dst) {
           int ky = 4 * (t >> 1) + (s >> 2), kx = 4 * (t & 1) + (s & 3);
           dst[(t * 32 + o) * 512 + s * 32 + c] = f2bf(w[((o * 32 + c) * 8 + ky) * 8 + kx]);
         }
+}
+// x2: ConvTranspose2d weight (c in, o out, 6, 6) s2 p2 -> [128 = s*32+o][288 = t*32+c], s = ry*2+rx,
+// t = (dy+1)*3+(dx+1), ky = ry + 2 - 2dy, kx = rx + 2 - 2dx   (out y = 2i - 2 + ky)
+void pack_deconv2(const float* w, uint16_t* dst) {
+  for (int s = 0; s < 4; ++s)
+    for (int o = 0; o < 32; ++o)
+      for (int t = 0; t < 9; ++t)
+        for (int c = 0; c < 32; ++c) {
+          int ry = s >> 1, rx = s & 1, dy = t / 3 - 1, dx = t % 3 - 1;
+          int ky = ry + 2 - 2 * dy, kx = rx + 2 - 2 * dx;
+          dst[(s * 32 + o) * 288 + t * 32 + c] = f2bf(w[((c * 32 + o) * 6 + ky) * 6 + kx]);
+        }
+}
+// x2: Conv2d weight (o, c, 6, 6) s2 p2 -> [32 = o][1152 = (ky*6+kx)*32 + c]
+void pack_downconv2(const float* w, uint16_t* dst) {
+  for (int o = 0; o < 32; ++o)
+    for (int t = 0; t < 36; ++t)
+      for (int c = 0; c < 32; ++c) dst[o * 1152 + t * 32 + c] = f2bf(w[(o * 32 + c) * 36 + t]);
 }
 // conv_out (3,32,3,3) for the output-shift form -> [32 = (ky*3+kx)*3 + o][32 = c], rows 27..31 zero
 void pack_conv_out(const float* w, uint16_t* dst) {
@@ -597,7 +716,7 @@ struct vsr_srfbn_plan {
   size_t misc_off;        // fp32: sub_mean bias (3)
   size_t weight_bytes;
   // workspace offsets
-  size_t o_a0, o_c128, o_xfeat, o_hidden, o_lr[7], o_u, o_hr[6], o_hb, o_acc, o_premix, ws_bytes;
+  size_t o_a0, o_c128, o_xfeat, o_hidden, o_lr[7], o_u, o_hr[6], o_hb, o_ht, o_acc, o_premix, ws_bytes;
   bool bound;
   const uint8_t* dev_w;
   uint8_t* ws;
@@ -621,11 +740,12 @@ static void layout_weights(vsr_srfbn_plan* pl) {
   put(W_FEAT_IN, 32, 128, 33);
   put(W_COMPRESS_IN, 32, 64, 33);
   for (int i = 0; i < 5; ++i) put(W_UPTRAN0 + i, 32, 32 * (i + 2), 33);
-  for (int i = 0; i < 6; ++i) put(W_UP0 + i, 512, 128, 33);
+  const bool x2 = pl->cfg.upscale == 2;   // k6 s2 p2: 3x3 LR taps x 4 sub-positions / 36 taps; else k8 s4 p2
+  for (int i = 0; i < 6; ++i) put(W_UP0 + i, x2 ? 128 : 512, x2 ? 288 : 128, 33);
   for (int i = 0; i < 5; ++i) put(W_DOWNTRAN0 + i, 32, 32 * (i + 2), 33);
-  for (int i = 0; i < 6; ++i) put(W_DOWN0 + i, 128, 512, 33);
+  for (int i = 0; i < 6; ++i) put(W_DOWN0 + i, x2 ? 32 : 128, x2 ? 1152 : 512, 33);
   put(W_COMPRESS_OUT, 32, 192, 33);
-  put(W_OUT, 512, 128, 33);
+  put(W_OUT, x2 ? 128 : 512, x2 ? 288 : 128, 33);
   put(W_CONV_OUT, 32, 32, 16 + 7);
   pl->fc_off = off;
   off = align_up(off + (size_t)(32 * pl->cfg.num_maps + 65) * 4, 256);
@@ -650,10 +770,13 @@ static void layout_workspace(vsr_srfbn_plan* pl) {
   pl->o_hidden = put(P * 64);
   for (int i = 0; i < 7; ++i) pl->o_lr[i] = put(P * 64);
   pl->o_u = put(P * 64);
-  for (int i = 0; i < 6; ++i) pl->o_hr[i] = put(Rb * 64);
-  pl->o_hb = put(P * 16 * 64);   // plain-NHWC result of the `out` deconv
-  pl->o_acc = put(P * 512);   // fp32 partial slots of the fused down kernel
-  pl->o_premix = put(P * 16 * 3 * 4);
+  const size_t s2 = (size_t)c.upscale * c.upscale;
+  const bool x2 = c.upscale == 2;
+  for (int i = 0; i < 6; ++i) pl->o_hr[i] = put(x2 ? P * s2 * 64 : Rb * 64);   // x2: plain NHWC
+  pl->o_hb = put(P * s2 * 64);   // plain-NHWC result of the `out` deconv
+  pl->o_ht = put(x2 ? P * s2 * 64 : 0);   // x2: downtran result (the x4 path keeps it on chip)
+  pl->o_acc = put(x2 ? 0 : P * 512);   // fp32 partial slots of the fused down kernel
+  pl->o_premix = put(P * s2 * 3 * 4);
   pl->ws_bytes = off;
 }
 
@@ -661,8 +784,10 @@ extern "C" int vsr_srfbn_plan_create(const vsr_srfbn_config* cfg, vsr_srfbn_plan
   if (!cfg || !out_plan) return VSR_ERR_INVALID_ARG;
   *out_plan = nullptr;
   if (cfg->num_maps < 1 || cfg->h < 1 || cfg->w < 1 || cfg->num_steps < 1) return VSR_ERR_INVALID_ARG;
-  // geometry hard-wired by the reference: x4, k8 s4 p2, 32 features, 6 groups (SRProjectionModule.py:97-103)
-  if (cfg->num_groups != kGroups || cfg->num_features != kNF || cfg->upscale != 4 || cfg->num_maps > kMaxMaps)
+  // geometry hard-wired by the reference: x4, k8 s4 p2, 32 features, 6 groups (SRProjectionModule.py:97-103);
+  // x2 (config C4) uses SRFBN's k6 s2 p2, for which the reference has no code
+  if (cfg->num_groups != kGroups || cfg->num_features != kNF || (cfg->upscale != 4 && cfg->upscale != 2) ||
+      cfg->num_maps > kMaxMaps)
     return VSR_ERR_UNSUPPORTED;
   vsr_srfbn_plan* pl = new (std::nothrow) vsr_srfbn_plan();
   if (!pl) return VSR_ERR_INVALID_ARG;
@@ -716,15 +841,19 @@ extern "C" int vsr_srfbn_pack_weights(const vsr_srfbn_plan* pl, const vsr_srfbn_
     pack_pointwise(w->downtran_w[i], 32, 32 * (i + 2), W(W_DOWNTRAN0 + i));
     ok = ok && bias(W_DOWNTRAN0 + i, w->downtran_b[i], 32, w->downtran_slope[i]);
   }
+  const bool x2 = pl->cfg.upscale == 2;
   for (int i = 0; i < 6; ++i) {
-    pack_deconv(w->up_w[i], W(W_UP0 + i));
+    if (x2) pack_deconv2(w->up_w[i], W(W_UP0 + i));
+    else pack_deconv(w->up_w[i], W(W_UP0 + i));
     ok = ok && bias(W_UP0 + i, w->up_b[i], 32, w->up_slope[i]);
-    pack_downconv_fused(w->down_w[i], W(W_DOWN0 + i));
+    if (x2) pack_downconv2(w->down_w[i], W(W_DOWN0 + i));
+    else pack_downconv_fused(w->down_w[i], W(W_DOWN0 + i));
     ok = ok && bias(W_DOWN0 + i, w->down_b[i], 32, w->down_slope[i]);
   }
   pack_pointwise(w->compress_out_w, 32, 192, W(W_COMPRESS_OUT));
   ok = ok && bias(W_COMPRESS_OUT, w->compress_out_b, 32, w->compress_out_slope);
-  pack_deconv(w->out_w, W(W_OUT));
+  if (x2) pack_deconv2(w->out_w, W(W_OUT));
+  else pack_deconv(w->out_w, W(W_OUT));
   ok = ok && bias(W_OUT, w->out_b, 32, w->out_slope);
   pack_conv_out(w->conv_out_w, W(W_CONV_OUT));
   if (!w->conv_out_b) return VSR_ERR_INVALID_ARG;
@@ -794,6 +923,22 @@ extern "C" int vsr_srfbn_bind(vsr_srfbn_plan* pl, const void* dev_weights, void*
                              0, h, w));
         up_in = ws + pl->o_u;
       }
+      if (c.upscale == 2) {
+        PUSH(build_deconv2(L, up_in, M, h, w, Wp(W_UP0 + i), Bp(W_UP0 + i), ws + pl->o_hr[i]));
+        const void* down_in = ws + pl->o_hr[0];
+        if (i > 0) {  // downtran(cat(hr[0..i])) over flat HR rows
+          Src s[6];
+          for (int j = 0; j <= i; ++j) s[j] = Src{ws + pl->o_hr[j], 32, 0, 32};
+          rc = build_pointwise(L, s, i + 1, P * 4, Wp(W_DOWNTRAN0 + i - 1), Bp(W_DOWNTRAN0 + i - 1), 32, 1,
+                               ws + pl->o_ht, 64, 0, 0, h, w);
+          if (rc) return rc;
+          L.kclass = KC_PW_HR;
+          pl->layers.push_back(L);
+          down_in = ws + pl->o_ht;
+        }
+        PUSH(build_downconv2(L, down_in, M, h, w, Wp(W_DOWN0 + i), Bp(W_DOWN0 + i), ws + pl->o_lr[i + 1]));
+        continue;
+      }
       PUSH(build_deconv(L, up_in, M, h, w, Wp(W_UP0 + i), Bp(W_UP0 + i), ws + pl->o_hr[i], 0));
       {  // downtran(cat(hr[0..i])) + downBlocks[i], fused; sums land in the fp32 LR accumulator
         const void* hrs[6];
@@ -811,8 +956,9 @@ extern "C" int vsr_srfbn_bind(vsr_srfbn_plan* pl, const void* dev_weights, void*
                            w));
     }
   }
-  PUSH(build_deconv(L, ws + pl->o_hidden, M, h, w, Wp(W_OUT), Bp(W_OUT), ws + pl->o_hb, 1));
-  PUSH(build_conv_out(L, ws + pl->o_hb, M, h, w, Wp(W_CONV_OUT), Bp(W_CONV_OUT),
+  if (c.upscale == 2) PUSH(build_deconv2(L, ws + pl->o_hidden, M, h, w, Wp(W_OUT), Bp(W_OUT), ws + pl->o_hb));
+  else PUSH(build_deconv(L, ws + pl->o_hidden, M, h, w, Wp(W_OUT), Bp(W_OUT), ws + pl->o_hb, 1));
+  PUSH(build_conv_out(L, ws + pl->o_hb, M, h, w, c.upscale, Wp(W_CONV_OUT), Bp(W_CONV_OUT),
                       reinterpret_cast<float*>(ws + pl->o_premix)));
   pl->conv_out_layer = (int)pl->layers.size() - 1;
 #undef PUSH
@@ -847,7 +993,7 @@ extern "C" int vsr_srfbn_forward(vsr_srfbn_plan* pl, const float* x, float* y, v
   }
   mark();
   {
-    const int64_t n = (int64_t)3 * 16 * c.h * c.w;
+    const int64_t n = (int64_t)3 * c.upscale * c.upscale * c.h * c.w;
     int64_t blocks = ceil_div64(ceil_div64(n, 4), 256);
     if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
     fc_fuse_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const float*>(pl->ws + pl->o_premix),
@@ -896,7 +1042,7 @@ extern "C" int vsr_srfbn_profile_read(vsr_srfbn_plan* pl, double* ms, int32_t* l
     int k;
     double f, b;
     if (i == 0) { k = KC_IM2COL; f = 0; b = P * (12.0 + 64.0); }
-    else if (i == n - 1) { k = KC_FC; f = 16.0 * P / c.num_maps * 3 * 2.0 * (32.0 * c.num_maps + 32.0); b = 16.0 * P * 12.0 + 16.0 * P / c.num_maps * 12.0; }
+    else if (i == n - 1) { const double s2 = (double)c.upscale * c.upscale; k = KC_FC; f = s2 * P / c.num_maps * 3 * 2.0 * (32.0 * c.num_maps + 32.0); b = s2 * P * 12.0 + s2 * P / c.num_maps * 12.0; }
     else { const Layer& L = pl->layers[i - 1]; k = L.kclass; f = L.flops; b = L.bytes; }
     ms[k] += t; launches[k] += 1; flops[k] += f; bytes[k] += b;
   }
@@ -921,7 +1067,7 @@ extern "C" int vsr_srfbn_debug_premix(const vsr_srfbn_plan* pl, float* out_maps,
   if (!pl || !out_maps) return VSR_ERR_INVALID_ARG;
   if (!pl->bound) return VSR_ERR_STATE;
   const vsr_srfbn_config& c = pl->cfg;
-  size_t bytes = (size_t)c.num_maps * 3 * 16 * c.h * c.w * 4;
+  size_t bytes = (size_t)c.num_maps * 3 * c.upscale * c.upscale * c.h * c.w * 4;
   return cuda_status(cudaMemcpyAsync(out_maps, pl->ws + pl->o_premix, bytes, cudaMemcpyDeviceToDevice, as_stream(stream)));
 }
 

@@ -3,7 +3,7 @@ maps) with the reference's surface:
 
     SRProjectionModule(in_channels=3, out_channels=3, num_features=32, upscale_factor=4,
                        num_steps=3, num_groups=6, act_type='prelu', norm_type=None)
-    .forward(x (M,3,h,w) fp32 0..255) -> (1,3,4h,4w) fp32
+    .forward(x (M,3,h,w) fp32 0..255) -> (1,3,s*h,s*w) fp32
     ref: my_packages/SRProjection/SRProjectionModule.py:96-150
 
 Parameters carry the reference's state-dict names and shapes, so a
@@ -25,6 +25,9 @@ import torch.nn as nn
 from ... import _lib
 
 RGB_MEAN = (0.4488, 0.4371, 0.4040)   # SRProjectionModule.py:105
+# (kernel, stride, padding) of the up/down projection units.  x4 is the reference's hard-wired geometry
+# (SRProjectionModule.py:10-12,101-103); x2 is SRFBN's, needed by BASELINE config C4.
+GEOMETRY = {4: (8, 4, 2), 2: (6, 2, 2)}
 
 
 def _block(conv, act=True):
@@ -47,11 +50,11 @@ class _MeanShift(nn.Conv2d):
 class _FeedbackParams(nn.Module):
     """Parameter container with FeedbackBlock's names (SRProjectionModule.py:7-42)."""
 
-    def __init__(self, nf, num_groups):
+    def __init__(self, nf, num_groups, ksp=(8, 4, 2)):
         super().__init__()
         self.compress_in = _block(nn.Conv2d(2 * nf, nf, 1))
-        self.upBlocks = nn.ModuleList([_block(nn.ConvTranspose2d(nf, nf, 8, 4, 2)) for _ in range(num_groups)])
-        self.downBlocks = nn.ModuleList([_block(nn.Conv2d(nf, nf, 8, 4, 2)) for _ in range(num_groups)])
+        self.upBlocks = nn.ModuleList([_block(nn.ConvTranspose2d(nf, nf, *ksp)) for _ in range(num_groups)])
+        self.downBlocks = nn.ModuleList([_block(nn.Conv2d(nf, nf, *ksp)) for _ in range(num_groups)])
         self.uptranBlocks = nn.ModuleList([_block(nn.Conv2d(nf * (i + 2), nf, 1)) for i in range(num_groups - 1)])
         self.downtranBlocks = nn.ModuleList([_block(nn.Conv2d(nf * (i + 2), nf, 1)) for i in range(num_groups - 1)])
         self.compress_out = _block(nn.Conv2d(num_groups * nf, nf, 1))
@@ -61,10 +64,11 @@ class SRProjectionModule(nn.Module):
     def __init__(self, in_channels=3, out_channels=3, num_features=32, upscale_factor=4, num_steps=3, num_groups=6,
                  act_type='prelu', norm_type=None, num_maps=8):
         super(SRProjectionModule, self).__init__()
-        if (in_channels, out_channels, num_features, upscale_factor, num_groups) != (3, 3, 32, 4, 6) \
-                or act_type != 'prelu' or norm_type is not None:
-            raise NotImplementedError("the B200 path implements the reference's only geometry: 3->3 channels, "
-                                      "32 features, x4 (k8 s4 p2), 6 groups, PReLU, no norm")
+        if (in_channels, out_channels, num_features, num_groups) != (3, 3, 32, 6) \
+                or upscale_factor not in GEOMETRY or act_type != 'prelu' or norm_type is not None:
+            raise NotImplementedError("the B200 path implements 3->3 channels, 32 features, 6 groups, PReLU, no "
+                                      "norm, x4 (k8 s4 p2, the reference's geometry) or x2 (k6 s2 p2)")
+        ksp = GEOMETRY[upscale_factor]
         self.num_steps = num_steps
         self.num_features = num_features
         self.upscale_factor = upscale_factor
@@ -73,8 +77,8 @@ class SRProjectionModule(nn.Module):
         self.sub_mean = _MeanShift(RGB_MEAN, -1)
         self.conv_in = _block(nn.Conv2d(in_channels, 4 * nf, 3, padding=1))
         self.feat_in = _block(nn.Conv2d(4 * nf, nf, 1))
-        self.block = _FeedbackParams(nf, num_groups)
-        self.out = _block(nn.ConvTranspose2d(nf, nf, 8, 4, 2))
+        self.block = _FeedbackParams(nf, num_groups, ksp)
+        self.out = _block(nn.ConvTranspose2d(nf, nf, *ksp))
         self.conv_out = _block(nn.Conv2d(nf, out_channels, 3, padding=1), act=False)
         self.add_mean = _MeanShift(RGB_MEAN, 1)
         self.fc = nn.Sequential(nn.Linear(num_maps, 32), nn.ReLU(), nn.Linear(32, 1), nn.ReLU())
@@ -154,7 +158,8 @@ class SRProjectionModule(nn.Module):
         x = x.to(torch.float32).contiguous()
         M, _, h, w = x.shape
         ent = self._plan_for(M, h, w, x.device)
-        y = torch.empty((1, 3, 4 * h, 4 * w), dtype=torch.float32, device=x.device)
+        s = self.upscale_factor
+        y = torch.empty((1, 3, s * h, s * w), dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
             _lib.check(_lib.lib().vsr_srfbn_forward(ent["plan"], x.data_ptr(), y.data_ptr(),
                                                     torch.cuda.current_stream().cuda_stream), "srfbn_forward")
@@ -165,7 +170,8 @@ class SRProjectionModule(nn.Module):
         self.forward(x)
         M, _, h, w = x.shape
         ent = self._plans[(M, h, w, x.device.index)]
-        out = torch.empty((M, 3, 4 * h, 4 * w), dtype=torch.float32, device=x.device)
+        s = self.upscale_factor
+        out = torch.empty((M, 3, s * h, s * w), dtype=torch.float32, device=x.device)
         _lib.check(_lib.lib().vsr_srfbn_debug_premix(ent["plan"], out.data_ptr(),
                                                      torch.cuda.current_stream().cuda_stream), "srfbn_debug_premix")
         return out
