@@ -129,6 +129,7 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.tiles_x * p.tiles_y * p.batch;
 
+  // (no early griddepcontrol.launch_dependents: dependents are released as CTAs exit)
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.num_stages; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -169,6 +170,7 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
         mbar_expect_tx(w_full, (uint32_t)(p.nsrc * kWtChunkBytes));
         for (int j = 0; j < p.nsrc; ++j) tma_load_2d(s_wt + j * kWtChunkBytes, &p.wt_map, w_full, j * 32, 0);
       }
+      griddep_wait();   // weights are static; the HR maps only after the previous layers have completed
       int s = 0;
       uint32_t phase = 0;
       // L2 prefetch cursor: runs kAhead half-tiles (8 sub-positions of every source = 64 KB per source)
@@ -343,6 +345,7 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
     // ===================== epilogue warps 2..17 =====================
     // warp -> TMEM lane quarter q = warp % 4 (hardware rule) and sub = which of the 4 column groups
     // (phase A: sub-position within the group; final: tap) this warp handles
+    griddep_wait();     // the partial-sum slots are read by the previous finalize launch
     const int q = warp & 3;
     const int sub = (warp - 2) >> 2;
     const int row = q * 32 + lane;
@@ -457,6 +460,8 @@ __global__ void __launch_bounds__(256)
 finalize_lr_kernel(const float4* __restrict__ part, const float* __restrict__ bias, uint4* __restrict__ out, int64_t n8,
                    int w) {
   const float slope = __ldg(bias + 32);
+  // (no early griddepcontrol.launch_dependents: dependents are released as CTAs exit)
+  griddep_wait();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t px = i >> 2;
     const int c8 = (int)(i & 3);

@@ -336,6 +336,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.n_tiles * p.tiles_x * p.tiles_y * p.batch;
 
+  // (no early griddepcontrol.launch_dependents: dependents are released as CTAs exit)
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.num_stages; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -364,6 +365,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
       mbar_expect_tx(b_full, (uint32_t)(p.num_chunks * kBBytes));
       for (int kc = 0; kc < p.num_chunks; ++kc)
         tma_load_2d(smem_b + kc * kBBytes, &p.b_map, b_full, kc * CK, n_tile0 * BN);
+      griddep_wait();   // weights are static; activations only after the previous layers have completed
       int s = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -418,6 +420,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
+    griddep_wait();                         // output buffers may still be read by earlier layers
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;          // row of the 128-pixel tile
     int as = 0;

@@ -120,7 +120,9 @@ int launch_variant(const Layer& L, cudaStream_t st) {
     if (e != cudaSuccess) return cuda_status(e);
     attr_set = true;
   }
-  igemm_kernel<MODE, CK, BN><<<L.grid, MODE == EPI_DECONV ? kDeconvThreads : kIgemmThreads, L.smem, st>>>(L.p);
+  cudaError_t e = launch_pdl(igemm_kernel<MODE, CK, BN>, L.grid, MODE == EPI_DECONV ? kDeconvThreads : kIgemmThreads,
+                             L.smem, st, L.p);
+  if (e != cudaSuccess) return cuda_status(e);
   return after_launch();
 }
 
@@ -133,7 +135,8 @@ int launch_fused(const Layer& L, cudaStream_t st) {
     if (e != cudaSuccess) return cuda_status(e);
     attr_set = true;
   }
-  fused_down_kernel<HAS_TRAN><<<L.grid, kFusedThreads, L.smem, st>>>(L.f);
+  cudaError_t e = launch_pdl(fused_down_kernel<HAS_TRAN>, L.grid, kFusedThreads, L.smem, st, L.f);
+  if (e != cudaSuccess) return cuda_status(e);
   return after_launch();
 }
 
@@ -144,8 +147,9 @@ int launch_layer(const Layer& L, cudaStream_t st) {
     case V_FINALIZE: {
       int64_t blocks = ceil_div64(L.fin_n8, 256);
       if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-      finalize_lr_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(L.fin_acc), L.fin_bias,
-                                                      reinterpret_cast<uint4*>(L.fin_out), L.fin_n8, L.fin_w);
+      cudaError_t e = launch_pdl(finalize_lr_kernel, (int)blocks, 256, 0, st, reinterpret_cast<const float4*>(L.fin_acc),
+                                 L.fin_bias, reinterpret_cast<uint4*>(L.fin_out), L.fin_n8, L.fin_w);
+      if (e != cudaSuccess) return cuda_status(e);
       return after_launch();
     }
     case V_PW32: return launch_variant<EPI_ROWS, 32, 32>(L, st);
@@ -627,6 +631,7 @@ fc_fuse_kernel(const float* __restrict__ maps, const float* __restrict__ fcw, fl
   __shared__ float s_w[32 * kMaxMaps + 65];
   const int nw = 32 * M + 65;
   for (int i = threadIdx.x; i < nw; i += blockDim.x) s_w[i] = fcw[i];
+  griddep_wait();   // weights above are static; the per-map images come from the previous launch
   __syncthreads();
   const float* w0 = s_w;
   const float* b0 = s_w + 32 * M;
@@ -996,8 +1001,9 @@ extern "C" int vsr_srfbn_forward(vsr_srfbn_plan* pl, const float* x, float* y, v
     const int64_t n = (int64_t)3 * c.upscale * c.upscale * c.h * c.w;
     int64_t blocks = ceil_div64(ceil_div64(n, 4), 256);
     if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-    fc_fuse_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const float*>(pl->ws + pl->o_premix),
-                                                reinterpret_cast<const float*>(pl->dev_w + pl->fc_off), y, c.num_maps, n);
+    cudaError_t e = launch_pdl(fc_fuse_kernel, (int)blocks, 256, 0, st, reinterpret_cast<const float*>(pl->ws + pl->o_premix),
+                               reinterpret_cast<const float*>(pl->dev_w + pl->fc_off), y, c.num_maps, n);
+    if (e != cudaSuccess) return cuda_status(e);
     int rc = after_launch();
     if (rc) return rc;
   }
