@@ -154,6 +154,20 @@ int vsr_estimate_slot(const float* hr, const uint8_t* mask, float* slot, int h, 
                       vsr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * flow colour coding + resize glue on the device.
+ * ref: utils/flow_utils.py:4-24 (flow2img), :27-61, :64-112; FlowProjectionModule.py:31-32 (the reference
+ * colour-codes on the host: .cpu().numpy() -> flow2img -> torch.tensor(...).cuda());
+ * network/video_super_resolution.py:35,52 (transpose1323 + F.interpolate, default nearest).
+ * flow (h,w,2) f32 -> img_u8 (h,w,3) u8 Middlebury colour code (NULL to skip) and/or
+ * planes (3,out_h,out_w) f32 = the same image transposed to CHW and nearest-resized (NULL to skip).
+ * The normalisation is a global max of the flow magnitude (flow_utils.py:14-15), so it is one flow
+ * map per call.  workspace: >= 8 bytes of device memory, 4-byte aligned.  NumPy >= 2 promotion rules
+ * (fp32 up to the normalising division, float64 after `+ eps`), see tests/golden/flow2img.npz.
+ * ---------------------------------------------------------------------------------------- */
+int vsr_flow_to_image(const float* flow, int h, int w, uint8_t* img_u8, float* planes, int out_h,
+                      int out_w, void* workspace, vsr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * a6 / a7: the fusion / upsampling convolutions (SRFBN + per-pixel fc over the map axis).
  * ref: SRProjectionModule.forward (SRProjectionModule.py:133-147), FeedbackBlock (:7-93),
  * blocks.py:7-74, with the INTENDED dense-concat dataflow.

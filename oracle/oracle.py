@@ -56,6 +56,10 @@ def lib():
         _lib.or_channelnorm_backward.restype = None
         _lib.or_correlation.argtypes = [_f32p] * 3 + [I] * 11
         _lib.or_correlation.restype = None
+        _lib.or_flow2img.argtypes = [_f32p, _u8p, I, I]
+        _lib.or_flow2img.restype = None
+        _lib.or_resize_nearest_planar.argtypes = [_u8p, _f32p, I, I, I, I]
+        _lib.or_resize_nearest_planar.restype = None
     return _lib
 
 
@@ -280,3 +284,21 @@ def warp_fuse_front(frames, flows, inv_depth, logits_a, logits_b, estimate=None,
     return stack, {"proj_flow": proj_f, "count_flow": cnt_f, "hole_flow": hole_f, "proj_depth": proj_d, "wsum": wsum,
                    "count_depth": cnt_d, "hole_depth": hole_d, "warped": warped, "resid": resid, "mask": mask,
                    "mask_warped": mask_w}
+
+
+def flow2img(flow):
+    """utils/flow_utils.py:4-24: flow (h,w,2) fp32 -> Middlebury colour code (h,w,3) u8."""
+    flow = _c(flow, np.float32)
+    h, w = flow.shape[:2]
+    img = np.empty((h, w, 3), np.uint8)
+    lib().or_flow2img(_p(flow, _f32p), _p(img, _u8p), h, w)
+    return img
+
+
+def resize_nearest_planar(img, H, W):
+    """interpolate(transpose1323(img), (H,W)) (video_super_resolution.py:35): (h,w,3) u8 -> (3,H,W) fp32."""
+    img = _c(img, np.uint8)
+    h, w = img.shape[:2]
+    out = np.empty((3, H, W), np.float32)
+    lib().or_resize_nearest_planar(_p(img, _u8p), _p(out, _f32p), h, w, H, W)
+    return out

@@ -7,6 +7,10 @@ this hot path the flow comes from a pluggable `estimator(input1, input2) -> (h',
 itself is out of scope; benchmarks plug synthetic flow) and the module does the
 north-star work on the GPU: forward splat with count, normalise, hole fill (ops.project_flow,
 SURVEY.md Appendix B).  The three output channels are (projected fx, projected fy, hole mask).
+
+`colour=True` keeps the reference's output instead -- the Middlebury colour code of the estimated flow as an
+(h',w',3) fp32 map (:31-32, utils/flow_utils.py:4-24) -- computed on the device (ops.flow_to_image) rather than
+through .cpu().numpy() and back.
 """
 import torch
 from torch.nn.modules.module import Module
@@ -16,8 +20,9 @@ from ...utils.tools import StaticCenterCrop
 
 
 class FlowProjectionModule(Module):
-    def __init__(self, image_size=None, render_size=None, estimator=None):
+    def __init__(self, image_size=None, render_size=None, estimator=None, colour=False):
         super(FlowProjectionModule, self).__init__()
+        self.colour = colour
         self.cropper = None
         self.image_size = image_size
         self.render_size = render_size
@@ -40,11 +45,20 @@ class FlowProjectionModule(Module):
             proj, wsum, count, hole = proj[0], wsum[0], count[0], hole[0]
         return {"proj": proj, "wsum": wsum, "count": count, "hole": hole}
 
+    def colour_code(self, flow, out_size=None):
+        """flow (h',w',2) CUDA fp32 -> (h',w',3) fp32 colour image (FlowProjectionModule.py:32), or with
+        out_size=(H,W) the (3,H,W) planes after the caller's transpose + nearest resize
+        (network/video_super_resolution.py:35)."""
+        img, planes = ops.flow_to_image(flow.contiguous(), out_size=out_size, want_u8=out_size is None)
+        return img.to(torch.float32) if out_size is None else planes
+
     def forward(self, input1, input2):
         if self.estimator is None:
             raise RuntimeError("FlowProjectionModule: no flow estimator attached (FlowNet2 is outside the "
                                "B200 hot path); pass estimator=callable or call .project(flow)")
         crop = self._crop(input1)
         flow = self.estimator(crop(input1), crop(input2))          # (h',w',2)
+        if self.colour:
+            return self.colour_code(flow)
         r = self.project(flow)
         return torch.cat((r["proj"], r["hole"].to(torch.float32).unsqueeze(-1)), dim=-1)

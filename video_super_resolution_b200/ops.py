@@ -190,6 +190,30 @@ def project_depth_flow(flow: torch.Tensor, inv_depth: torch.Tensor):
     return project_flow(flow, inv_depth)
 
 
+def flow_to_image(flow: torch.Tensor, out_size=None, want_u8: bool = True):
+    """Middlebury colour code of one flow map, on the device.  flow (h,w,2) f32 -> (img, planes):
+    img (h,w,3) u8 (None unless want_u8), planes (3,H,W) f32 = the image transposed to CHW and nearest-resized to
+    out_size=(H,W) (None unless out_size is given).
+    ref: utils/flow_utils.py:4-24 via FlowProjectionModule.py:31-32; video_super_resolution.py:35,52."""
+    _req(flow, torch.float32, "flow")
+    if flow.dim() != 3 or flow.shape[2] != 2:
+        raise ValueError("flow_to_image: (h,w,2) flow expected")
+    if out_size is None and not want_u8:
+        raise ValueError("flow_to_image: nothing to compute")
+    h, w = flow.shape[:2]
+    img = torch.empty((h, w, 3), dtype=torch.uint8, device=flow.device) if want_u8 else None
+    planes = torch.empty((3, int(out_size[0]), int(out_size[1])), dtype=torch.float32, device=flow.device) \
+        if out_size is not None else None
+    ws = torch.empty(2, dtype=torch.int32, device=flow.device)
+    with torch.cuda.device(flow.device):
+        _lib.check(_lib.lib().vsr_flow_to_image(flow.data_ptr(), h, w, img.data_ptr() if want_u8 else None,
+                                                planes.data_ptr() if planes is not None else None,
+                                                planes.shape[1] if planes is not None else 0,
+                                                planes.shape[2] if planes is not None else 0,
+                                                ws.data_ptr(), _stream()), "flow_to_image")
+    return img, planes
+
+
 def vos_threshold(logits_a: torch.Tensor, logits_b: torch.Tensor) -> torch.Tensor:
     """sigmoid(a)+sigmoid(b) > 0.7 -> u8 {0,1}.  ref: VOSProjectionModule.py:22-25."""
     _req(logits_a, torch.float32, "logits_a")
