@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from video_super_resolution_b200.pipeline import gather_frames, shard_windows
+from video_super_resolution_b200.pipeline import gather_frames, gather_frames_ragged, shard_windows
 
 
 def test_shard_windows_covers_all_once():
@@ -31,6 +31,11 @@ def _worker(rank, world, port, out):
         local = torch.stack([torch.full((H, W, 3), i, dtype=torch.uint8) for i in idx])
         allf = gather_frames(local)
         ok = tuple(allf.shape) == (n * world, H, W, 3) and all(int(allf[i, 0, 0, 0]) == i for i in range(n * world))
+        # shards of unequal length (C5: 38/38/.../32 windows): counts exchanged, padded gather, padding dropped
+        mine = list(shard_windows(5, world, rank))               # 3 + 2 windows
+        local = torch.stack([torch.full((H, W, 3), 10 + i, dtype=torch.uint8) for i in mine])
+        rag = gather_frames_ragged(local)
+        ok = ok and tuple(rag.shape) == (5, H, W, 3) and all(int(rag[i, 0, 0, 0]) == 10 + i for i in range(5))
         out[rank] = bool(ok)
     finally:
         dist.destroy_process_group()

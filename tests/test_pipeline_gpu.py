@@ -88,3 +88,47 @@ def test_module_surfaces_refuse_missing_estimators():
     assert tuple(out.shape) == (64, 64, 3)                       # (h',w',3) like the reference (:33)
     want = orc.flow_projection(flow.cpu().numpy()[None])
     assert np.array_equal(out[..., 2].cpu().numpy().astype(np.uint8), want[3][0])
+
+
+def test_run_sequence_chunked_and_sharded():
+    """The video loop (main.py:190-203) over the reference's chunks: sharding by whole chunks (shard_chunks)
+    reproduces the single-run frames bit for bit; the even split differs only inside the chunk it cuts."""
+    from video_super_resolution_b200.network.video_super_resolution import VSR
+    from video_super_resolution_b200.pipeline import run_sequence, shard_chunks, shard_chunks_even
+    from video_super_resolution_b200.utils.video_utils import chunk_windows
+    T, h, w, n = 3, 16, 24, 23
+    frames = syn.frames(n, h, w, seed=1).to(DEV)
+    flows = syn.smooth_flow(n - 1, h, w, 2.0, seed=2).to(DEV)
+    inv = syn.inv_depth(n - 1, h, w, seed=3).to(DEV)
+    la, lb = (t.to(DEV) for t in syn.logits(h, w, seed=4))
+    torch.manual_seed(0)
+    vsr = VSR(window=T)
+    chunks = chunk_windows(n, T, splitvideonum=4)               # 5-window chunks: [5,5,5,5,1]
+    assert [len(c) for c in chunks] == [5, 5, 5, 5, 1]
+    whole, idx = run_sequence(vsr, frames, flows, inv, lambda k: (la, lb), chunks)
+    assert idx == list(range(n - T + 1)) and whole.shape == (n - T + 1, 4 * h, 4 * w, 3) and whole.dtype == torch.uint8
+    parts = [run_sequence(vsr, frames, flows, inv, lambda k: (la, lb), shard_chunks(chunks, 2, r)) for r in range(2)]
+    assert parts[0][1] + parts[1][1] == idx
+    assert torch.equal(torch.cat([parts[0][0], parts[1][0]]), whole)
+    even = [run_sequence(vsr, frames, flows, inv, lambda k: (la, lb), shard_chunks_even(chunks, 2, r)) for r in range(2)]
+    cat = torch.cat([even[0][0], even[1][0]])
+    cut = even[1][1][0]                                         # first window of rank 1: an extra reset
+    assert cut % 5 != 0                                         # ... inside a chunk
+    same = [bool(torch.equal(cat[k], whole[k])) for k in idx]
+    chunk_end = (cut // 5 + 1) * 5
+    assert all(same[:cut]) and all(same[chunk_end:])
+    assert not same[cut]
+
+
+def test_pinned_frame_ring_overlapped_h2d():
+    from video_super_resolution_b200.utils.video_utils import PinnedFrameRing
+    ring = PinnedFrameRing((3, 8, 12, 3), depth=2, device=DEV)
+    outs = []
+    for k in range(5):
+        src = torch.full((3, 8, 12, 3), float(k))
+        dev, ready, slot = ring.put(src)
+        torch.cuda.current_stream().wait_event(ready)
+        outs.append(dev.sum().clone())
+        ring.release(slot)
+    torch.cuda.synchronize()
+    assert [float(o) for o in outs] == [k * 3 * 8 * 12 * 3 for k in range(5)]

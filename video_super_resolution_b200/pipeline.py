@@ -32,6 +32,39 @@ def shard_windows(num_windows: int, world_size: int, rank: int) -> range:
     return range(min(rank * per, num_windows), min((rank + 1) * per, num_windows))
 
 
+def shard_chunks(chunks, world_size: int, rank: int) -> list:
+    """Contiguous groups of whole chunks for `rank`, balanced by window count.  With the reference's own
+    chunks (utils.video_utils.chunk_windows) every shard boundary is a chunk boundary, where the reference
+    resets the recurrence anyway (main.py:196): the sharded result is identical to a single-GPU run."""
+    chunks = [c for c in chunks if len(c) > 0]
+    total = sum(len(c) for c in chunks)
+    out, acc, r = [[] for _ in range(world_size)], 0, 0
+    for c in chunks:
+        # move on when this rank holds its share (boundaries at multiples of total / world)
+        while r < world_size - 1 and acc >= (r + 1) * total / world_size:
+            r += 1
+        out[r].append(c)
+        acc += len(c)
+    return out[rank]
+
+
+def shard_chunks_even(chunks, world_size: int, rank: int) -> list:
+    """Even split by windows (rank r takes windows [r*ceil(N/G), (r+1)*ceil(N/G))), chunks cut at the
+    rank boundaries.  Better balanced than shard_chunks when there are few chunks per rank (C5: 38 windows per
+    rank instead of 45/30), at the price of one extra recurrence reset where a rank boundary falls inside a
+    chunk -- results differ from the single-GPU run only downstream of those resets, inside that chunk."""
+    chunks = [c for c in chunks if len(c) > 0]
+    total = sum(len(c) for c in chunks)
+    mine = shard_windows(total, world_size, rank)
+    out, base = [], 0
+    for c in chunks:
+        lo, hi = max(mine.start, base), min(mine.stop, base + len(c))
+        if lo < hi:
+            out.append(range(c.start + lo - base, c.start + hi - base))
+        base += len(c)
+    return out
+
+
 class WarpFusePipeline:
     def __init__(self, T: int, h: int, w: int, sr: SRProjectionModule | None = None, scale: int = 4,
                  device="cuda:0", run_fusion: bool = True):
@@ -93,3 +126,49 @@ def gather_frames(local_frames: torch.Tensor, group=None) -> torch.Tensor:
     else:
         dist.all_gather(list(out.unbind(0)), local_frames.contiguous(), group=group)  # gloo (CPU tests)
     return out.flatten(0, 1)
+
+
+def gather_frames_ragged(local_frames: torch.Tensor, group=None) -> torch.Tensor:
+    """gather_frames for shards of unequal length: counts are exchanged first, shards are padded to the
+    longest one for the single all-gather, and the padding is dropped."""
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local_frames
+    world = dist.get_world_size(group)
+    n = torch.tensor([local_frames.shape[0]], dtype=torch.int64, device=local_frames.device)
+    counts = torch.zeros(world, dtype=torch.int64, device=local_frames.device)
+    if local_frames.is_cuda:
+        dist.all_gather_into_tensor(counts, n, group=group)
+    else:
+        dist.all_gather(list(counts.unbind(0)), n[0], group=group)
+    counts = counts.tolist()
+    m = max(counts)
+    pad = torch.zeros((m,) + tuple(local_frames.shape[1:]), dtype=local_frames.dtype, device=local_frames.device)
+    pad[:local_frames.shape[0]] = local_frames
+    allf = gather_frames(pad, group).unflatten(0, (world, m))
+    return torch.cat([allf[r, :counts[r]] for r in range(world)])
+
+
+def run_sequence(vsr, frames, flows, inv_depth, logits, chunks, out: torch.Tensor | None = None):
+    """The reference's loop over a video (main.py:190-203) on this rank's chunks.
+
+    frames (N,h,w,3) fp32 0..255, flows (N-1,h,w,2), inv_depth (N-1,h,w) on the device; logits: callable
+    k -> (logits_a, logits_b) for window k; chunks: list of ranges of window indices (shard_chunks).
+    Within a chunk window k+1 receives window k's output as its estimate; every chunk starts with
+    estimated_image = None.  Returns (u8 frames (n_local,H,W,3), list of window indices)."""
+    T = vsr.window
+    idx = [k for c in chunks for k in c]
+    s = vsr.model.upscale_factor
+    h, w = frames.shape[1:3]
+    if out is None:
+        out = torch.empty((len(idx), s * h, s * w, 3), dtype=torch.uint8, device=frames.device)
+    i = 0
+    for c in chunks:
+        est = None
+        for k in c:
+            la, lb = logits(k)
+            y = vsr.forward_geometry(frames[k:k + T], flows[k:k + T - 1], inv_depth[k:k + T - 1], la, lb, est)
+            est = y
+            out[i] = y[0].clamp(0, 255).round().to(torch.uint8)      # (H,W,3) u8, utils/video_utils.py:23
+            i += 1
+    return out, idx
