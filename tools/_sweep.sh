@@ -1,4 +1,4 @@
-python -m pytest tests/test_pipeline_gpu.py -m gpu -x -q 2>&1 | tail -15 > gpurun_out/tests_seq.log
-python tools/bench_configs.py --config c3 > gpurun_out/bench_c3_r01.json 2> gpurun_out/bench_c3.err
-python tools/bench_configs.py --config c4 > gpurun_out/bench_c4_r01.json 2> gpurun_out/bench_c4.err
-python tools/bench_configs.py --config c5 > gpurun_out/bench_c5_n1_r01.json 2> gpurun_out/bench_c5.err
+python -m pytest tests/test_srfbn_gpu.py tests/test_fullsize_gpu.py -m gpu -x -q 2>&1 | tail -8 > gpurun_out/tests_dc.log
+python tools/layer_times.py --no-bw --summary > gpurun_out/lt_warp_arrive.log 2>&1
+VSR_DECONV_DEBUG=7 python tools/layer_times.py --no-bw --summary 2>&1 | grep -E "deconv" >> gpurun_out/lt_warp_arrive.log
+python bench.py --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/bench_s3c.json 2> gpurun_out/bench_s3c.err

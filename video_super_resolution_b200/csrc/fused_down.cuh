@@ -140,11 +140,11 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
       mbar_init(&wd_full[s], 1);
       mbar_init(&wd_empty[s], 1);
       mbar_init(&da_full[s], 1);
-      mbar_init(&da_empty[s], 32 * kFusedEpiWarps);
+      mbar_init(&da_empty[s], kFusedEpiWarps);
       mbar_init(&db_full[s], 1);
-      mbar_init(&db_empty[s], 32 * kFusedEpiWarps);
+      mbar_init(&db_empty[s], kFusedEpiWarps);
     }
-    mbar_init(h_full, 32 * kFusedEpiWarps);
+    mbar_init(h_full, kFusedEpiWarps);
     mbar_init(h_empty, 1);
     fence_barrier_init();
   }
@@ -368,13 +368,13 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
           if (p.debug & 2) {
             zero16(o);
             tc_fence_before();
-            mbar_arrive(&da_empty[buf]);
+            mbar_arrive_warp(&da_empty[buf]);
           } else {
             uint32_t v[32];
             tmem_ld32(lane_base + (uint32_t)(buf * 128 + sub * 32), v);
             tmem_ld_wait();
             tc_fence_before();
-            mbar_arrive(&da_empty[buf]);
+            mbar_arrive_warp(&da_empty[buf]);
             const int s16 = g * 4 + sub, ry = s16 >> 2, rx = s16 & 3;
             const bool ring = (Yb == 0 && ry < 2) || (Yb == p.lr_h && ry >= 2) || (Xb == 0 && rx < 2) ||
                               (Xb == p.lr_w && rx >= 2);
@@ -392,7 +392,7 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
                 make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
           }
           fence_proxy_async_smem();
-          mbar_arrive(h_full);
+          mbar_arrive_warp(h_full);
           ++m_h;
         }
       }
@@ -406,14 +406,14 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
       tc_fence_after();
       if (p.debug & 4) {
         tc_fence_before();
-        mbar_arrive(&db_empty[tb]);
+        mbar_arrive_warp(&db_empty[tb]);
       } else {
         uint32_t v[4][8];
 #pragma unroll
         for (int t = 0; t < 4; ++t) tmem_ld8(lane_base + kDB + (uint32_t)(tb * 128 + t * 32 + sub * 8), v[t]);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(&db_empty[tb]);
+        mbar_arrive_warp(&db_empty[tb]);
         const int xl = lane & 15;
 #pragma unroll
         for (int dy = 0; dy < 2; ++dy) {

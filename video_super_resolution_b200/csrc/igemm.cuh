@@ -45,6 +45,9 @@ struct Chunk {
   int8_t dy;
   int8_t pad;
   int32_t c0;   // channel (innermost) offset
+  int32_t a_off;  // byte offset of this chunk's [128 x CK] A operand inside its pipeline stage
+  int32_t tx;     // bytes the chunk's TMA box brings (0: no load -- the operand is a shifted view of
+                  // another chunk's box: a tap one image row down is the same box 16 rows = 16*2*CK bytes in)
 };
 
 struct alignas(64) IgemmParams {
@@ -54,6 +57,7 @@ struct alignas(64) IgemmParams {
   Chunk chunks[kMaxChunks];
   int32_t num_chunks;
   int32_t cps;                 // K chunks per pipeline stage (one barrier round trip per stage, not per chunk)
+  int32_t stage_bytes;         // bytes of one pipeline stage (multiple of 1024)
   int32_t num_stages;
   // tile grid: total tiles = n_tiles * tiles_x * tiles_y * batch, n fastest
   int32_t n_tiles, tiles_x, tiles_y, batch;
@@ -91,6 +95,13 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// one arrival per warp: 512 epilogue threads arriving one by one are 512 serialised shared-memory atomics on one
+// word per hand-over (~32 cycles per warp, B300_MICROARCH "ATOMS single-bank"); the warp synchronises first
+// (every lane has executed its tcgen05.fence / fence.proxy.async), then one lane arrives for all
+__device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t addr = smem_u32(bar);
@@ -298,10 +309,10 @@ __host__ __device__ constexpr int a_stage_bytes() { return kTileM * CK * 2; }
 constexpr int kDeconvStageBytes = kDeconvEpiWarps * 32 * 128;   // EPI_DECONV: per warp 32 blocks x 2 sub-positions x 64 B
 
 template <int CK, int BN>
-inline size_t igemm_smem_bytes(int num_chunks, int num_stages, int extra = 0) {
+inline size_t igemm_smem_bytes(int num_chunks, size_t ring_bytes, int extra = 0) {
   size_t b = (size_t)num_chunks * b_chunk_bytes<CK, BN>();
   b = (b + 1023) / 1024 * 1024;
-  return 1024 /*align slack*/ + b + (size_t)num_stages * a_stage_bytes<CK>() + 1024 /*barriers + bias*/ + 2048 + extra;
+  return 1024 /*align slack*/ + b + ring_bytes + 1024 /*barriers + bias*/ + 2048 + extra;
 }
 
 template <int MODE, int CK, int BN>
@@ -322,7 +333,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
   const int b_region = ((p.num_chunks * kBBytes) + 1023) / 1024 * 1024;
   uint8_t* smem_b = smem;
   uint8_t* smem_a = smem + b_region;
-  uint8_t* tail = smem_a + p.num_stages * p.cps * kABytes;
+  uint8_t* tail = smem_a + p.num_stages * p.stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);          // [kMaxStages]
   uint64_t* empty_bar = full_bar + kMaxStages;                     // [kMaxStages]
   uint64_t* tmem_full = empty_bar + kMaxStages;                    // [2]
@@ -344,7 +355,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], kEpiThreads);
+      mbar_init(&tmem_empty[s], kEpiThreads / 32);
     }
     mbar_init(b_full, 1);
     fence_barrier_init();
@@ -373,11 +384,14 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
         for (int kc0 = 0; kc0 < p.num_chunks; kc0 += p.cps) {
           const int nk = min(p.cps, p.num_chunks - kc0);
           mbar_wait(&empty_bar[s], phase ^ 1);
-          mbar_expect_tx(&full_bar[s], (uint32_t)(nk * kABytes));
+          uint32_t tx = 0;
+          for (int j = 0; j < nk; ++j) tx += (uint32_t)p.chunks[kc0 + j].tx;
+          mbar_expect_tx(&full_bar[s], tx);
           for (int j = 0; j < nk; ++j) {
             const Chunk c = p.chunks[kc0 + j];
-            tma_load_4d(smem_a + (s * p.cps + j) * kABytes, &p.a_maps[c.map], &full_bar[s], c.c0, t.x0 + c.dx,
-                        t.y0 + c.dy, t.b);
+            if (c.tx)
+              tma_load_4d(smem_a + s * p.stage_bytes + c.a_off, &p.a_maps[c.map], &full_bar[s], c.c0, t.x0 + c.dx,
+                          t.y0 + c.dy, t.b);
           }
           if (++s == p.num_stages) { s = 0; phase ^= 1; }
         }
@@ -405,7 +419,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
           tc_fence_after();
           for (int j = 0; j < nk; ++j) {
             const int kc = kc0 + j;
-            const uint64_t a0 = dA + (uint64_t)(((s * p.cps + j) * kABytes) >> 4);
+            const uint64_t a0 = dA + (uint64_t)((s * p.stage_bytes + p.chunks[kc].a_off) >> 4);
             const uint64_t b0 = dB + (uint64_t)((kc * kBBytes) >> 4);
             if (!(p.debug & 4))
 #pragma unroll
@@ -459,7 +473,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
           tmem_ld_wait();
           if (cg == BN / 32 - 1) {
             tc_fence_before();
-            mbar_arrive(&tmem_empty[as]);     // accumulator stage is free again
+            mbar_arrive_warp(&tmem_empty[as]);     // accumulator stage is free again
           }
           if (valid) {
             uint32_t o[16];
@@ -487,7 +501,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
             tmem_ld_wait();
             if (c2 == 1) {
               tc_fence_before();
-              mbar_arrive(&tmem_empty[as]);
+              mbar_arrive_warp(&tmem_empty[as]);
             }
             const int s16 = t.n_tile * 8 + cg;
             const int ry = s16 >> 2, rx = s16 & 3;
@@ -507,8 +521,6 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
           // contiguous 2 KB runs of the pair's plane, clips at the tensor edge, and costs the LSU
           // nothing (the first version read the tile back with LDS and stored with STG: L1TEX 70 % busy).
           uint8_t* stg = s_stage + (warp - 2) * (32 * 128);
-          if (lane == 0) tma_store_wait_read();       // previous tile's stores have read the staging tile
-          __syncwarp();
 #pragma unroll
           for (int c2 = 0; c2 < 2; ++c2) {
             const int cg = sub * 2 + c2;
@@ -522,7 +534,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
             }
             if (c2 == 1) {
               tc_fence_before();
-              mbar_arrive(&tmem_empty[as]);
+              mbar_arrive_warp(&tmem_empty[as]);
             }
             if (p.debug & 2) continue;
             const int s16 = t.n_tile * 8 + cg;
@@ -532,6 +544,10 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
             uint32_t o[16];
             if (inside) convert32(v, s_bias, pc, o);   // ring positions (tile border only) stay zero
             else zero16(o);
+            if (c2 == 0) {   // the previous tile's store must have read the staging tile before it is overwritten
+              if (lane == 0) tma_store_wait_read();   // (waited for here, after the TMEM read + conversion, not before)
+              __syncwarp();
+            }
             uint8_t* srow = stg + lane * 128;
             const int sw = lane & 7;
 #pragma unroll
@@ -565,7 +581,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
           tmem_ld_wait();
           if (cg == 3) {
             tc_fence_before();
-            mbar_arrive(&tmem_empty[as]);
+            mbar_arrive_warp(&tmem_empty[as]);
           }
           if (valid) {
             uint32_t o[16];
@@ -587,7 +603,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
           tmem_ld32(taddr, v);
           tmem_ld_wait();
           tc_fence_before();
-          mbar_arrive(&tmem_empty[as]);
+          mbar_arrive_warp(&tmem_empty[as]);
           float* srow = S + row * kConvOutPitch;
 #pragma unroll
           for (int j = 0; j < 27; ++j) srow[j] = __uint_as_float(v[j]);

@@ -161,20 +161,28 @@ int launch_layer(const Layer& L, cudaStream_t st) {
   }
 }
 
-size_t variant_smem(int variant, int chunks, int stages) {
+size_t variant_smem(int variant, int chunks, size_t ring) {
   switch (variant) {
-    case V_PW32: return igemm_smem_bytes<32, 32>(chunks, stages);
+    case V_PW32: return igemm_smem_bytes<32, 32>(chunks, ring);
     case V_PW128:
-    case V_DECONV2: return igemm_smem_bytes<32, 128>(chunks, stages);
-    case V_DECONV: return igemm_smem_bytes<32, 256>(chunks, stages, kDeconvStageBytes);
-    default: return igemm_smem_bytes<32, 32>(chunks, stages, kConvOutStageBytes);
+    case V_DECONV2: return igemm_smem_bytes<32, 128>(chunks, ring);
+    case V_DECONV: return igemm_smem_bytes<32, 256>(chunks, ring, kDeconvStageBytes);
+    default: return igemm_smem_bytes<32, 32>(chunks, ring, kConvOutStageBytes);
   }
 }
 
 void finish_layer(Layer& L, int ctas_per_sm) {
   IgemmParams& p = L.p;
   if (p.cps < 1) p.cps = 1;
-  L.smem = variant_smem(L.variant, p.num_chunks, p.num_stages * p.cps);
+  if (p.stage_bytes == 0) {   // default: every chunk loads its own [128 x 32] box
+    constexpr int kA = a_stage_bytes<32>();
+    p.stage_bytes = p.cps * kA;
+    for (int i = 0; i < p.num_chunks; ++i) {
+      p.chunks[i].a_off = (i % p.cps) * kA;
+      p.chunks[i].tx = kA;
+    }
+  }
+  L.smem = variant_smem(L.variant, p.num_chunks, (size_t)p.num_stages * p.stage_bytes);
   int64_t total = (int64_t)p.n_tiles * p.tiles_x * p.tiles_y * p.batch;
   int64_t g = (int64_t)kNumSMs * ctas_per_sm;
   if (g > total) g = total;
@@ -246,20 +254,27 @@ int build_deconv(Layer& L, const void* x, int B, int h, int w, const void* w_dev
   memset(&L, 0, sizeof(L));
   L.variant = V_DECONV;
   IgemmParams& p = L.p;
-  int rc = make_act_map(&p.a_maps[0], x, kNF, w, h, B, 32, kTW, kTH);
+  // one box per dx: 16 x (8+1) LR pixels; the dy = -1 tap is the box itself, the dy = 0 tap the same box one
+  // image row (16 pixels = 1024 bytes, a whole number of swizzle atoms) further in -- 2 TMA boxes per tile, not 4
+  int rc = make_act_map(&p.a_maps[0], x, kNF, w, h, B, 32, kTW, kTH + 1);
   if (rc) return rc;
   rc = make_w_map(&p.b_map, w_dev, 4 * kNF, 512, 32, 256);
   if (rc) return rc;
+  constexpr int kBox = kTW * (kTH + 1) * 64;   // 9216 bytes
   // chunk t = (dy+1)*2 + (dx+1), tap at LR (Yb+dy, Xb+dx), dy,dx in {-1,0}
   for (int t = 0; t < 4; ++t) {
+    const int dyi = t >> 1, dxi = t & 1;
     p.chunks[t].map = 0;
-    p.chunks[t].dy = (int8_t)((t >> 1) - 1);
-    p.chunks[t].dx = (int8_t)((t & 1) - 1);
+    p.chunks[t].dy = -1;                     // box origin row (both dy taps live in the 9-row box)
+    p.chunks[t].dx = (int8_t)(dxi - 1);
     p.chunks[t].c0 = 0;
+    p.chunks[t].a_off = dxi * kBox + dyi * (kTW * 64);
+    p.chunks[t].tx = dyi == 0 ? kBox : 0;
   }
   p.num_chunks = 4;
   p.cps = 4;            // the 4 taps of a tile share one barrier round trip (the handshake loop of the issuing
-  p.num_stages = 2;     // threads, not the MMAs, is this kernel's floor: ~2000 cycles per tile with one per tap)
+  p.stage_bytes = 2 * kBox;   // threads, not the MMAs, was this kernel's floor: ~2000 cycles per tile with one per tap)
+  p.num_stages = 4;
   p.n_tiles = 2;
   p.tiles_x = ceil_div(w + 1, kTW);
   p.tiles_y = ceil_div(h + 1, kTH);
@@ -276,10 +291,8 @@ int build_deconv(Layer& L, const void* x, int B, int h, int w, const void* w_dev
   {
     const char* e = getenv("VSR_DECONV_DEBUG");
     p.debug = e ? atoi(e) : 0;
-    e = getenv("VSR_DECONV_CPS");        // tuning knobs: chunks per stage (1, 2 or 4) and ring depth
-    if (e && (atoi(e) == 1 || atoi(e) == 2 || atoi(e) == 4)) p.cps = atoi(e);
-    e = getenv("VSR_DECONV_STAGES");
-    if (e && atoi(e) >= 1 && atoi(e) * p.cps <= 12) p.num_stages = atoi(e);
+    e = getenv("VSR_DECONV_STAGES");     // tuning knob: ring depth (18 KB per stage)
+    if (e && atoi(e) >= 1 && atoi(e) <= 5) p.num_stages = atoi(e);
   }
   if (!nhwc) {
     EncodeTiledFn enc = encode_fn();
