@@ -1,4 +1,3 @@
-python -m pytest tests/test_srfbn_gpu.py tests/test_fullsize_gpu.py -m gpu -x -q 2>&1 | tail -8 > gpurun_out/tests_dc.log
-python tools/layer_times.py --no-bw --summary > gpurun_out/lt_warp_arrive.log 2>&1
-VSR_DECONV_DEBUG=7 python tools/layer_times.py --no-bw --summary 2>&1 | grep -E "deconv" >> gpurun_out/lt_warp_arrive.log
-python bench.py --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/bench_s3c.json 2> gpurun_out/bench_s3c.err
+python -m pytest tests/test_ops_gpu.py tests/test_fullsize_gpu.py tests/test_pipeline_gpu.py -m gpu -x -q 2>&1 | tail -12 > gpurun_out/tests_splat.log
+python tools/bench_configs.py --config c3 > gpurun_out/bench_c3_r01b.json 2> gpurun_out/bench_c3.err
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_splat.csv python tools/profile_splat.py > gpurun_out/ps_ncu.log 2>&1
