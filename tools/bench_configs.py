@@ -39,6 +39,7 @@ def setup():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ["NCCL_DEBUG"] = os.environ.get("VSR_NCCL_DEBUG", "WARN")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # the NCCL banner must not land on stdout
         dist.init_process_group("nccl", device_id=dev)
     return rank, world, dev
 
