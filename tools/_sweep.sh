@@ -1,3 +1,4 @@
-python -m pytest tests/test_ops_gpu.py tests/test_fullsize_gpu.py tests/test_pipeline_gpu.py -m gpu -x -q 2>&1 | tail -12 > gpurun_out/tests_splat.log
-python tools/bench_configs.py --config c3 > gpurun_out/bench_c3_r01b.json 2> gpurun_out/bench_c3.err
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_splat.csv python tools/profile_splat.py > gpurun_out/ps_ncu.log 2>&1
+for d in 0 8 1; do
+echo "debug $d" >> gpurun_out/lt_dc8.log
+VSR_DECONV_DEBUG=$d python tools/layer_times.py --no-bw --summary 2>&1 | grep -E "deconv" >> gpurun_out/lt_dc8.log
+done

@@ -76,7 +76,7 @@ struct alignas(64) IgemmParams {
   int32_t lr_h, lr_w;          // LR size (block-layout masks, deconv geometry)
   int32_t hrb_mask;            // EPI_ROWS flat over the HR block layout: zero the padding ring
   int32_t deconv_nhwc;         // EPI_DECONV: 1 = write plain NHWC HR instead of the block layout
-  int32_t debug;               // timing experiments (wrong results): bit0 no TMA stores, bit1 no TMEM reads/convert, bit2 no MMAs
+  int32_t debug;               // timing experiments (wrong results): bit0 no TMA stores, bit1 no TMEM reads/convert, bit2 no MMAs, bit3 all stores to one place
   // EPI_CONV_OUT extras
   const float* skip_src;       // network input x (M,3,h,w) fp32
   float inv_scale;             // 1 / upscale factor of the bilinear skip (0.25 or 0.5)
@@ -286,16 +286,48 @@ __device__ __forceinline__ void zero16(uint32_t (&o)[16]) {
 struct TileCoord {
   int n_tile, x0, y0, b;
 };
-__device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile) {
-  TileCoord t;
-  t.n_tile = tile % p.n_tiles;
-  int r = tile / p.n_tiles;
-  t.x0 = (r % p.tiles_x) * p.tile_w + p.org_x;
-  r /= p.tiles_x;
-  t.y0 = (r % p.tiles_y) * p.tile_h + p.org_y;
-  t.b = r / p.tiles_y;
-  return t;
-}
+// Tile walk of a persistent CTA: tile = blockIdx.x + k * gridDim.x, decoded as (n fastest, x, y, b).  The
+// decode costs four divisions by run-time values (~150 dependent instructions); done per tile by the single
+// producer thread and by every epilogue warp it was a visible part of the per-tile floor of the thin layers
+// (deconv: ~1 us per tile).  The walk divides once and then advances by the constant stride with carries.
+struct TileWalk {
+  int n, x, y, b;            // current tile, in tile units
+  int sn, sx, sy, sb;        // gridDim.x decomposed in the same radix
+  __device__ __forceinline__ void init(const IgemmParams& p, int tile, int stride) {
+    n = tile % p.n_tiles;
+    int r = tile / p.n_tiles;
+    x = r % p.tiles_x;
+    r /= p.tiles_x;
+    y = r % p.tiles_y;
+    b = r / p.tiles_y;
+    sn = stride % p.n_tiles;
+    r = stride / p.n_tiles;
+    sx = r % p.tiles_x;
+    r /= p.tiles_x;
+    sy = r % p.tiles_y;
+    sb = r / p.tiles_y;
+  }
+  __device__ __forceinline__ void next(const IgemmParams& p) {
+    n += sn;
+    int c = 0;
+    if (n >= p.n_tiles) { n -= p.n_tiles; c = 1; }
+    x += sx + c;
+    c = 0;
+    if (x >= p.tiles_x) { x -= p.tiles_x; c = 1; }
+    y += sy + c;
+    c = 0;
+    if (y >= p.tiles_y) { y -= p.tiles_y; c = 1; }
+    b += sb + c;
+  }
+  __device__ __forceinline__ TileCoord coord(const IgemmParams& p) const {
+    TileCoord t;
+    t.n_tile = n;
+    t.x0 = x * p.tile_w + p.org_x;
+    t.y0 = y * p.tile_h + p.org_y;
+    t.b = b;
+    return t;
+  }
+};
 
 // smem carve-up (dynamic, base aligned to 1024 by the kernel):
 //   [0, num_chunks*BN*CK*2)            resident weights, one swizzled [BN, CK] block per K chunk
@@ -379,8 +411,10 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
       griddep_wait();   // weights are static; activations only after the previous layers have completed
       int s = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile);
+      TileWalk walk;
+      walk.init(p, blockIdx.x, gridDim.x);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, walk.next(p)) {
+        const TileCoord t = walk.coord(p);
         for (int kc0 = 0; kc0 < p.num_chunks; kc0 += p.cps) {
           const int nk = min(p.cps, p.num_chunks - kc0);
           mbar_wait(&empty_bar[s], phase ^ 1);
@@ -439,8 +473,10 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
     const int row = q * 32 + lane;          // row of the 128-pixel tile
     int as = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(p, tile);
+    TileWalk walk;
+    walk.init(p, blockIdx.x, gridDim.x);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, walk.next(p)) {
+      const TileCoord t = walk.coord(p);
       mbar_wait(&tmem_full[as], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
@@ -560,7 +596,9 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
           if (lane == 0) {
             // one box = this warp's 2 block rows x 16 blocks of one sub-position-pair plane; rows or
             // columns beyond the tensor edge are clipped by the TMA unit
-            if (t.y0 + 2 * q <= p.lr_h && !(p.debug & 1))
+            if (p.debug & 8)   // timing experiment: every tile stores to the first tile's place (L2-resident, no DRAM)
+              tma_store_4d(&p.out_map, stg, 0, 0, 2 * q, t.n_tile * 4 + sub);
+            else if (t.y0 + 2 * q <= p.lr_h && !(p.debug & 1))
               tma_store_4d(&p.out_map, stg, 0, t.x0, t.y0 + 2 * q, t.b * 8 + t.n_tile * 4 + sub);
             tma_store_commit();
           }
