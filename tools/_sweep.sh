@@ -1,4 +1,2 @@
-for d in 0 8 1; do
-echo "debug $d" >> gpurun_out/lt_dc8.log
-VSR_DECONV_DEBUG=$d python tools/layer_times.py --no-bw --summary 2>&1 | grep -E "deconv" >> gpurun_out/lt_dc8.log
-done
+python -m pytest tests/test_srfbn_gpu.py tests/test_fullsize_gpu.py -m gpu -x -q 2>&1 | tail -8 > gpurun_out/tests_x2b.log
+python tools/bench_configs.py --config c4 > gpurun_out/bench_c4_r01b.json 2> gpurun_out/bench_c4.err

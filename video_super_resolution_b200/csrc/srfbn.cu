@@ -323,18 +323,24 @@ int build_deconv2(Layer& L, const void* x, int B, int h, int w, const void* w_de
   memset(&L, 0, sizeof(L));
   L.variant = V_DECONV2;
   IgemmParams& p = L.p;
-  int rc = make_act_map(&p.a_maps[0], x, kNF, w, h, B, 32, kTW, kTH);
+  // one 10-row box per dx; the three dy taps are the same box 0 / 1 / 2 image rows (1024 bytes each) further in
+  int rc = make_act_map(&p.a_maps[0], x, kNF, w, h, B, 32, kTW, kTH + 2);
   if (rc) return rc;
   rc = make_w_map(&p.b_map, w_dev, 9 * kNF, 128, 32, 128);
   if (rc) return rc;
+  constexpr int kBox = kTW * (kTH + 2) * 64;   // 10240 bytes
   for (int t = 0; t < 9; ++t) {   // tap at LR (Y+dy, X+dx)
+    const int dyi = t / 3, dxi = t % 3;
     p.chunks[t].map = 0;
-    p.chunks[t].dy = (int8_t)(t / 3 - 1);
-    p.chunks[t].dx = (int8_t)(t % 3 - 1);
+    p.chunks[t].dy = -1;
+    p.chunks[t].dx = (int8_t)(dxi - 1);
     p.chunks[t].c0 = 0;
+    p.chunks[t].a_off = dxi * kBox + dyi * (kTW * 64);
+    p.chunks[t].tx = dyi == 0 ? kBox : 0;
   }
   p.num_chunks = 9;
-  p.cps = 3;
+  p.cps = 9;
+  p.stage_bytes = 3 * kBox;
   p.num_stages = 3;
   p.n_tiles = 1;
   p.tiles_x = ceil_div(w, kTW);
@@ -368,7 +374,7 @@ int build_downconv2(Layer& L, const void* xhr, int B, int h, int w, const void* 
   for (int py = 0; py < 2; ++py) {
     cuuint64_t dims[4] = {64, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)B};
     cuuint64_t strides[3] = {128, (cuuint64_t)256 * w, (cuuint64_t)256 * w * h};
-    cuuint32_t box[4] = {32, (cuuint32_t)kTW, (cuuint32_t)kTH, 1};
+    cuuint32_t box[4] = {32, (cuuint32_t)kTW, (cuuint32_t)kTH + 2, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     void* base = const_cast<uint8_t*>(reinterpret_cast<const uint8_t*>(xhr)) + (size_t)py * 128 * w;
     CUresult r = enc(&p.a_maps[py], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es,
@@ -378,17 +384,26 @@ int build_downconv2(Layer& L, const void* xhr, int B, int h, int w, const void* 
   }
   int rc = make_w_map(&p.b_map, w_dev, 36 * kNF, 32, 32, 32);
   if (rc) return rc;
-  for (int ky = 0; ky < 6; ++ky)
-    for (int kx = 0; kx < 6; ++kx) {
-      Chunk& c = p.chunks[ky * 6 + kx];
-      c.map = (int8_t)(ky & 1);
-      c.dy = (int8_t)((ky >> 1) - 1);
-      c.dx = (int8_t)((kx >> 1) - 1);
-      c.c0 = (kx & 1) * 32;
-    }
+  // tap (ky, kx) = (2*a + py, 2*b + px): half-resolution offsets dy = a-1, dx = b-1.  For fixed (py, px, dx) the three
+  // dy taps are one 10-row box read 0 / 1 / 2 rows in: 12 boxes per tile instead of 36.  Chunk order (= weight
+  // packing order, pack_downconv2): ((py*2 + px)*3 + b)*3 + a; one pipeline stage = the 18 taps of one row parity.
+  constexpr int kBox = kTW * (kTH + 2) * 64;   // 10240 bytes
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px)
+      for (int b = 0; b < 3; ++b)
+        for (int a = 0; a < 3; ++a) {
+          Chunk& c = p.chunks[((py * 2 + px) * 3 + b) * 3 + a];
+          c.map = (int8_t)py;
+          c.dy = -1;
+          c.dx = (int8_t)(b - 1);
+          c.c0 = px * 32;
+          c.a_off = (px * 3 + b) * kBox + a * (kTW * 64);
+          c.tx = a == 0 ? kBox : 0;
+        }
   p.num_chunks = 36;
-  p.cps = 4;
-  p.num_stages = 4;
+  p.cps = 18;
+  p.stage_bytes = 6 * kBox;
+  p.num_stages = 2;
   p.n_tiles = 1;
   p.tiles_x = ceil_div(w, kTW);
   p.tiles_y = ceil_div(h, kTH);
@@ -587,11 +602,17 @@ void pack_deconv2(const float* w, uint16_t* dst) {
           dst[(s * 32 + o) * 288 + t * 32 + c] = f2bf(w[((c * 32 + o) * 6 + ky) * 6 + kx]);
         }
 }
-// x2: Conv2d weight (o, c, 6, 6) s2 p2 -> [32 = o][1152 = (ky*6+kx)*32 + c]
+// x2: Conv2d weight (o, c, 6, 6) s2 p2 -> [32 = o][1152 = chunk*32 + c], chunk = ((py*2 + px)*3 + b)*3 + a for tap
+// (ky, kx) = (2a + py, 2b + px) -- the order build_downconv2 issues its taps in
 void pack_downconv2(const float* w, uint16_t* dst) {
   for (int o = 0; o < 32; ++o)
-    for (int t = 0; t < 36; ++t)
-      for (int c = 0; c < 32; ++c) dst[o * 1152 + t * 32 + c] = f2bf(w[(o * 32 + c) * 36 + t]);
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px)
+        for (int b = 0; b < 3; ++b)
+          for (int a = 0; a < 3; ++a) {
+            const int chunk = ((py * 2 + px) * 3 + b) * 3 + a, ky = 2 * a + py, kx = 2 * b + px;
+            for (int c = 0; c < 32; ++c) dst[o * 1152 + chunk * 32 + c] = f2bf(w[((o * 32 + c) * 6 + ky) * 6 + kx]);
+          }
 }
 // conv_out (3,32,3,3) for the output-shift form -> [32 = (ky*3+kx)*3 + o][32 = c], rows 27..31 zero
 void pack_conv_out(const float* w, uint16_t* dst) {
