@@ -1,4 +1,4 @@
-"""GPU tests at BASELINE.json's full sizes (C2, C3, C5) through properties that do not need the CPU
+"""GPU tests of BASELINE.json's configurations (C1 .. C5) at their full sizes through properties that do not need the CPU
 oracle at that size, plus direct oracle comparisons where the C oracle is fast enough."""
 import numpy as np
 import pytest
@@ -12,6 +12,25 @@ from video_super_resolution_b200.pipeline import shard_windows
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
+
+
+def test_c1_single_pair_64x64_plumbing():
+    """C1: one synthetic frame pair 64x64, random flow + depth: FlowProjection, DepthProjection and the bilinear
+    warp along the projected flow, GPU (through the C ABI) against the CPU oracle."""
+    h = w = 64
+    flow = syn.random_flow(1, h, w, 6.0, seed=1)
+    inv = syn.inv_depth(1, h, w, seed=2)
+    frame = syn.frames(1, h, w, seed=3)
+    for d in (None, inv):
+        if d is None:
+            proj, wsum, count, hole = ops.project_flow(flow.to(DEV))
+        else:
+            proj, wsum, count, hole = ops.project_depth_flow(flow.to(DEV), d.to(DEV))
+        o_proj, o_wsum, o_count, o_hole = orc.flow_projection(flow.numpy(), None if d is None else d.numpy())
+        assert np.array_equal(count.cpu().numpy(), o_count) and np.array_equal(hole.cpu().numpy(), o_hole)
+        assert np.abs(proj.cpu().numpy() - o_proj).max() <= 1e-3
+        warped = ops.warp(frame.to(DEV), proj, True)                     # reference arithmetic, bit for bit
+        assert np.array_equal(warped.cpu().numpy(), orc.warp_nhwc(frame.numpy(), proj.cpu().numpy(), True))
 
 
 def test_c3_large_motion_occlusion_1080p_against_oracle():

@@ -126,6 +126,8 @@ def test_autograd_function_surfaces_backward():
     dict(shape=(1, 16, 20, 28), pad=5, k=3, md=4, s1=1, s2=1),        # 3x3 kernel window (pad >= md + 1: with a
                                                                       # smaller pad the reference reads outside its padded copy)
     dict(shape=(1, 8, 21, 37), pad=4, k=1, md=4, s1=2, s2=2),         # strided outputs
+    dict(shape=(1, 20, 9, 300), pad=20, k=1, md=20, s1=1, s2=2),      # register-tiled path: 3 x-tiles, ragged, C % 8 != 0
+    dict(shape=(2, 12, 11, 70), pad=8, k=1, md=8, s1=1, s2=2),        # register-tiled path with D = 9
 ])
 def test_reference_correlation_equals_oracle_and_product(cfg):
     """correlation_cuda.forward of the reference binary (correlation_cuda_kernel.cu:46-147) vs oracle vs product;
@@ -144,3 +146,19 @@ def test_reference_correlation_equals_oracle_and_product(cfg):
     assert np.abs(got.cpu().numpy() - want).max() <= tol
     orc_out = orc.correlation(a.cpu().numpy(), b.cpu().numpy(), cfg["pad"], cfg["k"], cfg["md"], cfg["s1"], cfg["s2"])
     assert np.abs(orc_out - want).max() <= tol
+
+
+def test_correlation_register_tiled_path_is_bit_identical_to_generic_kernel(monkeypatch):
+    """kernel_size 1 / stride1 1 / stride2 2 (FlowNetC.py:22) takes the register-tiled kernel; it keeps the generic
+    kernel's fp32 FMA chain in channel order, so the two agree bit for bit (also with pad < max_displacement, where
+    the output shrinks and the window centres start inside the image)."""
+    g = torch.Generator().manual_seed(7)
+    for shape, pad, md in (((1, 37, 30, 150), 20, 20), ((2, 16, 50, 90), 6, 10)):
+        a = torch.randn(shape, generator=g).to(DEV)
+        b = torch.randn(shape, generator=g).to(DEV)
+        monkeypatch.delenv("VSR_CORR_GENERIC", raising=False)
+        fast = ops.correlation(a, b, pad, 1, md, 1, 2, 1)
+        monkeypatch.setenv("VSR_CORR_GENERIC", "1")
+        slow = ops.correlation(a, b, pad, 1, md, 1, 2, 1)
+        assert torch.equal(fast, slow)
+        assert fast.abs().max().item() > 0

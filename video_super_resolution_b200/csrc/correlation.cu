@@ -17,6 +17,8 @@
 // so results agree to fp32 rounding, not bit for bit).
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace vsr {
 namespace {
 
@@ -82,6 +84,124 @@ correlation_forward_kernel(const float* __restrict__ in1, const float* __restric
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Fast path for FlowNetC's configuration (kernel_size 1, stride1 1, stride2 2; FlowNetC.py:22): the cost volume of
+// one (n, y, tj) row pair is a banded product out[x, ti] = sum_c A[c, x] * B[c, x + 2*(ti-R)] -- register-tiled.
+// A warp owns 128 consecutive x of one row pair.  Channels are staged 8 at a time in shared memory with the two
+// row segments DE-INTERLEAVED BY COLUMN PARITY, because every displacement is even: a thread that owns the four
+// same-parity columns x, x+2, x+4, x+6 then needs 4 contiguous A values and 24 contiguous B values per channel --
+// 7 16-byte shared loads for 84 FMAs, against one global load per FMA in the generic kernel above (which was
+// L1-bound at 2 TFLOP/s).  Same fp32 FMA chain in channel order as the generic kernel: identical bits.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kCorrCc = 8;                     // channels per staging round
+constexpr int kCorrXT = 128;                   // output columns per warp task
+constexpr int kCorrWarps = 4;
+constexpr int kCorrBW = kCorrXT + 2 * (kMaxD - 1);   // 168 columns of the second image per task
+
+__global__ void __launch_bounds__(32 * kCorrWarps)
+correlation_s2_kernel(const float* __restrict__ in1, const float* __restrict__ in2, float* __restrict__ out, int B,
+                      int C, int H, int W, int outH, int outW, int off, int R, int D, int xtiles) {
+  __shared__ __align__(16) float sA[kCorrWarps][kCorrCc][2][kCorrXT / 2];
+  __shared__ __align__(16) float sB[kCorrWarps][kCorrCc][2][kCorrBW / 2];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int par = lane >> 4, q = lane & 15;    // a quarter-warp shares the parity: conflict-free 16-byte loads
+  const int64_t warp_global = (int64_t)blockIdx.x * kCorrWarps + wib;
+  const int64_t n_warps = (int64_t)gridDim.x * kCorrWarps;
+  const int64_t n_tasks = (int64_t)B * outH * D * xtiles;
+  const int64_t HW = (int64_t)H * W;
+  float (*A)[2][kCorrXT / 2] = sA[wib];
+  float (*Bs)[2][kCorrBW / 2] = sB[wib];
+  for (int64_t task = warp_global; task < n_tasks; task += n_warps) {
+    const int xt = (int)(task % xtiles);
+    int64_t r = task / xtiles;
+    const int tjw = (int)(r % D);
+    r /= D;
+    const int y = (int)(r % outH);
+    const int n = (int)(r / outH);
+    const int x0 = xt * kCorrXT;
+    const int ya = y + off, yb = ya + (tjw - R) * 2;
+    const int xs = x0 + off;                      // in1 column of output column x0
+    const bool rows_ok = ya >= 0 && ya < H && yb >= 0 && yb < H;   // a zero-padded row contributes nothing
+    float acc[4][kMaxD];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int t = 0; t < kMaxD; ++t) acc[k][t] = 0.0f;
+    if (rows_ok) {
+      const float* p1 = in1 + (int64_t)n * C * HW + (int64_t)ya * W;
+      const float* p2 = in2 + (int64_t)n * C * HW + (int64_t)yb * W;
+      // column validity of this lane's staging slots, once per task (bit j: slot lane + 32 j)
+      uint32_t okA = 0, okB = 0;
+#pragma unroll
+      for (int j = 0; j < kCorrXT / 32; ++j) {
+        const int xi = lane + 32 * j, gx = xs + xi;
+        okA |= (uint32_t)(gx >= 0 && gx < W && x0 + xi < outW) << j;
+      }
+#pragma unroll
+      for (int j = 0; j < (kCorrBW + 31) / 32; ++j) {
+        const int xi = lane + 32 * j, gx = xs - 2 * R + xi;
+        okB |= (uint32_t)(xi < kCorrBW && gx >= 0 && gx < W) << j;
+      }
+      const float* q1 = p1 + xs + lane;
+      const float* q2 = p2 + xs - 2 * R + lane;
+      float* dA = &A[0][lane & 1][lane >> 1];            // slot lane + 32 j -> [(lane&1)][(lane>>1) + 16 j]
+      float* dB = &Bs[0][lane & 1][lane >> 1];
+      for (int c0 = 0; c0 < C; c0 += kCorrCc) {
+        const int nc = min(kCorrCc, C - c0);
+#pragma unroll
+        for (int c = 0; c < kCorrCc; ++c) {
+          const uint32_t mA = c < nc ? okA : 0u, mB = c < nc ? okB : 0u;
+          const float* r1 = q1 + (int64_t)(c0 + c) * HW;
+          const float* r2 = q2 + (int64_t)(c0 + c) * HW;
+#pragma unroll
+          for (int j = 0; j < kCorrXT / 32; ++j)
+            dA[c * kCorrXT + 16 * j] = ((mA >> j) & 1u) ? __ldg(r1 + 32 * j) : 0.0f;
+#pragma unroll
+          for (int j = 0; j < (kCorrBW + 31) / 32; ++j)
+            if (lane + 32 * j < kCorrBW) dB[c * kCorrBW + 16 * j] = ((mB >> j) & 1u) ? __ldg(r2 + 32 * j) : 0.0f;
+        }
+        __syncwarp();
+#pragma unroll 2
+        for (int c = 0; c < kCorrCc; ++c) {
+          const float4 a4 = *reinterpret_cast<const float4*>(&A[c][par][4 * q]);
+          const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+          float bb[24];
+#pragma unroll
+          for (int j = 0; j < 6; ++j) {
+            const float4 b4 = *reinterpret_cast<const float4*>(&Bs[c][par][4 * q + 4 * j]);
+            bb[4 * j] = b4.x; bb[4 * j + 1] = b4.y; bb[4 * j + 2] = b4.z; bb[4 * j + 3] = b4.w;
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int t = 0; t < kMaxD; ++t)
+              if (t < D) acc[k][t] = fmaf(a[k], bb[k + t], acc[k][t]);
+        }
+        __syncwarp();
+      }
+    }
+    // transpose through shared memory so that the stores are 128 contiguous floats per displacement
+    const float nelems = (float)C;
+    float* S = &A[0][0][0];
+    float* o = out + (((int64_t)n * D * D + (int64_t)tjw * D) * outH + y) * outW + x0;
+#pragma unroll
+    for (int t = 0; t < kMaxD; ++t) {
+      if (t < D) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) S[8 * q + par + 2 * k] = __fdiv_rn(acc[k][t], nelems);
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < kCorrXT / 32; ++j) {
+          const int xi = lane + 32 * j;
+          if (x0 + xi < outW) o[(int64_t)t * outH * outW + xi] = S[xi];
+        }
+        __syncwarp();
+      }
+    }
+  }
+}
+
 }  // namespace
 }  // namespace vsr
 
@@ -114,6 +234,16 @@ extern "C" int vsr_correlation_forward(const float* input1, const float* input2,
   if (rc) return rc;
   const int R = max_displacement / stride2, D = 2 * R + 1;
   if (D > kMaxD) return VSR_ERR_UNSUPPORTED;
+  if (kernel_size == 1 && stride1 == 1 && stride2 == 2 && !getenv("VSR_CORR_GENERIC")) {   // FlowNetC's configuration
+    const int xtiles = ceil_div(ow, kCorrXT);
+    const int64_t tasks = (int64_t)B * oh * D * xtiles;
+    int64_t blocks = ceil_div64(tasks, kCorrWarps);
+    const int64_t cap = (int64_t)kNumSMs * 64;
+    if (blocks > cap) blocks = cap;
+    correlation_s2_kernel<<<(int)blocks, 32 * kCorrWarps, 0, as_stream(stream)>>>(
+        input1, input2, output, B, C, H, W, oh, ow, max_displacement - pad_size, R, D, xtiles);
+    return after_launch();
+  }
   const int segs = ceil_div(ow, 32);
   const int64_t n_tasks = (int64_t)B * oh * D * segs;
   int64_t blocks = ceil_div64(n_tasks, kThreads / 32);
