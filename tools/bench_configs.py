@@ -146,6 +146,41 @@ def run_c4(args):
                                                for k, v in prof.items() if v["launches"]}}), flush=True)
 
 
+def run_c2t3(args):
+    """C2's frame size with the REFERENCE's window: 480x270 -> 1920x1080, T = 3 (M = 8 maps, SRProjectionModule.py:127)."""
+    import torch
+    from video_super_resolution_b200 import synthetic as syn
+    from video_super_resolution_b200.my_packages.SRProjection.SRProjectionModule import SRProjectionModule
+    from video_super_resolution_b200.pipeline import WarpFusePipeline
+    rank, world, dev = setup()
+    _, tf = peaks()
+    T, h, w, s = 3, 270, 480, 4
+    M = 3 * T - 1
+    torch.manual_seed(0)
+    sr = gained(SRProjectionModule(num_maps=M))
+    pipe = WarpFusePipeline(T, h, w, sr, s, device=dev)
+    la, lb = syn.logits(h, w, seed=3 + rank)
+    inp = [syn.frames(T, h, w, seed=rank).to(dev), syn.smooth_flow(T - 1, h, w, 8.0, seed=1 + rank).to(dev),
+           syn.inv_depth(T - 1, h, w, seed=2 + rank).to(dev), la.to(dev), lb.to(dev)]
+    for _ in range(max(args.warmup, 3)):
+        pipe.step(*inp)
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        pipe.step(*inp)
+    e1.record()
+    barrier(world)
+    ms = max_over_ranks(e0.elapsed_time(e1) / args.steps, world, dev)
+    if rank == 0:
+        flops = 2 * M * h * w * 7.348e6
+        print(json.dumps({"config": "C2 frame size with the reference's 3-frame window (M=8): 4x VSR 480x270->1920x1080, "
+                                    "one window per GPU", "metric": "sr_frames_per_s_4x_1080p_out_T3", "unit": "frames/s",
+                          "n_gpus": world, "steps": args.steps, "value": world / (ms / 1e3), "ms_per_step": ms,
+                          "scaling": "weak", "tflops_per_step": flops / 1e12,
+                          "step_tensor_frac": flops / ms / 1e9 / tf}), flush=True)
+
+
 def run_c5(args):
     """300-frame 720x360 -> 2880x1440 (4x) sequence, T=3 windows (M=8), the reference's 20 chunks with the
     recurrence reset at chunk starts (main.py:196), sharded over the ranks; one NCCL gather of the u8 frames."""
@@ -216,15 +251,15 @@ def run_c5(args):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", required=True, choices=["c3", "c4", "c5"])
+    ap.add_argument("--config", required=True, choices=["c3", "c4", "c5", "c2t3"])
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--frames", type=int, default=300)
     ap.add_argument("--exact-chunks", action="store_true")
     args = ap.parse_args()
     if args.steps is None:
-        args.steps = {"c3": 20, "c4": 3, "c5": 1}[args.config]
-    {"c3": run_c3, "c4": run_c4, "c5": run_c5}[args.config](args)
+        args.steps = {"c3": 20, "c4": 3, "c5": 1, "c2t3": 10}[args.config]
+    {"c3": run_c3, "c4": run_c4, "c5": run_c5, "c2t3": run_c2t3}[args.config](args)
 
 
 if __name__ == "__main__":
