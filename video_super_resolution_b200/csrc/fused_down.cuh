@@ -55,7 +55,9 @@ struct alignas(64) FusedDownParams {
                                       // the TMEM reads + conversion of phase A, bit2 skip the final TMEM reads/stores,
                                       // bit3 skip phase-B MMAs
   const float* tran_bias;             // [32] biases + [1] PReLU slope of the downtran
-  float* part;                        // (B, h, w, 4 slots, 32) fp32 partial sums (see final epilogue)
+  const float* down_bias;             // [32] biases + [1] PReLU slope of the strided conv
+  float* part;                        // (B, h, w, 4 slots, 32) fp32 partial sums of the BOUNDARY pixels (see final epilogue)
+  void* lr_out;                       // (B, h, w, 32) bf16: finished interior pixels
 };
 
 __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
@@ -123,7 +125,8 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
   uint64_t* db_full = h_empty + 1;                             // [2]
   uint64_t* db_empty = db_full + 2;                            // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(db_empty + 2);
-  float* s_bias = reinterpret_cast<float*>(tail + 512);        // 33 floats
+  float* s_bias = reinterpret_cast<float*>(tail + 512);        // 33 floats: downtran bias + slope
+  float* s_down = s_bias + 36;                                 // 33 floats: strided-conv bias + slope
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -151,6 +154,7 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
   if (warp == 1) tmem_alloc<kTmemCols>(tmem_ptr);
   if (HAS_TRAN)
     for (int i = threadIdx.x; i < 33; i += kFusedThreads) s_bias[i] = p.tran_bias[i];
+  for (int i = threadIdx.x; i < 33; i += kFusedThreads) s_down[i] = p.down_bias[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -397,11 +401,17 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
         }
       }
       // final: channels [8*sub, 8*sub+8) of the four tap partials of D_B[tb].  Block (Yb,Xb)'s tap (dy,dx)
-      // belongs to LR pixel (Yb-dy, Xb-dx).  The dx=1 partial is handed to the left neighbour lane
-      // (same block row of the tile) by shuffle; what is left is written, without atomics, to a
-      // slot that has exactly one writer:  slot 2*dy   : tap (dy,0) + right neighbour's tap (dy,1)
-      //                                     slot 2*dy+1 : tap (dy,1) arriving from the next tile
-      //                                                   (only pixels with X % 16 == 15 have one)
+      // belongs to LR pixel (Yb-dy, Xb-dx).  The dx=1 partial is handed to the left neighbour lane (same block
+      // row of the tile) by shuffle, giving each lane the two row partials comb[dy] of pixels (Yb-dy, Xb).
+      //  * INTERIOR pixels -- even tile row, not the tile's last column: both row partials sit in this warp
+      //    (lanes 0-15 hold block row 2q, lanes 16-31 block row 2q+1), so lane l < 16 adds its comb[0] and lane
+      //    l+16's comb[1], applies bias + PReLU and stores the finished BF16 pixel: 64 bytes instead of two FP32
+      //    slot writes, a finalize read of both and its store.
+      //  * BOUNDARY pixels -- odd rows (their second partial lives in the next warp or the next tile) and
+      //    columns X % 16 == 15 (their dx=1 partials live in the next tile): written, without atomics, to slots
+      //    with exactly one writer each:  slot 2*dy   : tap (dy,0) + right neighbour's tap (dy,1)
+      //                                   slot 2*dy+1 : tap (dy,1) arriving from the next tile
+      //    finalize_lr_kernel sums them.  Same additions in the same order either way: deterministic.
       mbar_wait_sleep(&db_full[tb], m_b[tb] & 1, (uint32_t)(p.debug >> 8));
       tc_fence_after();
       if (p.debug & 4) {
@@ -414,22 +424,37 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive_warp(&db_empty[tb]);
-        const int xl = lane & 15;
+        const int xl = lane & 15, half = lane >> 4;
+        float comb[2][8];
 #pragma unroll
-        for (int dy = 0; dy < 2; ++dy) {
-          float comb[8];
+        for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             const float right = __uint_as_float(v[dy * 2 + 1][k]);
             const float from_right = __shfl_down_sync(0xffffffffu, right, 1);
-            comb[k] = __uint_as_float(v[dy * 2][k]) + (xl < 15 ? from_right : 0.0f);
+            comb[dy][k] = __uint_as_float(v[dy * 2][k]) + (xl < 15 ? from_right : 0.0f);
           }
+        float below[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) below[k] = __shfl_down_sync(0xffffffffu, comb[1][k], 16);
+        if (half == 0 && xl < 15 && in_tensor && Yb < p.lr_h && Xb < p.lr_w) {   // interior pixel (Yb, Xb): finish it
+          const float slope = s_down[32];
+          float r[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) r[k] = prelu(comb[0][k] + below[k] + s_down[sub * 8 + k], slope, 1);
+          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.lr_out) +
+                                                 ((((int64_t)b * p.lr_h + Yb) * p.lr_w + Xb) * 64 + sub * 16));
+          *dst = make_uint4(pack_bf16(r[0], r[1]), pack_bf16(r[2], r[3]), pack_bf16(r[4], r[5]), pack_bf16(r[6], r[7]));
+        }
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
           const int Y = Yb - dy;
           if (in_tensor && Y >= 0 && Y < p.lr_h) {
-            if (Xb < p.lr_w) {
+            const bool boundary = ((half ^ dy) == 1) || (xl == 15);        // odd row, or the tile's last column
+            if (Xb < p.lr_w && boundary) {
               float4* dst = reinterpret_cast<float4*>(p.part + ((((int64_t)b * p.lr_h + Y) * p.lr_w + Xb) * 4 + 2 * dy) * 32 + sub * 8);
-              dst[0] = make_float4(comb[0], comb[1], comb[2], comb[3]);
-              dst[1] = make_float4(comb[4], comb[5], comb[6], comb[7]);
+              dst[0] = make_float4(comb[dy][0], comb[dy][1], comb[dy][2], comb[dy][3]);
+              dst[1] = make_float4(comb[dy][4], comb[dy][5], comb[dy][6], comb[dy][7]);
             }
             if (xl == 0 && Xb > 0) {
               float4* dst = reinterpret_cast<float4*>(p.part + ((((int64_t)b * p.lr_h + Y) * p.lr_w + Xb - 1) * 4 + 2 * dy + 1) * 32 + sub * 8);
@@ -454,24 +479,26 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
   }
 }
 
+// Boundary pixels (odd rows, columns X % 16 == 15; see the fused kernel's final epilogue):
 // lr_out[p, c] = bf16(PReLU(sum of the pixel's partial slots + bias[c])).  8 channels per thread.
 // Deterministic: every slot has one writer, the sum order is fixed.
 __global__ void __launch_bounds__(256)
 finalize_lr_kernel(const float4* __restrict__ part, const float* __restrict__ bias, uint4* __restrict__ out, int64_t n8,
-                   int w) {
+                   int h, int w) {
   const float slope = __ldg(bias + 32);
-  // (no early griddepcontrol.launch_dependents: dependents are released as CTAs exit)
   griddep_wait();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t px = i >> 2;
     const int c8 = (int)(i & 3);
-    const int X = (int)(px % w);
+    const int X = (int)(px % w), Y = (int)((px / w) % h);
+    const bool last_col = (X & 15) == 15;
+    if (!((Y & 1) || last_col)) continue;                // interior: finished by the fused kernel
     const float4* base = part + px * 32 + c8 * 2;          // 32 float4 per pixel, 8 per slot
     float4 a0 = base[0], a1 = base[1];
     const float4 b0 = base[16], b1 = base[17];
     a0 = make_float4(a0.x + b0.x, a0.y + b0.y, a0.z + b0.z, a0.w + b0.w);
     a1 = make_float4(a1.x + b1.x, a1.y + b1.y, a1.z + b1.z, a1.w + b1.w);
-    if ((X & 15) == 15) {
+    if (last_col) {
       const float4 c0 = base[8], c1 = base[9], d0 = base[24], d1 = base[25];
       a0 = make_float4(a0.x + (c0.x + d0.x), a0.y + (c0.y + d0.y), a0.z + (c0.z + d0.z), a0.w + (c0.w + d0.w));
       a1 = make_float4(a1.x + (c1.x + d1.x), a1.y + (c1.y + d1.y), a1.z + (c1.z + d1.z), a1.w + (c1.w + d1.w));

@@ -103,7 +103,7 @@ struct Layer {
   const float* fin_bias;
   void* fin_out;
   int64_t fin_n8;
-  int fin_w;
+  int fin_w, fin_h;
   int grid;
   size_t smem;
   int kclass;
@@ -148,7 +148,7 @@ int launch_layer(const Layer& L, cudaStream_t st) {
       int64_t blocks = ceil_div64(L.fin_n8, 256);
       if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
       cudaError_t e = launch_pdl(finalize_lr_kernel, (int)blocks, 256, 0, st, reinterpret_cast<const float4*>(L.fin_acc),
-                                 L.fin_bias, reinterpret_cast<uint4*>(L.fin_out), L.fin_n8, L.fin_w);
+                                 L.fin_bias, reinterpret_cast<uint4*>(L.fin_out), L.fin_n8, L.fin_h, L.fin_w);
       if (e != cudaSuccess) return cuda_status(e);
       return after_launch();
     }
@@ -430,7 +430,8 @@ int build_downconv2(Layer& L, const void* xhr, int B, int h, int w, const void* 
 // downtran (1x1 over hr[0..nsrc-1], nsrc >= 2) + PReLU + Conv2d(32,32,8,4,2) pre-activation sums -> acc;
 // nsrc == 1: the conv alone on hr[0].  hr[j]: HR block layout (B,h+1,w+1,16,32); acc (B,h,w,32) fp32.
 int build_fused_down(Layer& L, const void* const* hr, int nsrc, int B, int h, int w, const void* wt_dev,
-                     const float* tran_bias_dev, const void* wd_dev, float* part) {
+                     const float* tran_bias_dev, const void* wd_dev, const float* down_bias_dev, float* part,
+                     void* lr_out) {
   memset(&L, 0, sizeof(L));
   const bool tran = nsrc > 1;
   L.variant = tran ? V_FUSED_TRAN : V_FUSED_PLAIN;
@@ -470,7 +471,9 @@ int build_fused_down(Layer& L, const void* const* hr, int nsrc, int B, int h, in
     if (e && atoi(e) > 0 && atoi(e) <= (tran ? 7 : 5)) f.num_stages = atoi(e);
   }
   f.tran_bias = tran_bias_dev;
+  f.down_bias = down_bias_dev;
   f.part = part;
+  f.lr_out = lr_out;
   {
     // measured on B200 (C2 shape, nsrc = 6): weights resident + 3 x 16 KB activation stages 3.73 ms,
     // weights streamed per group from L2 + 7 stages 3.22 ms -> streaming is the default
@@ -488,11 +491,11 @@ int build_fused_down(Layer& L, const void* const* hr, int nsrc, int B, int h, in
   const double lrpx = (double)B * h * w;
   L.kclass = KC_FUSED_DOWN;
   L.flops = lrpx * 131072.0 + (tran ? lrpx * 16.0 * 2.0 * 32.0 * nsrc * 32.0 : 0.0);
-  L.bytes = lrpx * 64.0 * (16.0 * nsrc) + lrpx * 272.0;
+  L.bytes = lrpx * 64.0 * (16.0 * nsrc) + lrpx * 64.0;   // HR maps in, one BF16 LR map out (slots are not compulsory)
   return VSR_OK;
 }
 
-int build_finalize(Layer& L, float* acc, const float* bias_dev, void* out, int64_t pixels, int w) {
+int build_finalize(Layer& L, float* acc, const float* bias_dev, void* out, int64_t pixels, int h, int w) {
   memset(&L, 0, sizeof(L));
   L.variant = V_FINALIZE;
   L.fin_acc = acc;
@@ -500,9 +503,10 @@ int build_finalize(Layer& L, float* acc, const float* bias_dev, void* out, int64
   L.fin_out = out;
   L.fin_n8 = pixels * 4;
   L.fin_w = w;
+  L.fin_h = h;
   L.kclass = KC_FINALIZE;
   L.flops = 0;
-  L.bytes = (double)pixels * (272.0 + 64.0);
+  L.bytes = 0;   // the boundary-pixel pass moves no compulsory bytes (its pixels' output is counted in the fused launch)
   return VSR_OK;
 }
 
@@ -983,9 +987,9 @@ extern "C" int vsr_srfbn_bind(vsr_srfbn_plan* pl, const void* dev_weights, void*
         const void* hrs[6];
         for (int j = 0; j <= i; ++j) hrs[j] = ws + pl->o_hr[j];
         PUSH(build_fused_down(L, hrs, i + 1, M, h, w, i > 0 ? Wp(W_DOWNTRAN0 + i - 1) : nullptr,
-                              i > 0 ? Bp(W_DOWNTRAN0 + i - 1) : nullptr, Wp(W_DOWN0 + i),
-                              reinterpret_cast<float*>(ws + pl->o_acc)));
-        PUSH(build_finalize(L, reinterpret_cast<float*>(ws + pl->o_acc), Bp(W_DOWN0 + i), ws + pl->o_lr[i + 1], P, w));
+                              i > 0 ? Bp(W_DOWNTRAN0 + i - 1) : nullptr, Wp(W_DOWN0 + i), Bp(W_DOWN0 + i),
+                              reinterpret_cast<float*>(ws + pl->o_acc), ws + pl->o_lr[i + 1]));
+        PUSH(build_finalize(L, reinterpret_cast<float*>(ws + pl->o_acc), Bp(W_DOWN0 + i), ws + pl->o_lr[i + 1], P, h, w));
       }
     }
     {  // compress_out(cat(lr[1..6])) -> hidden
@@ -1216,11 +1220,12 @@ extern "C" int vsr_test_fused_down(const void* hr_bf16, int nsrc, int B, int h, 
   const size_t plane = (size_t)B * (h + 1) * (w + 1) * 16 * 64;
   for (int j = 0; j < nsrc; ++j) hrs[j] = reinterpret_cast<const uint8_t*>(hr_bf16) + j * plane;
   Layer L;
-  rc = build_fused_down(L, hrs, nsrc, B, h, w, ws + 160 * 1024, reinterpret_cast<const float*>(ws + 257 * 1024), ws, acc);
+  rc = build_fused_down(L, hrs, nsrc, B, h, w, ws + 160 * 1024, reinterpret_cast<const float*>(ws + 257 * 1024), ws,
+                        reinterpret_cast<const float*>(ws + 256 * 1024), acc, y_bf16);
   if (rc) return rc;
   rc = launch_layer(L, st);
   if (rc) return rc;
-  rc = build_finalize(L, acc, reinterpret_cast<const float*>(ws + 256 * 1024), y_bf16, (int64_t)B * h * w, w);
+  rc = build_finalize(L, acc, reinterpret_cast<const float*>(ws + 256 * 1024), y_bf16, (int64_t)B * h * w, h, w);
   if (rc) return rc;
   rc = launch_layer(L, st);
   if (rc) return rc;
