@@ -39,6 +39,7 @@ constexpr int kWdGroupBytes = 128 * 128 * 2; // 8x8-s4 weights of one sub-positi
 constexpr int kWdRingBytes = 2 * kWdGroupBytes;  // streamed per group from L2 through a 2-deep ring
 constexpr int kWtChunkBytes = 32 * 32 * 2;   // one 32x32 downtran slice (64-byte rows, 64B swizzle)
 constexpr int kHBytes = 128 * 128 * 2;       // phase-B A operand of one sub-position group
+constexpr int kXchgBytes = 3 * 4 * 16 * 8 * 4;   // row partials handed from lane quarter q+1 to q: [3][4 subs][16 px][8 ch] fp32
 
 struct alignas(64) FusedDownParams {
   CUtensorMap hr_maps[kMaxSources];   // HAS_TRAN: 4-D (64, w+1, h+1, 8*B) pair planes, box (64,16,8,1) = 2 sub-positions, 128B swizzle
@@ -58,6 +59,8 @@ struct alignas(64) FusedDownParams {
   const float* down_bias;             // [32] biases + [1] PReLU slope of the strided conv
   float* part;                        // (B, h, w, 4 slots, 32) fp32 partial sums of the BOUNDARY pixels (see final epilogue)
   void* lr_out;                       // (B, h, w, 32) bf16: finished interior pixels
+  int32_t xchg;                       // 1: tile rows 1,3,5 are finished too (row partials exchanged between lane quarters
+                                      // through shared memory); 0: only the even tile rows
 };
 
 __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
@@ -91,11 +94,11 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
 }
 
 template <bool HAS_TRAN>
-inline size_t fused_down_smem_bytes(int nsrc, int num_stages, int wd_resident) {
+inline size_t fused_down_smem_bytes(int nsrc, int num_stages, int wd_resident, int xchg) {
   size_t wt = HAS_TRAN ? ((size_t)nsrc * kWtChunkBytes + 1023) / 1024 * 1024 : 0;
   size_t stage = HAS_TRAN ? 16384 : 2 * 16384;
   return 1024 + (wd_resident ? 4 * kWdGroupBytes : kWdRingBytes) + wt + (HAS_TRAN ? kHBytes : 0) +
-         (size_t)num_stages * stage + 1024;
+         (size_t)num_stages * stage + 1024 + (xchg ? kXchgBytes : 0);
 }
 
 template <bool HAS_TRAN>
@@ -127,6 +130,7 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(db_empty + 2);
   float* s_bias = reinterpret_cast<float*>(tail + 512);        // 33 floats: downtran bias + slope
   float* s_down = s_bias + 36;                                 // 33 floats: strided-conv bias + slope
+  float4* s_x = reinterpret_cast<float4*>(tail + 1024);        // kXchgBytes: final-epilogue row exchange
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -403,12 +407,12 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
       // final: channels [8*sub, 8*sub+8) of the four tap partials of D_B[tb].  Block (Yb,Xb)'s tap (dy,dx)
       // belongs to LR pixel (Yb-dy, Xb-dx).  The dx=1 partial is handed to the left neighbour lane (same block
       // row of the tile) by shuffle, giving each lane the two row partials comb[dy] of pixels (Yb-dy, Xb).
-      //  * INTERIOR pixels -- even tile row, not the tile's last column: both row partials sit in this warp
-      //    (lanes 0-15 hold block row 2q, lanes 16-31 block row 2q+1), so lane l < 16 adds its comb[0] and lane
-      //    l+16's comb[1], applies bias + PReLU and stores the finished BF16 pixel: 64 bytes instead of two FP32
-      //    slot writes, a finalize read of both and its store.
-      //  * BOUNDARY pixels -- odd rows (their second partial lives in the next warp or the next tile) and
-      //    columns X % 16 == 15 (their dx=1 partials live in the next tile): written, without atomics, to slots
+      //  * INTERIOR pixels -- tile rows 0..6, not the tile's last column: the second row partial is lane + 16's
+      //    (lanes 0-15 hold block row 2q, lanes 16-31 block row 2q+1) or comes from the next lane quarter through a
+      //    6 KB shared-memory exchange; the lane adds it to its comb[0], applies bias + PReLU and stores the
+      //    finished BF16 pixel: 64 bytes instead of two FP32 slot writes, a finalize read of both and its store.
+      //  * BOUNDARY pixels -- tile row 7 (its second partial lives in the next tile) and columns X % 16 == 15
+      //    (their dx=1 partials live in the next tile), 18 % of the pixels: written, without atomics, to slots
       //    with exactly one writer each:  slot 2*dy   : tap (dy,0) + right neighbour's tap (dy,1)
       //                                   slot 2*dy+1 : tap (dy,1) arriving from the next tile
       //    finalize_lr_kernel sums them.  Same additions in the same order either way: deterministic.
@@ -434,10 +438,26 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
             const float from_right = __shfl_down_sync(0xffffffffu, right, 1);
             comb[dy][k] = __uint_as_float(v[dy * 2][k]) + (xl < 15 ? from_right : 0.0f);
           }
+        // second row partial of this lane's pixel (Yb, Xb): block row Yb+1's comb[1].  Even tile rows: lane + 16 of
+        // this warp.  Odd tile rows 1, 3, 5: lanes 0-15 of the next lane quarter, through shared memory.
         float below[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) below[k] = __shfl_down_sync(0xffffffffu, comb[1][k], 16);
-        if (half == 0 && xl < 15 && in_tensor && Yb < p.lr_h && Xb < p.lr_w) {   // interior pixel (Yb, Xb): finish it
+        if (p.xchg && half == 0 && q > 0) {
+          float4* x = s_x + (((q - 1) * 4 + sub) * 16 + xl) * 2;
+          x[0] = make_float4(comb[1][0], comb[1][1], comb[1][2], comb[1][3]);
+          x[1] = make_float4(comb[1][4], comb[1][5], comb[1][6], comb[1][7]);
+        }
+        if (p.xchg) asm volatile("bar.sync 1, %0;" ::"n"(32 * kFusedEpiWarps) : "memory");     // the 16 epilogue warps only
+        if (p.xchg && half == 1 && q < 3) {
+          const float4* x = s_x + ((q * 4 + sub) * 16 + xl) * 2;
+          const float4 x0v = x[0], x1v = x[1];
+          below[0] = x0v.x; below[1] = x0v.y; below[2] = x0v.z; below[3] = x0v.w;
+          below[4] = x1v.x; below[5] = x1v.y; below[6] = x1v.z; below[7] = x1v.w;
+        }
+        if (p.xchg) asm volatile("bar.sync 1, %0;" ::"n"(32 * kFusedEpiWarps) : "memory");     // reads done before the next tile's writes
+        const int rr = 2 * q + half;                                               // block row inside the tile
+        if ((p.xchg ? rr < 7 : half == 0) && xl < 15 && in_tensor && Yb < p.lr_h && Xb < p.lr_w) {   // interior pixel (Yb, Xb)
           const float slope = s_down[32];
           float r[8];
 #pragma unroll
@@ -450,7 +470,8 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
         for (int dy = 0; dy < 2; ++dy) {
           const int Y = Yb - dy;
           if (in_tensor && Y >= 0 && Y < p.lr_h) {
-            const bool boundary = ((half ^ dy) == 1) || (xl == 15);        // odd row, or the tile's last column
+            // row 7 of a tile (without the exchange: every odd row), or the tile's last column
+            const bool boundary = (p.xchg ? (((rr - dy) & 7) == 7) : (((rr - dy) & 1) == 1)) || (xl == 15);
             if (Xb < p.lr_w && boundary) {
               float4* dst = reinterpret_cast<float4*>(p.part + ((((int64_t)b * p.lr_h + Y) * p.lr_w + Xb) * 4 + 2 * dy) * 32 + sub * 8);
               dst[0] = make_float4(comb[dy][0], comb[dy][1], comb[dy][2], comb[dy][3]);
@@ -479,12 +500,13 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
   }
 }
 
-// Boundary pixels (odd rows, columns X % 16 == 15; see the fused kernel's final epilogue):
+// Boundary pixels (rows Y % 8 == 7 -- row_mask 7; odd rows without the exchange -- row_mask 1; columns X % 16 == 15;
+// see the fused kernel's final epilogue):
 // lr_out[p, c] = bf16(PReLU(sum of the pixel's partial slots + bias[c])).  8 channels per thread.
 // Deterministic: every slot has one writer, the sum order is fixed.
 __global__ void __launch_bounds__(256)
 finalize_lr_kernel(const float4* __restrict__ part, const float* __restrict__ bias, uint4* __restrict__ out, int64_t n8,
-                   int h, int w) {
+                   int h, int w, int row_mask) {
   const float slope = __ldg(bias + 32);
   griddep_wait();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
@@ -492,7 +514,7 @@ finalize_lr_kernel(const float4* __restrict__ part, const float* __restrict__ bi
     const int c8 = (int)(i & 3);
     const int X = (int)(px % w), Y = (int)((px / w) % h);
     const bool last_col = (X & 15) == 15;
-    if (!((Y & 1) || last_col)) continue;                // interior: finished by the fused kernel
+    if (!((Y & row_mask) == row_mask || last_col)) continue;   // interior: finished by the fused kernel
     const float4* base = part + px * 32 + c8 * 2;          // 32 float4 per pixel, 8 per slot
     float4 a0 = base[0], a1 = base[1];
     const float4 b0 = base[16], b1 = base[17];

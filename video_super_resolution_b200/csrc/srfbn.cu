@@ -111,6 +111,11 @@ struct Layer {
   double bytes;   // compulsory HBM bytes of this launch: its inputs + outputs, each once
 };
 
+int fused_xchg() {   // tuning knob, see FusedDownParams::xchg
+  const char* e = getenv("VSR_FUSED_XCHG");
+  return e ? (atoi(e) != 0) : 1;
+}
+
 template <int MODE, int CK, int BN>
 int launch_variant(const Layer& L, cudaStream_t st) {
   static bool attr_set = false;   // per process; the attribute is sticky per function
@@ -148,7 +153,8 @@ int launch_layer(const Layer& L, cudaStream_t st) {
       int64_t blocks = ceil_div64(L.fin_n8, 256);
       if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
       cudaError_t e = launch_pdl(finalize_lr_kernel, (int)blocks, 256, 0, st, reinterpret_cast<const float4*>(L.fin_acc),
-                                 L.fin_bias, reinterpret_cast<uint4*>(L.fin_out), L.fin_n8, L.fin_h, L.fin_w);
+                                 L.fin_bias, reinterpret_cast<uint4*>(L.fin_out), L.fin_n8, L.fin_h, L.fin_w,
+                                 fused_xchg() ? 7 : 1);
       if (e != cudaSuccess) return cuda_status(e);
       return after_launch();
     }
@@ -470,6 +476,7 @@ int build_fused_down(Layer& L, const void* const* hr, int nsrc, int B, int h, in
     const char* e = getenv("VSR_FUSED_STAGES");
     if (e && atoi(e) > 0 && atoi(e) <= (tran ? 7 : 5)) f.num_stages = atoi(e);
   }
+  f.xchg = fused_xchg();
   f.tran_bias = tran_bias_dev;
   f.down_bias = down_bias_dev;
   f.part = part;
@@ -481,11 +488,11 @@ int build_fused_down(Layer& L, const void* const* hr, int nsrc, int B, int h, in
     f.wd_resident = e ? atoi(e) : 0;
     if (f.wd_resident) f.num_stages = tran ? 3 : 2;
   }
-  while (f.num_stages > 2 && (tran ? fused_down_smem_bytes<true>(nsrc, f.num_stages, f.wd_resident)
-                                   : fused_down_smem_bytes<false>(nsrc, f.num_stages, f.wd_resident)) > 227 * 1024)
+  while (f.num_stages > 2 && (tran ? fused_down_smem_bytes<true>(nsrc, f.num_stages, f.wd_resident, f.xchg)
+                                   : fused_down_smem_bytes<false>(nsrc, f.num_stages, f.wd_resident, f.xchg)) > 227 * 1024)
     --f.num_stages;
-  L.smem = tran ? fused_down_smem_bytes<true>(nsrc, f.num_stages, f.wd_resident)
-                : fused_down_smem_bytes<false>(nsrc, f.num_stages, f.wd_resident);
+  L.smem = tran ? fused_down_smem_bytes<true>(nsrc, f.num_stages, f.wd_resident, f.xchg)
+                : fused_down_smem_bytes<false>(nsrc, f.num_stages, f.wd_resident, f.xchg);
   int64_t total = (int64_t)f.tiles_x * f.tiles_y * B;
   L.grid = (int)(total < kNumSMs ? total : kNumSMs);
   const double lrpx = (double)B * h * w;
