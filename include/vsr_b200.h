@@ -106,6 +106,15 @@ int vsr_correlation_output_shape(int C, int H, int W, int pad_size, int kernel_s
 int vsr_correlation_forward(const float* input1, const float* input2, float* output, int B, int C, int H, int W,
                             int pad_size, int kernel_size, int max_displacement, int stride1, int stride2,
                             int corr_multiply, vsr_stream_t stream);
+/* Backward of the cost volume (completes CorrelationFunction, correlation.py:32-47): replaces
+ * correlation_cuda.backward = correlation_backward_cuda(input1, input2, rInput1, rInput2, gradOutput, gradInput1,
+ * gradInput2, ...) correlation_cuda.cc:89-166 -> correlation_cuda_kernel.cu:148-333.  grad_output (B, D*D, outH, outW),
+ * grad_input1/2 (B,C,H,W), all f32; every element of the gradients is written (no pre-zeroing needed).  stride1 must
+ * be 1 (VSR_ERR_UNSUPPORTED otherwise: the reference's kernels write out of bounds for stride1 > 1). */
+int vsr_correlation_backward(const float* input1, const float* input2, const float* grad_output,
+                             float* grad_input1, float* grad_input2, int B, int C, int H, int W, int pad_size,
+                             int kernel_size, int max_displacement, int stride1, int stride2, int corr_multiply,
+                             vsr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * a1 / a2: flow projection (forward splat + count + normalise + hole fill), SURVEY.md App. B.

@@ -56,6 +56,8 @@ def lib():
         _lib.or_channelnorm_backward.restype = None
         _lib.or_correlation.argtypes = [_f32p] * 3 + [I] * 11
         _lib.or_correlation.restype = None
+        _lib.or_correlation_backward.argtypes = [_f32p] * 3 + [I] * 11
+        _lib.or_correlation_backward.restype = None
         _lib.or_flow2img.argtypes = [_f32p, _u8p, I, I]
         _lib.or_flow2img.restype = None
         _lib.or_resize_nearest_planar.argtypes = [_u8p, _f32p, I, I, I, I]
@@ -302,3 +304,16 @@ def resize_nearest_planar(img, H, W):
     out = np.empty((3, H, W), np.float32)
     lib().or_resize_nearest_planar(_p(img, _u8p), _p(out, _f32p), h, w, H, W)
     return out
+
+
+def correlation_backward(input1, input2, grad_output, pad_size, kernel_size, max_displacement, stride2):
+    """correlation_cuda.backward with stride1 = 1 (correlation_cuda_kernel.cu:148-333): (grad_input1, grad_input2)."""
+    a, b, g = _c(input1, np.float32), _c(input2, np.float32), _c(grad_output, np.float32)
+    B, C, H, W = a.shape
+    oh, ow = g.shape[2], g.shape[3]
+    g1, g2 = np.empty_like(a), np.empty_like(a)
+    lib().or_correlation_backward(_p(b, _f32p), _p(g, _f32p), _p(g1, _f32p), 0, B, C, H, W, pad_size, kernel_size,
+                                  max_displacement, stride2, oh, ow)
+    lib().or_correlation_backward(_p(a, _f32p), _p(g, _f32p), _p(g2, _f32p), 1, B, C, H, W, pad_size, kernel_size,
+                                  max_displacement, stride2, oh, ow)
+    return g1, g2

@@ -162,3 +162,51 @@ def test_correlation_register_tiled_path_is_bit_identical_to_generic_kernel(monk
         slow = ops.correlation(a, b, pad, 1, md, 1, 2, 1)
         assert torch.equal(fast, slow)
         assert fast.abs().max().item() > 0
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(shape=(1, 8, 24, 40), pad=20, k=1, md=20, s2=2),          # FlowNetC geometry (FlowNetC.py:22)
+    dict(shape=(2, 5, 13, 21), pad=8, k=1, md=8, s2=2),
+    dict(shape=(1, 6, 20, 28), pad=5, k=3, md=4, s2=1),            # 3x3 kernel window: sums over up to 9 outputs
+])
+def test_reference_correlation_backward_equals_oracle_and_product(cfg):
+    """correlation_cuda.backward of the reference binary (correlation_cuda_kernel.cu:148-333) vs oracle vs product,
+    stride1 = 1; fp32 summation order differs between the three, so compare to 1e-5 relative."""
+    ref = _ref("correlation_cuda")
+    g = torch.Generator().manual_seed(cfg["shape"][1] + cfg["md"])
+    a = torch.randn(cfg["shape"], generator=g).to(DEV)
+    b = torch.randn(cfg["shape"], generator=g).to(DEV)
+    out = ops.correlation(a, b, cfg["pad"], cfg["k"], cfg["md"], 1, cfg["s2"], 1)
+    go = torch.randn(out.shape, generator=g).to(DEV)
+    r1, r2, g1, g2 = a.new_empty(0), a.new_empty(0), a.new_empty(0), a.new_empty(0)      # correlation.py:37-42
+    ref.backward(a, b, r1, r2, go, g1, g2, cfg["pad"], cfg["k"], cfg["md"], 1, cfg["s2"], 1)
+    torch.cuda.synchronize()
+    got1, got2 = ops.correlation_backward(a, b, go, cfg["pad"], cfg["k"], cfg["md"], 1, cfg["s2"], 1)
+    o1, o2 = orc.correlation_backward(a.cpu().numpy(), b.cpu().numpy(), go.cpu().numpy(), cfg["pad"], cfg["k"], cfg["md"], cfg["s2"])
+    for want, got, o in ((g1, got1, o1), (g2, got2, o2)):
+        w = want.cpu().numpy()
+        tol = 1e-5 * max(1.0, float(np.abs(w).max()))
+        assert np.abs(w).max() > 0
+        assert np.abs(got.cpu().numpy() - w).max() <= tol
+        assert np.abs(o - w).max() <= tol
+
+
+def test_correlation_function_autograd():
+    """CorrelationFunction.backward through autograd against a finite difference of the forward."""
+    from video_super_resolution_b200.my_packages.FlowProjection.networks.correlation_package.correlation import Correlation
+    g = torch.Generator().manual_seed(3)
+    a = torch.randn((1, 4, 12, 16), generator=g).to(DEV).requires_grad_(True)
+    b = torch.randn((1, 4, 12, 16), generator=g).to(DEV).requires_grad_(True)
+    corr = Correlation(pad_size=4, kernel_size=1, max_displacement=4, stride1=1, stride2=2)
+    w = torch.randn(corr(a, b).shape, generator=g).to(DEV)
+    (corr(a, b) * w).sum().backward()
+    eps = 1e-2
+    with torch.no_grad():
+        for t, grad in ((a, a.grad), (b, b.grad)):
+            base = (corr(a, b) * w).sum()
+            t[0, 2, 5, 7] += eps
+            num = ((corr(a, b) * w).sum() - base) / eps
+            t[0, 2, 5, 7] -= eps
+            assert abs(num.item() - grad[0, 2, 5, 7].item()) <= 2e-2 * max(1.0, abs(num.item()))
+    with pytest.raises(RuntimeError):
+        ops.correlation_backward(a.detach(), b.detach(), w, 4, 1, 4, 2, 2, 1)          # stride1 != 1: unsupported

@@ -202,6 +202,58 @@ correlation_s2_kernel(const float* __restrict__ in1, const float* __restrict__ i
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Backward (completes the CorrelationFunction surface; correlation_cuda_kernel.cu:148-333, stride1 = 1 -- for
+// stride1 > 1 the reference writes gradInput out of bounds).  One thread per input element (n, c, Y, X), X fastest:
+//   gradInput1[n,c,Y,X] = 1/(k*k*C) * sum_tc in2[n,c,Y + j2, X + i2] * sum_window gradOutput[n,tc,.,.]
+//   gradInput2[n,c,Y,X] = 1/(k*k*C) * sum_tc in1[n,c,Y - j2, X - i2] * sum_{window shifted by (j2,i2)} gradOutput[n,tc,.,.]
+// the window being the outputs whose kernel footprint covers the pixel (one output for kernel_size 1).  Both the
+// gradOutput and the shifted-image loads are coalesced along X.  fp32 FMA chain over tc in order (the reference
+// sums 32 strided partials and reduces them: equal to fp32 rounding, not bit for bit).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+correlation_backward_kernel(const float* __restrict__ other, const float* __restrict__ gout, float* __restrict__ gin,
+                            int which, int B, int C, int H, int W, int outH, int outW, int pad, int ksize, int maxdisp,
+                            int s2, int R, int D) {
+  const int64_t HW = (int64_t)H * W, OHW = (int64_t)outH * outW;
+  const int64_t total = (int64_t)B * C * HW;
+  const int krad = (ksize - 1) / 2;
+  const float nelems = (float)(ksize * ksize * C);
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int X = (int)(idx % W);
+    const int Y = (int)((idx / W) % H);
+    const int64_t nc = idx / HW;
+    const int n = (int)(nc / C);
+    const int y = Y + pad, x = X + pad;
+    const float* img = other + nc * HW;
+    const float* g = gout + (int64_t)n * D * D * OHW;
+    float acc = 0.0f;
+    for (int tj = 0; tj < D; ++tj) {
+      const int j2 = (tj - R) * s2;
+      const int oy = (which ? y - j2 : y + j2) - pad;
+      if (oy < 0 || oy >= H) continue;                       // the other image's row is zero padding
+      int ymin = y - krad - maxdisp - (which ? j2 : 0), ymax = ymin + 2 * krad;
+      if (ymax < 0 || ymin >= outH) continue;
+      ymin = max(ymin, 0);
+      ymax = min(ymax, outH - 1);
+      for (int ti = 0; ti < D; ++ti) {
+        const int i2 = (ti - R) * s2;
+        const int ox = (which ? x - i2 : x + i2) - pad;
+        int xmin = x - krad - maxdisp - (which ? i2 : 0), xmax = xmin + 2 * krad;
+        if (ox < 0 || ox >= W || xmax < 0 || xmin >= outW) continue;
+        xmin = max(xmin, 0);
+        xmax = min(xmax, outW - 1);
+        const float val = __ldg(img + (int64_t)oy * W + ox);
+        const float* gt = g + (int64_t)(tj * D + ti) * OHW;
+        for (int j = ymin; j <= ymax; ++j)
+          for (int i = xmin; i <= xmax; ++i) acc = fmaf(__ldg(gt + (int64_t)j * outW + i), val, acc);
+      }
+    }
+    gin[idx] = __fdiv_rn(acc, nelems);
+  }
+}
+
 }  // namespace
 }  // namespace vsr
 
@@ -252,5 +304,30 @@ extern "C" int vsr_correlation_forward(const float* input1, const float* input2,
   correlation_forward_kernel<<<(int)blocks, kThreads, 0, as_stream(stream)>>>(input1, input2, output, B, C, H, W, oh, ow,
                                                                              pad_size, kernel_size, max_displacement,
                                                                              stride1, stride2, R, D, segs);
+  return after_launch();
+}
+
+extern "C" int vsr_correlation_backward(const float* input1, const float* input2, const float* grad_output,
+                                        float* grad_input1, float* grad_input2, int B, int C, int H, int W, int pad_size,
+                                        int kernel_size, int max_displacement, int stride1, int stride2, int corr_multiply,
+                                        vsr_stream_t stream) {
+  (void)corr_multiply;
+  if (!input1 || !input2 || !grad_output || !grad_input1 || !grad_input2 || B <= 0 || C <= 0) return VSR_ERR_INVALID_ARG;
+  if (stride1 != 1) return VSR_ERR_UNSUPPORTED;   // the reference's backward indexes out of bounds for stride1 > 1
+  int oc, oh, ow;
+  int rc = vsr_correlation_output_shape(C, H, W, pad_size, kernel_size, max_displacement, stride1, stride2, &oc, &oh, &ow);
+  if (rc) return rc;
+  const int R = max_displacement / stride2, D = 2 * R + 1;
+  const int64_t total = (int64_t)B * C * H * W;
+  int64_t blocks = ceil_div64(total, kThreads);
+  const int64_t cap = (int64_t)kNumSMs * 8 * 8;
+  if (blocks > cap) blocks = cap;
+  cudaStream_t st = as_stream(stream);
+  correlation_backward_kernel<<<(int)blocks, kThreads, 0, st>>>(input2, grad_output, grad_input1, 0, B, C, H, W, oh, ow,
+                                                               pad_size, kernel_size, max_displacement, stride2, R, D);
+  rc = after_launch();
+  if (rc) return rc;
+  correlation_backward_kernel<<<(int)blocks, kThreads, 0, st>>>(input1, grad_output, grad_input2, 1, B, C, H, W, oh, ow,
+                                                               pad_size, kernel_size, max_displacement, stride2, R, D);
   return after_launch();
 }

@@ -5,8 +5,8 @@
                               stride1=1, stride2=2, corr_multiply=1)
     Correlation(pad_size=0, kernel_size=0, max_displacement=0, stride1=1, stride2=2, corr_multiply=1)
 
-FlowNetC uses pad 20, kernel 1, max_displacement 20, strides 1 / 2 (FlowNetC.py:22).  Forward only:
-the backward of the cost volume is not built."""
+FlowNetC uses pad 20, kernel 1, max_displacement 20, strides 1 / 2 (FlowNetC.py:22).  Backward
+(correlation.py:32-47) is built for stride1 = 1, the only case in which the reference's own kernels stay in bounds."""
 from torch.autograd import Function
 from torch.nn.modules.module import Module
 
@@ -17,12 +17,16 @@ class CorrelationFunction(Function):
     @staticmethod
     def forward(ctx, input1, input2, pad_size=3, kernel_size=3, max_displacement=20, stride1=1, stride2=2,
                 corr_multiply=1):
-        return ops.correlation(input1.contiguous(), input2.contiguous(), pad_size, kernel_size, max_displacement,
-                               stride1, stride2, corr_multiply)
+        input1, input2 = input1.contiguous(), input2.contiguous()
+        ctx.save_for_backward(input1, input2)
+        ctx.cfg = (pad_size, kernel_size, max_displacement, stride1, stride2, corr_multiply)
+        return ops.correlation(input1, input2, pad_size, kernel_size, max_displacement, stride1, stride2, corr_multiply)
 
     @staticmethod
     def backward(ctx, grad_output):
-        raise NotImplementedError("Correlation backward is not built (SURVEY.md 8f)")
+        input1, input2 = ctx.saved_tensors
+        g1, g2 = ops.correlation_backward(input1, input2, grad_output.contiguous(), *ctx.cfg)
+        return g1, g2, None, None, None, None, None, None
 
 
 class Correlation(Module):

@@ -108,6 +108,25 @@ def correlation(input1: torch.Tensor, input2: torch.Tensor, pad_size: int = 3, k
     return out
 
 
+def correlation_backward(input1: torch.Tensor, input2: torch.Tensor, grad_output: torch.Tensor, pad_size: int = 3,
+                         kernel_size: int = 3, max_displacement: int = 20, stride1: int = 1, stride2: int = 2,
+                         corr_multiply: int = 1):
+    """(grad_input1, grad_input2) of the cost volume.  ref: CorrelationFunction.backward (correlation.py:32-47)."""
+    _req(input1, torch.float32, "input1")
+    _req(input2, torch.float32, "input2")
+    _req(grad_output, torch.float32, "grad_output")
+    if input1.shape != input2.shape or input1.dim() != 4:
+        raise ValueError("correlation_backward: two (B,C,H,W) tensors of the same shape expected")
+    B, C, H, W = input1.shape
+    g1, g2 = torch.empty_like(input1), torch.empty_like(input2)
+    with torch.cuda.device(input1.device):
+        _lib.check(_lib.lib().vsr_correlation_backward(input1.data_ptr(), input2.data_ptr(), grad_output.data_ptr(),
+                                                       g1.data_ptr(), g2.data_ptr(), B, C, H, W, pad_size, kernel_size,
+                                                       max_displacement, stride1, stride2, corr_multiply, _stream()),
+                   "correlation_backward")
+    return g1, g2
+
+
 def warp(src: torch.Tensor, flow: torch.Tensor, bilinear: bool | int = True, ref: torch.Tensor | None = None):
     """Channels-last warp: src (B,H,W,C), flow (B,H,W,2) -> (B,H,W,C).  With `ref` (B,H,W,C) also
     returns the per-pixel L2 norm of (ref - warped), (B,H,W) (models.py:86-88 fused).
