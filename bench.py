@@ -301,16 +301,18 @@ def run_b200(args, rank, world, local_rank):
         roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
                 "traffic": None}
     # DRAM bytes per launch of that kernel class from the committed ncu capture of the same shapes
-    # (profiles/traffic_r01f.json: dram__bytes_read.sum + dram__bytes_write.sum, one pass, C2 size)
+    # (profiles/traffic_r01h.json: dram__bytes_read.sum + dram__bytes_write.sum, one pass, C2 size;
+    # tools/traffic_json.py)
     try:
         pat = {"fused_downtran_conv8x8s4": "fused_down_kernel", "deconv8x8s4": "igemm_kernel<1, 32, 256>",
                "pointwise_lr": "igemm_kernel<0, 32, 32>", "finalize_lr": "finalize_lr_kernel",
                "conv_out3x3": "igemm_kernel<2, 32, 32>", "conv_in_gemm": "igemm_kernel<0, 32, 128>",
                "fc_fuse": "fc_fuse_kernel", "im2col": "im2col_kernel"}[dom]
+        tfile = next(f for f in ("traffic_r01h.json", "traffic_r01f.json") if os.path.exists(os.path.join(ROOT, "profiles", f)))
         tr = [t["dram_read_bytes"] + t["dram_write_bytes"]
-              for t in json.load(open(os.path.join(ROOT, "profiles", "traffic_r01f.json"))) if pat in t["kernel"]]
+              for t in json.load(open(os.path.join(ROOT, "profiles", tfile))) if pat in t["kernel"]]
         roof["traffic"] = sum(tr) / len(tr) if tr else None
-        roof["traffic_source"] = "profiles/traffic_r01f.json (ncu, same shapes, average over the class's launches)"
+        roof["traffic_source"] = f"profiles/{tfile} (ncu, same shapes, average over the class's launches)"
     except Exception:
         pass
     roof.update({"kernel": dom, "launches_per_step": d["launches"], "avg_launch_ms": d["ms"] / d["launches"],
