@@ -103,7 +103,7 @@ struct Layer {
   const float* fin_bias;
   void* fin_out;
   int64_t fin_n8;
-  int fin_w, fin_h;
+  int fin_w, fin_h, fin_mask;   // fin_mask: 7 (rows Y % 8 == 7) or 1 (odd rows), matching the fused kernel's xchg mode
   int grid;
   size_t smem;
   int kclass;
@@ -154,7 +154,7 @@ int launch_layer(const Layer& L, cudaStream_t st) {
       if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
       cudaError_t e = launch_pdl(finalize_lr_kernel, (int)blocks, 256, 0, st, reinterpret_cast<const float4*>(L.fin_acc),
                                  L.fin_bias, reinterpret_cast<uint4*>(L.fin_out), L.fin_n8, L.fin_h, L.fin_w,
-                                 fused_xchg() ? 7 : 1);
+                                 L.fin_mask);
       if (e != cudaSuccess) return cuda_status(e);
       return after_launch();
     }
@@ -511,6 +511,7 @@ int build_finalize(Layer& L, float* acc, const float* bias_dev, void* out, int64
   L.fin_n8 = pixels * 4;
   L.fin_w = w;
   L.fin_h = h;
+  L.fin_mask = fused_xchg() ? 7 : 1;
   L.kclass = KC_FINALIZE;
   L.flops = 0;
   L.bytes = 0;   // the boundary-pixel pass moves no compulsory bytes (its pixels' output is counted in the fused launch)
