@@ -386,8 +386,8 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
             const int s16 = g * 4 + sub, ry = s16 >> 2, rx = s16 & 3;
             const bool ring = (Yb == 0 && ry < 2) || (Yb == p.lr_h && ry >= 2) || (Xb == 0 && rx < 2) ||
                               (Xb == p.lr_w && rx >= 2);
-            if (in_tensor && !ring) convert32(v, s_bias, pc, o);
-            else zero16(o);
+            convert32(v, s_bias, pc, o);
+            if (__builtin_expect(!(in_tensor && !ring), 0)) zero16(o);
           }
           ++m_a[buf];
           mbar_wait(h_empty, (m_h & 1) ^ 1);

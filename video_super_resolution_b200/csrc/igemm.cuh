@@ -561,11 +561,8 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
           for (int c2 = 0; c2 < 2; ++c2) {
             const int cg = sub * 2 + c2;
             uint32_t v[32];
-            if (p.debug & 2) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = 0;
-            } else {
-              tmem_ld32(taddr + cg * 32, v);
+            if (!(p.debug & 2)) {       // (the knock-out leaves v undefined; zeroing it here cost 32 CS2R per read even
+              tmem_ld32(taddr + cg * 32, v);   //  in production, ncu: 10 % of the kernel's instructions)
               tmem_ld_wait();
             }
             if (c2 == 1) {
@@ -578,8 +575,8 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
             const int Yt = 4 * Y + ry - 2, Xt = 4 * X + rx - 2;
             const bool inside = (Yt >= 0) && (Yt < H) && (Xt >= 0) && (Xt < W);   // else: zero ring
             uint32_t o[16];
-            if (inside) convert32(v, s_bias, pc, o);   // ring positions (tile border only) stay zero
-            else zero16(o);
+            convert32(v, s_bias, pc, o);
+            if (__builtin_expect(!inside, 0)) zero16(o);   // ring positions (tile border only) stay zero
             if (c2 == 0) {   // the previous tile's store must have read the staging tile before it is overwritten
               if (lane == 0) tma_store_wait_read();   // (waited for here, after the TMEM read + conversion, not before)
               __syncwarp();
