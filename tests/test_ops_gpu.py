@@ -166,6 +166,22 @@ def test_projection_edge_cases():
     _check_projection(i, synthetic.inv_depth(1, 12, 40, seed=9))
 
 
+@pytest.mark.parametrize("shape", [(1, 1, 1), (2, 1, 40), (1, 40, 1), (1, 2, 2), (1, 17, 33), (1, 33, 65), (3, 32, 32)])
+def test_projection_degenerate_shapes_and_border_hits(shape):
+    """Single rows / columns, sizes straddling the 32-pixel strips, and flows that land exactly on the last row /
+    column (the clamped duplicate targets = multiplicity 2 of the 2x2 box sum), half-integer and integer mixes."""
+    B, h, w = shape
+    g = torch.Generator().manual_seed(h * 100 + w)
+    flow = torch.randint(-3, 4, (B, h, w, 2), generator=g).float()
+    flow += torch.randint(0, 2, (B, h, w, 2), generator=g).float() * 0.5
+    yy, xx = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+    flow[:, :, -1, 0] = (w - 1 - xx[:, -1]).float()          # last column's sources stay on the last column
+    flow[:, -1, :, 1] = (h - 1 - yy[-1, :]).float()          # last row's sources stay on the last row
+    flow[:, 0, 0, :] = torch.tensor([float(w - 1), float(h - 1)])   # corner source -> opposite corner exactly
+    for inv in (None, synthetic.inv_depth(B, h, w, seed=h + w)):
+        _check_projection(flow, inv)
+
+
 def test_projection_full_size_properties():
     # C3 size (1080p): size-independent properties instead of the slow CPU oracle
     B, h, w = 1, 1080, 1920

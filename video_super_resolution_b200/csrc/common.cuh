@@ -25,6 +25,19 @@ inline int after_launch() {
 
 inline cudaStream_t as_stream(vsr_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// One-time per-DEVICE setup (function attributes and __constant__ data are per device): the design is one
+// process per GPU, but a process that drives several devices must not find the second one unprepared.
+struct PerDeviceOnce {
+  std::atomic<uint64_t> done{0};          // bit d: device d prepared (devices >= 64 are prepared on every call)
+  bool needed(int* dev) {
+    if (cudaGetDevice(dev) != cudaSuccess) *dev = 0;
+    return *dev >= 64 || !((done.load(std::memory_order_acquire) >> *dev) & 1ull);
+  }
+  void mark(int dev) {
+    if (dev < 64) done.fetch_or(1ull << dev, std::memory_order_release);
+  }
+};
+
 // Programmatic dependent launch: the next kernel of a stream may start its prologue (barrier init, TMEM
 // allocation, weight loads) on SMs the previous kernel has already left; it must not touch any
 // activation buffer before griddep_wait(), which returns once every earlier grid has completed and

@@ -127,15 +127,16 @@ extern "C" int vsr_flow_to_image(const float* flow, int h, int w, uint8_t* img_u
   if (!flow || !workspace || h <= 0 || w <= 0 || (!img_u8 && !planes)) return VSR_ERR_INVALID_ARG;
   if (planes && (out_h <= 0 || out_w <= 0)) return VSR_ERR_INVALID_ARG;
   cudaStream_t st = as_stream(stream);
-  static bool wheel_set = false;   // per process and device context; 1.3 KB
-  if (!wheel_set) {
+  static PerDeviceOnce once;   // __constant__ data is per device; 1.3 KB
+  int dev;
+  if (once.needed(&dev)) {
     double wheel[55 * 3];
     make_wheel(wheel);
     cudaError_t e = cudaMemcpyToSymbolAsync(c_wheel, wheel, sizeof(wheel), 0, cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return cuda_status(e);
     e = cudaStreamSynchronize(st);   // `wheel` lives on this stack frame
     if (e != cudaSuccess) return cuda_status(e);
-    wheel_set = true;
+    once.mark(dev);
   }
   cudaError_t e = cudaMemsetAsync(workspace, 0, 8, st);
   if (e != cudaSuccess) return cuda_status(e);

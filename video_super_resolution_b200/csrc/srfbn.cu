@@ -118,12 +118,13 @@ int fused_xchg() {   // tuning knob, see FusedDownParams::xchg
 
 template <int MODE, int CK, int BN>
 int launch_variant(const Layer& L, cudaStream_t st) {
-  static bool attr_set = false;   // per process; the attribute is sticky per function
-  if (!attr_set) {
+  static PerDeviceOnce once;       // the attribute is sticky per function and device
+  int dev;
+  if (once.needed(&dev)) {
     cudaError_t e = cudaFuncSetAttribute(igemm_kernel<MODE, CK, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          227 * 1024);
     if (e != cudaSuccess) return cuda_status(e);
-    attr_set = true;
+    once.mark(dev);
   }
   cudaError_t e = launch_pdl(igemm_kernel<MODE, CK, BN>, L.grid, MODE == EPI_DECONV ? kDeconvThreads : kIgemmThreads,
                              L.smem, st, L.p);
@@ -133,12 +134,13 @@ int launch_variant(const Layer& L, cudaStream_t st) {
 
 template <bool HAS_TRAN>
 int launch_fused(const Layer& L, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce once;
+  int dev;
+  if (once.needed(&dev)) {
     cudaError_t e = cudaFuncSetAttribute(fused_down_kernel<HAS_TRAN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          227 * 1024);
     if (e != cudaSuccess) return cuda_status(e);
-    attr_set = true;
+    once.mark(dev);
   }
   cudaError_t e = launch_pdl(fused_down_kernel<HAS_TRAN>, L.grid, kFusedThreads, L.smem, st, L.f);
   if (e != cudaSuccess) return cuda_status(e);
