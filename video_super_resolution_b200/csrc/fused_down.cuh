@@ -1,6 +1,6 @@
 // fused_down.cuh -- one kernel for the HR half of a feedback group:
 //
-//     lr[i+1] (pre-activation sums) = Conv8x8s4( PReLU( Conv1x1( cat(hr[0..i]) ) ) )
+//     lr[i+1] = PReLU( Conv8x8s4( PReLU( Conv1x1( cat(hr[0..i]) ) ) ) )
 //     ref: FeedbackBlock.forward, SRProjectionModule.py:70-80 (downtranBlocks[i-1] then downBlocks[i]),
 //          intended dense-concat dataflow
 //
@@ -17,14 +17,17 @@
 //   phase B: D_B[128, 4 taps x 32] += H_g[128, 128] * Wd_g[128, 128]^T        (K = 512 over 4 groups)
 //            "output-shift" form of the strided conv: block (Yb,Xb) contributes its tap-(dy,dx)
 //            partial product to LR pixel (Yb-dy, Xb-dx); every block is read exactly once
-//   epilogue: the four 32-channel partials of each block go to per-pixel FP32 "slots" with exactly one
-//            writer each (dx taps are first combined across lanes by shuffle), finalize_lr_kernel sums
-//            the slots, applies bias + PReLU and rounds to BF16 -- no atomics, deterministic.
+//   epilogue: the four 32-channel tap partials of each block are combined across lanes (dx: shuffle by 1,
+//            dy: shuffle by 16 / a 6 KB shared-memory exchange between lane quarters); 82 % of the LR
+//            pixels are complete inside the tile and leave as finished BF16 (bias + PReLU); the pixels
+//            of tile row 7 and of the tile's last column go to per-pixel FP32 "slots" with exactly one
+//            writer each and finalize_lr_kernel sums them -- no atomics, deterministic.
 //            (A first version used red.global.add.v4.f32: ~10k cycles per tile of L2 atomic
-//            throughput, the kernel's fixed cost; see profiles/.)
+//            throughput, the kernel's fixed cost; the second sent every pixel through the slots.)
 //
 // HAS_TRAN = false is group 0 (no downtran: H = hr[0]); phase B's A operand then comes straight from
-// TMA.  Warp roles as in igemm.cuh: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue.
+// TMA.  Warp roles: warp 0 TMA producer, warp 1 MMA issuer (phase A with HAS_TRAN), warps 2-17 epilogue,
+// warp 18 conv-weight streamer, warp 19 phase-B MMA issuer (HAS_TRAN).
 #pragma once
 #include "igemm.cuh"
 

@@ -12,8 +12,8 @@
 //    + cell(ty-1,tx) + cell(ty-1,tx-1), with the clamped duplicates (xR == xL at the last column, yB == yT at
 //    the last row) as multiplicity 2 of the target's own column / row.  One vector reduction per source
 //    pixel instead of four (the first version aggregated neighbouring lanes' targets by shuffle and still
-//    paid ~1.25 on smooth fields and 4 on config C3's i.i.d. field); the box sum is a gather through shared
-//    memory fused into the normalise pass, in a fixed order.
+//    paid ~1.25 on smooth fields and 4 on config C3's i.i.d. field); the box sum is a gather (registers +
+//    one shuffle) fused into the normalise pass, in a fixed order.
 //  * A cell is ONE float4 {sum -fx*D, sum -fy*D, sum D, count}: a 16-byte red.global.add.v4.f32 (sm_90+);
 //    the count rides along as a float (exact below 2^24) and is exported as int32 -> count/hole bit-exact.
 //  * Images are processed one at a time with a single-image cell array (16 B/pixel, 33 MB at 1080p) that

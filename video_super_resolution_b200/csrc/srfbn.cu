@@ -13,7 +13,8 @@
 //                           torch.cat never materialises), N=32
 //   ConvTranspose 8x8 s4  : output-stationary: block (Yb,Xb) of the "HR block layout" gets 2x2 LR
 //                           taps, N = 16 sub-positions x 32 channels (two N=256 halves)
-//   Conv 8x8 s4           : LR pixel (Y,X) reads the 2x2 blocks (Y..Y+1, X..X+1), K = 4*512, N=32
+//   Conv 8x8 s4           : fused with the 1x1 "downtran" in front of it (fused_down.cuh), output-shift form
+//   x2 geometry (k6 s2 p2): layered on plain NHWC HR features (build_deconv2 / build_downconv2)
 //   conv_out 3x3 32->3    : 9 taps at HR, N=16 (3 used), epilogue adds the bilinear skip and the
 //                           mean shifts and writes fp32 planes
 // HR block layout: an HR feature map of (4h,4w) pixels is stored as (h+1, w+1) blocks of 4x4 pixels
