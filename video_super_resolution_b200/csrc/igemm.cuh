@@ -122,16 +122,30 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns) {
   uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
+  const uint32_t hint = (ns >> 16) * 256u;   // knob: bits 16+ = suspend-time hint of try_wait in units of 256 ns, low 16 bits = nanosleep
+  ns &= 0xffffu;
   while (true) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, P1;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
+    if (hint) {
+      asm volatile(
+          "{\n"
+          ".reg .pred P1;\n"
+          "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n"
+          "selp.u32 %0, 1, 0, P1;\n"
+          "}\n"
+          : "=r"(done)
+          : "r"(addr), "r"(parity), "r"(hint)
+          : "memory");
+    } else {
+      asm volatile(
+          "{\n"
+          ".reg .pred P1;\n"
+          "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+          "selp.u32 %0, 1, 0, P1;\n"
+          "}\n"
+          : "=r"(done)
+          : "r"(addr), "r"(parity)
+          : "memory");
+    }
     if (done) break;
     if (ns) __nanosleep(ns);
   }
