@@ -503,21 +503,39 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
   }
 }
 
-// Boundary pixels (rows Y % 8 == 7 -- row_mask 7; odd rows without the exchange -- row_mask 1; columns X % 16 == 15;
+// Boundary pixels (rows Y % 8 == 7 -- period 8; odd rows without the exchange -- period 2; columns X % 16 == 15;
 // see the fused kernel's final epilogue):
 // lr_out[p, c] = bf16(PReLU(sum of the pixel's partial slots + bias[c])).  8 channels per thread.
 // Deterministic: every slot has one writer, the sum order is fixed.
 __global__ void __launch_bounds__(256)
-finalize_lr_kernel(const float4* __restrict__ part, const float* __restrict__ bias, uint4* __restrict__ out, int64_t n8,
-                   int h, int w, int row_mask) {
+finalize_lr_kernel(const float4* __restrict__ part, const float* __restrict__ bias, uint4* __restrict__ out, int B, int h,
+                   int w, int period) {
+  // Work items = boundary pixels only, enumerated arithmetically (the first version walked every pixel and skipped
+  // the interior ones): first the full rows Y = period*k + period-1, then, in the other rows, the columns X = 16*j + 15.
   const float slope = __ldg(bias + 32);
   griddep_wait();
+  const int R = h / period, Cc = w / 16;
+  const int64_t nA = (int64_t)B * R * w, nB = (int64_t)B * (h - R) * Cc;
+  const int64_t n8 = (nA + nB) * 4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t px = i >> 2;
     const int c8 = (int)(i & 3);
-    const int X = (int)(px % w), Y = (int)((px / w) % h);
+    int64_t it = i >> 2;
+    int b, Y, X;
+    if (it < nA) {
+      X = (int)(it % w);
+      const int64_t r = it / w;
+      Y = (int)(r % R) * period + period - 1;
+      b = (int)(r / R);
+    } else {
+      it -= nA;
+      X = (int)(it % Cc) * 16 + 15;
+      const int64_t r = it / Cc;
+      const int yy = (int)(r % (h - R));
+      Y = yy + yy / (period - 1);
+      b = (int)(r / (h - R));
+    }
     const bool last_col = (X & 15) == 15;
-    if (!((Y & row_mask) == row_mask || last_col)) continue;   // interior: finished by the fused kernel
+    const int64_t px = ((int64_t)b * h + Y) * w + X;
     const float4* base = part + px * 32 + c8 * 2;          // 32 float4 per pixel, 8 per slot
     float4 a0 = base[0], a1 = base[1];
     const float4 b0 = base[16], b1 = base[17];
@@ -531,7 +549,7 @@ finalize_lr_kernel(const float4* __restrict__ part, const float* __restrict__ bi
     float r[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
     for (int k = 0; k < 8; ++k) r[k] = prelu(r[k] + __ldg(bias + c8 * 8 + k), slope, 1);
-    out[i] = make_uint4(pack_bf16(r[0], r[1]), pack_bf16(r[2], r[3]), pack_bf16(r[4], r[5]), pack_bf16(r[6], r[7]));
+    out[px * 4 + c8] = make_uint4(pack_bf16(r[0], r[1]), pack_bf16(r[2], r[3]), pack_bf16(r[4], r[5]), pack_bf16(r[6], r[7]));
   }
 }
 

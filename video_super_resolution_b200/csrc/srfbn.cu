@@ -104,7 +104,7 @@ struct Layer {
   const float* fin_bias;
   void* fin_out;
   int64_t fin_n8;
-  int fin_w, fin_h, fin_mask;   // fin_mask: 7 (rows Y % 8 == 7) or 1 (odd rows), matching the fused kernel's xchg mode
+  int fin_w, fin_h, fin_b, fin_period;   // fin_period: 8 (rows Y % 8 == 7) or 2 (odd rows), matching the fused kernel's xchg mode
   int grid;
   size_t smem;
   int kclass;
@@ -153,11 +153,13 @@ int launch_layer(const Layer& L, cudaStream_t st) {
     case V_FUSED_TRAN: return launch_fused<true>(L, st);
     case V_FUSED_PLAIN: return launch_fused<false>(L, st);
     case V_FINALIZE: {
-      int64_t blocks = ceil_div64(L.fin_n8, 256);
+      const int R = L.fin_h / L.fin_period;
+      const int64_t items = ((int64_t)L.fin_b * R * L.fin_w + (int64_t)L.fin_b * (L.fin_h - R) * (L.fin_w / 16)) * 4;
+      if (items == 0) return VSR_OK;
+      int64_t blocks = ceil_div64(items, 256);
       if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
       cudaError_t e = launch_pdl(finalize_lr_kernel, (int)blocks, 256, 0, st, reinterpret_cast<const float4*>(L.fin_acc),
-                                 L.fin_bias, reinterpret_cast<uint4*>(L.fin_out), L.fin_n8, L.fin_h, L.fin_w,
-                                 L.fin_mask);
+                                 L.fin_bias, reinterpret_cast<uint4*>(L.fin_out), L.fin_b, L.fin_h, L.fin_w, L.fin_period);
       if (e != cudaSuccess) return cuda_status(e);
       return after_launch();
     }
@@ -514,7 +516,8 @@ int build_finalize(Layer& L, float* acc, const float* bias_dev, void* out, int64
   L.fin_n8 = pixels * 4;
   L.fin_w = w;
   L.fin_h = h;
-  L.fin_mask = fused_xchg() ? 7 : 1;
+  L.fin_b = (int)(pixels / ((int64_t)h * w));
+  L.fin_period = fused_xchg() ? 8 : 2;
   L.kclass = KC_FINALIZE;
   L.flops = 0;
   L.bytes = 0;   // the boundary-pixel pass moves no compulsory bytes (its pixels' output is counted in the fused launch)
