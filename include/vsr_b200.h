@@ -65,6 +65,20 @@ int vsr_warp_nhwc_f32(const float* src, const float* flow, float* dst,
                       const float* ref, float* norm_out,
                       int B, int H, int W, int C, int bilinear, vsr_stream_t stream);
 
+/* The neighbour warp of one frame window in a single launch, without a gathered copy of the frames:
+ * frames (T,H,W,3) f32 NHWC; flows (T-1,H,W,2) f32, one field per NEIGHBOUR in frame order with the centre
+ * frame left out, each mapping centre coordinates to that neighbour; warped (T-1,H,W,3); resid (T-1,H,W) or
+ * NULL = per-pixel L2 norm of (frames[centre] - warped[n]) (models.py:86-88 fused).  Arithmetic and
+ * `bilinear` modes as vsr_warp_nhwc_f32. */
+int vsr_warp_window_nhwc3(const float* frames, const float* flows, float* warped, float* resid,
+                          int T, int centre, int H, int W, int bilinear, vsr_stream_t stream);
+
+/* Flow composition out(p) = g(p) + f(p + g(p)) with f sampled bilinearly (the warp's taps and border rule,
+ * fp32 blend): if g maps image A to B and f maps B to C, out maps A to C.  g, f, out (B,H,W,2) f32.  Used to chain
+ * adjacent-pair flows into centre -> neighbour flows for windows longer than 3 frames.  g == NULL is the identity
+ * field: out = f (the first link of a chain, placed into the caller's contiguous (T-1,H,W,2) array). */
+int vsr_compose_flow(const float* g, const float* f, float* out, int B, int H, int W, vsr_stream_t stream);
+
 /* Nearest-neighbour label/mask warp on u8 (north star "VOSProjection: mask/label warping"),
  * ref arithmetic: resample2d_kernel.cu:65-70 (floor(xf + 0.5) in double, border clamp).
  * labels/dst (B,H,W) u8, flow (B,H,W,2) f32.  Bit-exact. */
@@ -125,12 +139,26 @@ int vsr_correlation_backward(const float* input1, const float* input2, const flo
  * outputs: proj (B,h,w,2) f32, wsum (B,h,w) f32 or NULL, count (B,h,w) i32, hole (B,h,w) u8.
  * workspace: vsr_flow_projection_workspace_bytes(B,h,w) bytes of device memory (any contents).
  * count / hole are bit-exact; proj / wsum are fp32 sums in nondeterministic order.
+ * A target counts as a hole when nothing hit it OR when its hits carry no positive weight (sum of inverse
+ * depths <= 0 or NaN): it is then filled from its neighbours like any other hole instead of dividing by zero.
+ * This entry point makes no assumption about the flow (config C3's +-64 px): atomic scatter into an L2-resident
+ * cell array, the stages of successive images pipelined inside one cooperative persistent kernel.
+ *
+ * vsr_flow_projection_forward_bounded: the caller additionally PROMISES |fx|, |fy| <= max_disp for every pixel
+ * (the smooth fields of configs C2/C4/C5: 8 px).  For 0 <= max_disp <= 16 the batch runs through shared-memory
+ * tiles (target tile + halo, owner-computes accumulation without atomics, one coalesced pass out).  A broken
+ * promise is detected on the device and the batch is redone by the general path: the result never depends on the
+ * promise, only the speed does.  Any other max_disp (negative, NaN, > 16) selects the general path directly.
  * ---------------------------------------------------------------------------------------- */
 size_t vsr_flow_projection_workspace_bytes(int B, int h, int w);
 int vsr_flow_projection_forward(const float* flow, const float* inv_depth,
                                 float* proj, float* wsum, int32_t* count, uint8_t* hole,
                                 void* workspace, size_t workspace_bytes,
                                 int B, int h, int w, vsr_stream_t stream);
+int vsr_flow_projection_forward_bounded(const float* flow, const float* inv_depth,
+                                        float* proj, float* wsum, int32_t* count, uint8_t* hole,
+                                        void* workspace, size_t workspace_bytes,
+                                        int B, int h, int w, float max_disp, vsr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * a5: VOS mask arithmetic.  ref: VOSProjectionModule.py:22-25 (sigmoid(a)+sigmoid(b) > 0.7),
@@ -152,12 +180,13 @@ int vsr_mask_fill(const float* image, const uint8_t* mask, float* masked,
  * frame at centre_idx), T-1 flow maps (projected fx, projected fy, warp-residual norm), T-1 depth
  * maps tiled x3 (utils/tools.py:76-77), 1 estimate.
  * warped (T-1,h,w,3) NHWC, centre (h,w,3), proj (T-1,h,w,2), resid (T-1,h,w), depth (T-1,h,w),
- * estimate (3,h,w) NCHW or NULL (= centre frame, video_super_resolution.py:37-38); stack (M,3,h,w).
+ * estimate (3,h,w) NCHW, or NULL: the slot then receives `fallback` (h,w,3) NHWC, which the caller sets to LR
+ * frame 0 of the window (video_super_resolution.py:37-38 `else data_clone[0:1]`); stack (M,3,h,w).
  * vsr_estimate_slot: slot (3,h,w) = mask ? 0 : hr[:, y*scale, x*scale] for hr (3,h*scale,w*scale);
  * mask (h,w) u8 or NULL.
  * ---------------------------------------------------------------------------------------- */
 int vsr_assemble_stack(const float* warped, const float* centre, const float* proj, const float* resid,
-                       const float* depth, const float* estimate, float* stack,
+                       const float* depth, const float* estimate, const float* fallback, float* stack,
                        int T, int centre_idx, int h, int w, vsr_stream_t stream);
 int vsr_estimate_slot(const float* hr, const uint8_t* mask, float* slot, int h, int w, int scale,
                       vsr_stream_t stream);
@@ -251,6 +280,10 @@ int vsr_srfbn_bind(vsr_srfbn_plan* plan, const void* dev_weights, void* dev_work
                    size_t workspace_bytes);
 /* x: (M,3,h,w) f32 NCHW, 0..255 (video_super_resolution.py:40,62); y: (1,3,s*h,s*w) f32. */
 int vsr_srfbn_forward(vsr_srfbn_plan* plan, const float* x, float* y, vsr_stream_t stream);
+/* Same, with the fused frame also (or only) as u8 pixels: y_u8 (s*h,s*w,3) NHWC = clamp(y,0,255) rounded half to
+ * even, the format the reference's loader holds frames in (utils/video_utils.py:23) -- what a frame writer or the
+ * final gather consumes.  Either of y / y_u8 may be NULL, not both. */
+int vsr_srfbn_forward_u8(vsr_srfbn_plan* plan, const float* x, float* y, uint8_t* y_u8, vsr_stream_t stream);
 /* Per-launch accounting for bench.py: with profiling enabled, vsr_srfbn_forward brackets every
  * kernel launch with CUDA events on the caller's stream; vsr_srfbn_profile_read waits for the last
  * forward and returns, per kernel class, the summed device time (ms), the number of launches, and

@@ -238,10 +238,13 @@ def mask_fill(image, mask):
     return out
 
 
-def assemble_stack(warped, centre, proj, resid, depth, estimate, centre_idx):
+def assemble_stack(warped, centre, proj, resid, depth, estimate, centre_idx, fallback=None):
     """numpy restatement of the stack assembly (video_super_resolution.py:33-40 generalised to T
     frames): warped (T-1,h,w,3), centre (h,w,3), proj (T-1,h,w,2), resid/depth (T-1,h,w),
-    estimate (3,h,w)|None -> (3T-1,3,h,w)."""
+    estimate (3,h,w)|None -> (3T-1,3,h,w).  Without an estimate the last slot is `fallback` (h,w,3) = LR frame 0
+    of the window (:37-38 `else data_clone[0:1]`)."""
+    if fallback is None:
+        fallback = centre
     Tm1, h, w, _ = warped.shape
     T = Tm1 + 1
     out = np.zeros((3 * T - 1, 3, h, w), np.float32)
@@ -257,8 +260,33 @@ def assemble_stack(warped, centre, proj, resid, depth, estimate, centre_idx):
         out[T + n, 1] = proj[n, :, :, 1]
         out[T + n, 2] = resid[n]
         out[2 * T - 1 + n] = np.stack((depth[n],) * 3)               # maskprocess
-    out[3 * T - 2] = centre.transpose(2, 0, 1) if estimate is None else estimate
+    out[3 * T - 2] = fallback.transpose(2, 0, 1) if estimate is None else estimate
     return out
+
+
+def compose_flow(g, f):
+    """out(p) = g(p) + f(p + g(p)), f (h,w,2) sampled with the Resample2d taps and border rule (Appendix A);
+    g maps image A to B, f maps B to C, the result maps A to C."""
+    g = _c(g, np.float32)
+    f = _c(f, np.float32)
+    return (g + warp_nhwc(f[None], g[None], True)[0]).astype(np.float32)
+
+
+def chain_flows(proj, flows, centre):
+    """Centre -> neighbour flows (T-1,h,w,2), frame order with the centre left out (WarpFusePipeline docstring):
+    past frames chain the PROJECTED flows (they live in the later frame's coordinates), future frames the forward
+    flows (they live in the earlier frame's)."""
+    Tm1 = flows.shape[0]
+    T, c = Tm1 + 1, centre
+    G = np.zeros_like(flows)
+    G[c - 1] = proj[c - 1]
+    for t in range(c - 2, -1, -1):
+        G[t] = compose_flow(G[t + 1], proj[t])
+    if c + 1 < T:
+        G[c] = flows[c]
+        for t in range(c + 2, T):
+            G[t - 1] = compose_flow(G[t - 2], flows[t - 1])
+    return G
 
 
 def estimate_slot(hr, mask, scale=4):
@@ -277,15 +305,16 @@ def warp_fuse_front(frames, flows, inv_depth, logits_a, logits_b, estimate=None,
     c = T // 2
     proj_f, _, cnt_f, hole_f = flow_projection(flows, None, threads=threads)
     proj_d, wsum, cnt_d, hole_d = flow_projection(flows, inv_depth, threads=threads)
+    G = chain_flows(proj_d, flows, c)
     neigh = np.ascontiguousarray(frames[[t for t in range(T) if t != c]])
-    warped = warp_nhwc(neigh, proj_d, True, threads=threads)
+    warped = warp_nhwc(neigh, G, True, threads=threads)
     resid = channelnorm_nhwc(frames[c][None] - warped)
     mask = vos_threshold(logits_a, logits_b)
-    mask_w = warp_labels(mask[None], proj_d[min(c, T - 2)][None])[0]
-    stack = assemble_stack(warped, frames[c], proj_f, resid, wsum, estimate, c)
+    mask_w = warp_labels(mask[None], G[c - 1][None])[0]
+    stack = assemble_stack(warped, frames[c], proj_f, resid, wsum, estimate, c, fallback=frames[0])
     return stack, {"proj_flow": proj_f, "count_flow": cnt_f, "hole_flow": hole_f, "proj_depth": proj_d, "wsum": wsum,
                    "count_depth": cnt_d, "hole_depth": hole_d, "warped": warped, "resid": resid, "mask": mask,
-                   "mask_warped": mask_w}
+                   "mask_warped": mask_w, "centre_flows": G}
 
 
 def flow2img(flow):

@@ -117,13 +117,16 @@ def test_channelnorm_bit_exact(shape):
     assert np.array_equal(got, orc.channelnorm_nchw(x.numpy()))
 
 
-def _check_projection(flow, inv):
-    proj, wsum, count, hole = ops.project_flow(flow.to(DEV), inv.to(DEV) if inv is not None else None)
+def _check_projection(flow, inv, bounds=(None,)):
+    """bounds: the max_disp promises to run with (None = general scatter path; a number = shared-memory tile path,
+    or its device-side fallback when the flow breaks the promise) -- every one must reproduce the oracle."""
     o_proj, o_wsum, o_count, o_hole = orc.flow_projection(flow.numpy(), inv.numpy() if inv is not None else None)
-    assert np.array_equal(_np(count), o_count)            # bit-exact (north star)
-    assert np.array_equal(_np(hole), o_hole)              # bit-exact
-    assert np.abs(_np(proj) - o_proj).max() <= TOL
-    assert np.abs(_np(wsum) - o_wsum).max() <= TOL * max(1.0, float(o_wsum.max()))
+    for md in bounds:
+        proj, wsum, count, hole = ops.project_flow(flow.to(DEV), inv.to(DEV) if inv is not None else None, md)
+        assert np.array_equal(_np(count), o_count), md        # bit-exact (north star)
+        assert np.array_equal(_np(hole), o_hole), md          # bit-exact
+        assert np.abs(_np(proj) - o_proj).max() <= TOL, md
+        assert np.abs(_np(wsum) - o_wsum).max() <= TOL * max(1.0, float(o_wsum.max())), md
     return o_count, o_hole
 
 
@@ -133,7 +136,19 @@ def test_projection_smooth_flow(shape, weighted):
     B, h, w = shape
     flow = synthetic.smooth_flow(B, h, w, 8.0, seed=h)
     inv = synthetic.inv_depth(B, h, w, seed=w) if weighted else None
-    _check_projection(flow, inv)
+    # 8.0 / 16.0: promises that hold (tile path); 3.0: a promise this field breaks (flag + redo by the general path)
+    _check_projection(flow, inv, bounds=(None, 8.0, 16.0, 3.0))
+
+
+@pytest.mark.parametrize("shape", [(1, 200, 400), (2, 65, 193), (1, 64, 192), (3, 129, 385)])
+def test_projection_tile_path_across_tile_borders(shape):
+    """Sizes around the 192 x 64 tile of the shared-memory path (one tile, one tile + 1, several tiles), smooth and
+    i.i.d. fields within the bound (i.i.d.: many lanes of one instruction hit the same cell -> the claim protocol)."""
+    B, h, w = shape
+    inv = synthetic.inv_depth(B, h, w, seed=3)
+    _check_projection(synthetic.smooth_flow(B, h, w, 8.0, seed=5), inv, bounds=(8.0,))
+    _check_projection(synthetic.random_flow(B, h, w, 6.0, seed=6), inv, bounds=(6.0, 7.5))
+    _check_projection(synthetic.random_flow(B, h, w, 16.0, seed=7), None, bounds=(16.0,))
 
 
 @pytest.mark.parametrize("weighted", [False, True])
@@ -141,8 +156,23 @@ def test_projection_collision_stress_random_flow(weighted):
     B, h, w = 2, 96, 160
     flow = synthetic.random_flow(B, h, w, 64.0, seed=1)
     inv = synthetic.inv_depth(B, h, w, seed=2) if weighted else None
-    count, hole = _check_projection(flow, inv)
+    count, hole = _check_projection(flow, inv, bounds=(None, 16.0))      # 16: broken promise -> general path
     assert hole.any() and count.max() >= 4
+
+
+def test_projection_zero_and_nan_depth_are_holes():
+    """An inverse depth of 0 (or NaN) from a real estimator: a target whose hits carry no positive weight is a hole
+    and is filled from its neighbours -- no division by zero, no NaN downstream (count stays the integer hit count)."""
+    B, h, w = 1, 40, 70
+    flow = torch.zeros((B, h, w, 2))
+    inv = synthetic.inv_depth(B, h, w, seed=1)
+    inv[0, 10:14, 20:25] = 0.0
+    inv[0, 30, 60] = float("nan")
+    for md in (None, 1.0):
+        proj, wsum, count, hole = ops.project_flow(flow.to(DEV), inv.to(DEV), md)
+        assert torch.isfinite(proj).all() and torch.isfinite(wsum).all()
+        assert int(count.min()) >= 1 and bool(hole[0, 11, 21]) and bool(hole[0, 12, 23])
+    _check_projection(flow, inv, bounds=(None, 1.0))
 
 
 def test_projection_dense_occlusion_fill_band():
@@ -155,15 +185,15 @@ def test_projection_dense_occlusion_fill_band():
 def test_projection_edge_cases():
     # zero flow (duplicate clamped targets at the borders), all out of range, NaN flow, integer flow
     z = torch.zeros((1, 9, 11, 2))
-    _check_projection(z, None)
-    _check_projection(torch.full((1, 6, 6, 2), 500.0), None)
+    _check_projection(z, None, bounds=(None, 0.0, 2.0))
+    _check_projection(torch.full((1, 6, 6, 2), 500.0), None, bounds=(None, 16.0))
     n = torch.zeros((1, 6, 7, 2))
     n[0, 2, 3, 0] = float("nan")
-    _check_projection(n, None)
+    _check_projection(n, None, bounds=(None, 1.0))
     i = torch.zeros((1, 12, 40, 2))
     i[..., 0] = 3.0
     i[..., 1] = -2.0
-    _check_projection(i, synthetic.inv_depth(1, 12, 40, seed=9))
+    _check_projection(i, synthetic.inv_depth(1, 12, 40, seed=9), bounds=(None, 3.0))
 
 
 @pytest.mark.parametrize("shape", [(1, 1, 1), (2, 1, 40), (1, 40, 1), (1, 2, 2), (1, 17, 33), (1, 33, 65), (3, 32, 32)])
@@ -179,7 +209,11 @@ def test_projection_degenerate_shapes_and_border_hits(shape):
     flow[:, -1, :, 1] = (h - 1 - yy[-1, :]).float()          # last row's sources stay on the last row
     flow[:, 0, 0, :] = torch.tensor([float(w - 1), float(h - 1)])   # corner source -> opposite corner exactly
     for inv in (None, synthetic.inv_depth(B, h, w, seed=h + w)):
-        _check_projection(flow, inv)
+        _check_projection(flow, inv, bounds=(None, 16.0) if max(h, w) <= 17 else (None,))
+    small = torch.randint(-3, 4, (B, h, w, 2), generator=g).float() * 0.5       # within +-1.5 px: the tile path
+    small[:, :, -1, 0] = 0.0
+    small[:, -1, :, 1] = 0.0
+    _check_projection(small, synthetic.inv_depth(B, h, w, seed=1), bounds=(1.5, 2.0))
 
 
 def test_projection_full_size_properties():
@@ -187,7 +221,7 @@ def test_projection_full_size_properties():
     B, h, w = 1, 1080, 1920
     flow = synthetic.smooth_flow(B, h, w, 8.0, seed=0).to(DEV)
     inv = synthetic.inv_depth(B, h, w, seed=1).to(DEV)
-    proj, wsum, count, hole = ops.project_flow(flow, inv)
+    proj, wsum, count, hole = ops.project_flow(flow, inv, 8.0)
     x2 = torch.arange(w, device=DEV).view(1, 1, w) + flow[..., 0]
     y2 = torch.arange(h, device=DEV).view(1, h, 1) + flow[..., 1]
     valid = (x2 >= 0) & (x2 <= w - 1) & (y2 >= 0) & (y2 <= h - 1)
@@ -197,8 +231,9 @@ def test_projection_full_size_properties():
     assert abs(wsum.sum().item() - wtot) <= 1e-4 * wtot      # linearity: total weight conserved
     assert proj.abs().max().item() <= 8.0 + 1e-3             # a weighted mean of |flow| <= 8
     # idempotent / deterministic integers
-    _, _, count2, hole2 = ops.project_flow(flow, inv)
+    proj2, wsum2, count2, hole2 = ops.project_flow(flow, inv)          # the general path agrees with the tile path
     assert torch.equal(count, count2) and torch.equal(hole, hole2)
+    assert (proj - proj2).abs().max().item() <= 1e-3 and (wsum - wsum2).abs().max().item() <= 1e-3
 
 
 def test_vos_threshold_and_mask_fill_bit_exact():

@@ -23,10 +23,12 @@ def _inputs(T, h, w, seed):
             syn.inv_depth(T - 1, h, w, seed=seed + 2), la, lb)
 
 
-@pytest.mark.parametrize("T,h,w", [(3, 32, 48), (5, 21, 37), (7, 16, 24)])
-def test_front_matches_oracle(T, h, w):
+@pytest.mark.parametrize("T,h,w,max_disp", [(3, 32, 48, None), (5, 21, 37, 5.0), (7, 16, 24, None), (7, 70, 200, 5.0),
+                                             (2, 20, 30, 5.0)])
+def test_front_matches_oracle(T, h, w, max_disp):
     fr, fl, d, la, lb = _inputs(T, h, w, seed=T)
-    pipe = WarpFusePipeline(T, h, w, SRProjectionModule(num_maps=3 * T - 1), 4, device=DEV, run_fusion=False)
+    pipe = WarpFusePipeline(T, h, w, SRProjectionModule(num_maps=3 * T - 1), 4, device=DEV, run_fusion=False,
+                            max_disp=max_disp)
     est = torch.rand((3, h, w), generator=torch.Generator().manual_seed(9)) * 255
     r = pipe.project_and_warp(fr.to(DEV), fl.to(DEV), d.to(DEV), la.to(DEV), lb.to(DEV), est.to(DEV))
     stack, want = orc.warp_fuse_front(fr.numpy(), fl.numpy(), d.numpy(), la.numpy(), lb.numpy(), est.numpy())
@@ -34,6 +36,8 @@ def test_front_matches_oracle(T, h, w):
         assert np.array_equal(r[k].cpu().numpy(), want[k]), k                  # bit-exact integer outputs
     for k in ("proj_flow", "proj_depth", "wsum"):
         assert np.abs(r[k].cpu().numpy() - want[k]).max() <= 1e-3, k           # fp32 sums in atomic order
+    # the chained centre -> neighbour flows: sums of (T-1)/2 sampled projected flows, each within 1e-3
+    assert np.abs(r["centre_flows"].cpu().numpy() - want["centre_flows"]).max() <= 1e-3 * T
     # the warp is bit-exact GIVEN its flow; here the flow itself differs by atomic ordering (<=1e-3 px),
     # which moves a 0..255 image by at most |gradient| * 1e-3
     assert np.abs(r["warped"].cpu().numpy() - want["warped"]).max() <= 0.5
@@ -41,6 +45,62 @@ def test_front_matches_oracle(T, h, w):
     assert got.shape == stack.shape
     assert np.abs(got - stack).max() <= 0.5
     assert np.array_equal(got[3 * T - 2], est.numpy())                         # estimate slot copied verbatim
+    # ... and held to the north star's 1e-3 with the flow taken out of the comparison: the pipeline's own warp
+    # kernel driven by the ORACLE's centre flows against the oracle's warp (reference arithmetic, Appendix A)
+    c = T // 2
+    warped2, resid2 = ops.warp_window(fr.to(DEV), torch.from_numpy(want["centre_flows"]).to(DEV), c, 2)
+    assert np.abs(warped2.cpu().numpy() - want["warped"]).max() <= 1e-3
+    assert np.abs(resid2.cpu().numpy() - want["resid"]).max() <= 2e-3
+    exact, _ = ops.warp_window(fr.to(DEV), torch.from_numpy(want["centre_flows"]).to(DEV), c, 1)
+    assert np.array_equal(exact.cpu().numpy(), want["warped"])                 # exact mode: bit for bit
+    lab = ops.warp_labels(r["mask"].unsqueeze(0), torch.from_numpy(want["centre_flows"][c - 1:c]).to(DEV))[0]
+    assert np.array_equal(lab.cpu().numpy(), want["mask_warped"])
+
+
+def test_estimate_fallback_is_lr_frame_0():
+    """No estimate (first window of a chunk / shard): the slot holds LR frame 0 of the window, as the reference's
+    `else data_clone[0:1]` (network/video_super_resolution.py:37-38)."""
+    T, h, w = 5, 18, 26
+    fr, fl, d, la, lb = _inputs(T, h, w, seed=3)
+    pipe = WarpFusePipeline(T, h, w, SRProjectionModule(num_maps=3 * T - 1), 4, device=DEV, run_fusion=False)
+    pipe.project_and_warp(fr.to(DEV), fl.to(DEV), d.to(DEV), la.to(DEV), lb.to(DEV), None)
+    assert np.array_equal(pipe.stack[3 * T - 2].cpu().numpy(), fr[0].permute(2, 0, 1).numpy())
+    hr = torch.rand((3, 4 * h, 4 * w), generator=torch.Generator().manual_seed(2)) * 255
+    pipe.project_and_warp(fr.to(DEV), fl.to(DEV), d.to(DEV), la.to(DEV), lb.to(DEV), None, estimate_hr=hr.to(DEV))
+    assert np.array_equal(pipe.stack[3 * T - 2].cpu().numpy(), hr[:, ::4, ::4].numpy())     # :35-37 nearest downsize
+
+
+@pytest.mark.parametrize("T", [2, 3, 5, 7])
+def test_translating_scene_is_aligned_to_the_centre_frame(T):
+    """A scene that translates by a constant integer velocity: frame t = base shifted by t*v, every flow n -> n+1
+    is the constant v.  Every neighbour -- before AND after the centre -- must come out equal to the centre frame
+    (away from the borders), the residual maps must vanish there, and a mask defined in frame c-1 must land on the
+    centre frame's pixels."""
+    h, w, vx, vy = 48, 64, 3, -2
+    g = torch.Generator().manual_seed(T)
+    big = torch.rand((h + 2 * 8 * T, w + 2 * 8 * T, 3), generator=g) * 255
+    o = 8 * T
+    # content at p in frame t sits at p + v in frame t+1  <=>  frame_t(p) = base(p - t*v)
+    frames = torch.stack([big[o - t * vy:o - t * vy + h, o - t * vx:o - t * vx + w] for t in range(T)]).contiguous()
+    flows = torch.zeros((T - 1, h, w, 2))
+    flows[..., 0], flows[..., 1] = float(vx), float(vy)
+    inv = syn.inv_depth(T - 1, h, w, seed=1)
+    c = T // 2
+    la = torch.full((h, w), -20.0)
+    la[10:20, 12:30] = 20.0                                   # mask (frame c-1 coordinates): a rectangle
+    for md in (None, 3.0):
+        pipe = WarpFusePipeline(T, h, w, SRProjectionModule(num_maps=3 * T - 1), 4, device=DEV, run_fusion=False,
+                                max_disp=md)
+        r = pipe.project_and_warp(frames.to(DEV), flows.to(DEV), inv.to(DEV), la.to(DEV), la.to(DEV))
+        m = 3 * T + 2                                         # border margin: chain length x |v| + taps
+        centre = frames[c, m:h - m, m:w - m]
+        for n, t in enumerate([t for t in range(T) if t != c]):
+            got = r["warped"][n].cpu()[m:h - m, m:w - m]
+            assert (got - centre).abs().max().item() <= 1e-3, (T, t)
+            assert r["resid"][n].cpu()[m:h - m, m:w - m].abs().max().item() <= 2e-3, (T, t)
+        want_mask = torch.zeros((h, w), dtype=torch.uint8)
+        want_mask[10 + vy:20 + vy, 12 + vx:30 + vx] = 1       # the rectangle moved by one frame of motion
+        assert torch.equal(r["mask_warped"].cpu()[m:h - m, m:w - m], want_mask[m:h - m, m:w - m])
 
 
 def test_estimate_slot_bit_exact():
@@ -75,6 +135,25 @@ def test_vsr_forward_geometry_against_oracle():
     assert err.max().item() <= 0.05 * scale + 0.5, (err.max().item(), scale)
     mse = (err ** 2).mean().item()
     assert 10 * math.log10(max(ref.abs().max().item(), 1.0) ** 2 / max(mse, 1e-20)) > 40.0
+
+
+def test_step_u8_frame_from_the_fuse_kernel():
+    """The u8 frame the fc-fuse kernel writes equals clamp(0,255) -> round half to even -> u8 of the fp32 frame
+    (pipeline.quantise_u8, the loader's pixel format), with and without the fp32 output."""
+    from video_super_resolution_b200.pipeline import quantise_u8
+    T, h, w = 3, 20, 28
+    M = 3 * T - 1
+    fr, fl, d, la, lb = _inputs(T, h, w, seed=5)
+    sr = SRProjectionModule(num_maps=M)
+    sr.load_state_dict(so.init_state_dict(num_maps=M, seed=1, gain=2.3))
+    pipe = WarpFusePipeline(T, h, w, sr, 4, device=DEV)
+    args = [t.to(DEV) for t in (fr, fl, d, la, lb)]
+    u8 = torch.zeros((4 * h, 4 * w, 3), dtype=torch.uint8, device=DEV)
+    y = pipe.step(*args, out_u8=u8)
+    assert torch.equal(u8, quantise_u8(y)) and int(u8.max()) > 0
+    u8b = torch.zeros_like(u8)
+    r = pipe.step(*args, out_u8=u8b, want_f32=False)
+    assert r is u8b and torch.equal(u8b, u8)
 
 
 def test_module_surfaces_refuse_missing_estimators():

@@ -6,7 +6,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvsr_b200.so")
+# VSR_B200_LIB: load another build of the same ABI (the knock-out build of timing experiments); never a fallback
+LIB_PATH = os.environ.get("VSR_B200_LIB") or os.path.join(_HERE, "libvsr_b200.so")
 
 c_void_p = ctypes.c_void_p
 c_int = ctypes.c_int
@@ -53,6 +54,8 @@ SIGNATURES = {
     "vsr_error_string": (ctypes.c_char_p, [c_int]),
     "vsr_resample2d_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "vsr_warp_nhwc_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "vsr_warp_window_nhwc3": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "vsr_compose_flow": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "vsr_warp_labels_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "vsr_channelnorm_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "vsr_resample2d_backward": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_void_p]),
@@ -62,10 +65,11 @@ SIGNATURES = {
     "vsr_correlation_backward": (c_int, [c_void_p] * 5 + [c_int] * 10 + [c_void_p]),
     "vsr_flow_projection_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "vsr_flow_projection_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_void_p]),
+    "vsr_flow_projection_forward_bounded": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_float, c_void_p]),
     "vsr_vos_threshold": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "vsr_flow_to_image": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "vsr_mask_fill": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
-    "vsr_assemble_stack": (c_int, [c_void_p] * 7 + [c_int, c_int, c_int, c_int, c_void_p]),
+    "vsr_assemble_stack": (c_int, [c_void_p] * 8 + [c_int, c_int, c_int, c_int, c_void_p]),
     "vsr_estimate_slot": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "vsr_srfbn_plan_create": (c_int, [ctypes.POINTER(SrfbnConfig), ctypes.POINTER(c_void_p)]),
     "vsr_srfbn_plan_destroy": (None, [c_void_p]),
@@ -74,6 +78,7 @@ SIGNATURES = {
     "vsr_srfbn_pack_weights": (c_int, [c_void_p, ctypes.POINTER(SrfbnWeights), c_void_p]),
     "vsr_srfbn_bind": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t]),
     "vsr_srfbn_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vsr_srfbn_forward_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vsr_srfbn_kernel_class_name": (ctypes.c_char_p, [c_int]),
     "vsr_srfbn_profile_enable": (c_int, [c_void_p, c_int]),
     "vsr_srfbn_profile_read": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

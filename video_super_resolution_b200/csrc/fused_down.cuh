@@ -269,7 +269,7 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
           const uint64_t a0 = dA + (uint64_t)((s * kStageBytes) >> 4);
           const uint64_t b0 = dWt + (uint64_t)((j * kWtChunkBytes) >> 4);
           const uint32_t d0 = tmem_base + (uint32_t)(buf * 128 + pair * 64);
-          if (!(p.debug & 1)) {
+          if (!(VSR_DBG(p) & 1)) {
             const uint32_t acc = (uint32_t)(j != 0);
             umma_bf16(d0, a0, b0, idesc_a, acc);
             umma_bf16(d0, a0 + 2, b0 + 2, idesc_a, 1u);
@@ -299,7 +299,7 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
       tc_fence_after();
       const uint32_t d = tmem_base + kDB + (uint32_t)(tb * 128);
       const uint64_t b0 = dWd + (uint64_t)((wslot * kWdGroupBytes) >> 4);
-      if (!(p.debug & 8)) {
+      if (!(VSR_DBG(p) & 8)) {
 #pragma unroll
         for (int kc = 0; kc < 2; ++kc)
 #pragma unroll
@@ -373,10 +373,10 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
 #pragma unroll 1
         for (int g = 0; g < 4; ++g) {
           const int buf = g & 1;
-          mbar_wait_sleep(&da_full[buf], m_a[buf] & 1, (uint32_t)(p.debug >> 8));
+          mbar_wait_sleep(&da_full[buf], m_a[buf] & 1, (uint32_t)(VSR_DBG(p) >> 8));
           tc_fence_after();
           uint32_t o[16];
-          if (p.debug & 2) {
+          if (VSR_DBG(p) & 2) {
             zero16(o);
             tc_fence_before();
             mbar_arrive_warp(&da_empty[buf]);
@@ -419,9 +419,9 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
       //    with exactly one writer each:  slot 2*dy   : tap (dy,0) + right neighbour's tap (dy,1)
       //                                   slot 2*dy+1 : tap (dy,1) arriving from the next tile
       //    finalize_lr_kernel sums them.  Same additions in the same order either way: deterministic.
-      mbar_wait_sleep(&db_full[tb], m_b[tb] & 1, (uint32_t)(p.debug >> 8));
+      mbar_wait_sleep(&db_full[tb], m_b[tb] & 1, (uint32_t)(VSR_DBG(p) >> 8));
       tc_fence_after();
-      if (p.debug & 4) {
+      if (VSR_DBG(p) & 4) {
         tc_fence_before();
         mbar_arrive_warp(&db_empty[tb]);
       } else {

@@ -469,7 +469,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
             const int kc = kc0 + j;
             const uint64_t a0 = dA + (uint64_t)((s * p.stage_bytes + p.chunks[kc].a_off) >> 4);
             const uint64_t b0 = dB + (uint64_t)((kc * kBBytes) >> 4);
-            if (!(p.debug & 4))
+            if (!(VSR_DBG(p) & 4))
 #pragma unroll
             for (int k = 0; k < CK / 16; ++k) umma_bf16(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, (uint32_t)((kc | k) != 0));
           }
@@ -575,7 +575,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
           for (int c2 = 0; c2 < 2; ++c2) {
             const int cg = sub * 2 + c2;
             uint32_t v[32];
-            if (!(p.debug & 2)) {       // (the knock-out leaves v undefined; zeroing it here cost 32 CS2R per read even
+            if (!(VSR_DBG(p) & 2)) {       // (the knock-out leaves v undefined; zeroing it here cost 32 CS2R per read even
               tmem_ld32(taddr + cg * 32, v);   //  in production, ncu: 10 % of the kernel's instructions)
               tmem_ld_wait();
             }
@@ -583,7 +583,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
               tc_fence_before();
               mbar_arrive_warp(&tmem_empty[as]);
             }
-            if (p.debug & 2) continue;
+            if (VSR_DBG(p) & 2) continue;
             const int s16 = t.n_tile * 8 + cg;
             const int ry = s16 >> 2, rx = s16 & 3;
             const int Yt = 4 * Y + ry - 2, Xt = 4 * X + rx - 2;
@@ -607,9 +607,9 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
           if (lane == 0) {
             // one box = this warp's 2 block rows x 16 blocks of one sub-position-pair plane; rows or
             // columns beyond the tensor edge are clipped by the TMA unit
-            if (p.debug & 8)   // timing experiment: every tile stores to the first tile's place (L2-resident, no DRAM)
+            if (VSR_DBG(p) & 8)   // timing experiment: every tile stores to the first tile's place (L2-resident, no DRAM)
               tma_store_4d(&p.out_map, stg, 0, 0, 2 * q, t.n_tile * 4 + sub);
-            else if (t.y0 + 2 * q <= p.lr_h && !(p.debug & 1))
+            else if (t.y0 + 2 * q <= p.lr_h && !(VSR_DBG(p) & 1))
               tma_store_4d(&p.out_map, stg, 0, t.x0, t.y0 + 2 * q, t.b * 8 + t.n_tile * 4 + sub);
             tma_store_commit();
           }

@@ -300,8 +300,11 @@ int build_deconv(Layer& L, const void* x, int B, int h, int w, const void* w_dev
   p.lr_w = w;
   p.deconv_nhwc = nhwc;
   {
-    const char* e = getenv("VSR_DECONV_DEBUG");
+    const char* e = nullptr;
+#ifdef VSR_KNOCKOUT
+    e = getenv("VSR_DECONV_DEBUG");
     p.debug = e ? atoi(e) : 0;
+#endif
     e = getenv("VSR_DECONV_STAGES");     // tuning knob: ring depth (18 KB per stage)
     if (e && atoi(e) >= 1 && atoi(e) <= 5) p.num_stages = atoi(e);
   }
@@ -473,10 +476,12 @@ int build_fused_down(Layer& L, const void* const* hr, int nsrc, int B, int h, in
     const char* e = getenv("VSR_PREFETCH_AHEAD");   // tuning knob (half-tiles of L2 prefetch distance)
     f.prefetch_ahead = e ? atoi(e) : 0;   // measured: hurts (strided 64 B boxes over-fetch), see DESIGN.md
   }
+#ifdef VSR_KNOCKOUT
   {
     const char* e = getenv("VSR_FUSED_DEBUG");
     f.debug = e ? atoi(e) : 0;
   }
+#endif
   {
     const char* e = getenv("VSR_FUSED_STAGES");
     if (e && atoi(e) > 0 && atoi(e) <= (tran ? 7 : 5)) f.num_stages = atoi(e);
@@ -679,7 +684,11 @@ im2col_kernel(const float* __restrict__ x, const float* __restrict__ sub_bias, u
 // (SRProjectionModule.py:126-131,146).  maps (M,3,H,W) f32 -> y (1,3,H,W) f32.
 // fcw: [32*M fc0_w][32 fc0_b][32 fc2_w][1 fc2_b]
 __global__ void __launch_bounds__(256)
-fc_fuse_kernel(const float* __restrict__ maps, const float* __restrict__ fcw, float* __restrict__ y, int M, int64_t n) {
+fc_fuse_kernel(const float* __restrict__ maps, const float* __restrict__ fcw, float* __restrict__ y,
+               uint8_t* __restrict__ y_u8, int M, int64_t n) {
+  // y (3,H,W) f32 planar and / or y_u8 (H,W,3): the frame quantised the way the reference's loader stores frames
+  // (utils/video_utils.py:23): clamp to 0..255, round half to even -- what a u8 frame writer or gather needs,
+  // a quarter of the fp32 bytes.
   __shared__ float s_w[32 * kMaxMaps + 65];
   const int nw = 32 * M + 65;
   for (int i = threadIdx.x; i < nw; i += blockDim.x) s_w[i] = fcw[i];
@@ -727,7 +736,13 @@ fc_fuse_kernel(const float* __restrict__ maps, const float* __restrict__ fcw, fl
 #pragma unroll
       for (int k = 0; k < 4; ++k) o[k] = fmaf(w, fmaxf(hid[k][j], 0.0f), o[k]);
     }
-    reinterpret_cast<float4*>(y)[q] = make_float4(fmaxf(o[0], 0.0f), fmaxf(o[1], 0.0f), fmaxf(o[2], 0.0f), fmaxf(o[3], 0.0f));
+    if (y) reinterpret_cast<float4*>(y)[q] = make_float4(fmaxf(o[0], 0.0f), fmaxf(o[1], 0.0f), fmaxf(o[2], 0.0f), fmaxf(o[3], 0.0f));
+    if (y_u8) {
+      const int64_t hw = n / 3, i0 = q << 2;
+      const int64_t c = i0 / hw, p0 = i0 - c * hw;     // hw % 4 == 0 (16 HR pixels per LR pixel): the 4 outputs share c
+#pragma unroll
+      for (int k = 0; k < 4; ++k) y_u8[(p0 + k) * 3 + c] = (uint8_t)__float2int_rn(fminf(fmaxf(o[k], 0.0f), 255.0f));
+    }
   }
   // ragged tail (n is 48*h*w, a multiple of 4 for every LR size; kept for safety)
   for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -742,7 +757,11 @@ fc_fuse_kernel(const float* __restrict__ maps, const float* __restrict__ fcw, fl
     float o = b2;
 #pragma unroll
     for (int j = 0; j < 32; ++j) o = fmaf(w2[j], fmaxf(hid[j], 0.0f), o);
-    y[i] = fmaxf(o, 0.0f);
+    if (y) y[i] = fmaxf(o, 0.0f);
+    if (y_u8) {
+      const int64_t hw = n / 3, c = i / hw;
+      y_u8[(i - c * hw) * 3 + c] = (uint8_t)__float2int_rn(fminf(fmaxf(o, 0.0f), 255.0f));
+    }
   }
 }
 
@@ -1024,7 +1043,11 @@ extern "C" int vsr_srfbn_bind(vsr_srfbn_plan* pl, const void* dev_weights, void*
 }
 
 extern "C" int vsr_srfbn_forward(vsr_srfbn_plan* pl, const float* x, float* y, vsr_stream_t stream) {
-  if (!pl || !x || !y) return VSR_ERR_INVALID_ARG;
+  return vsr_srfbn_forward_u8(pl, x, y, nullptr, stream);
+}
+
+extern "C" int vsr_srfbn_forward_u8(vsr_srfbn_plan* pl, const float* x, float* y, uint8_t* y_u8, vsr_stream_t stream) {
+  if (!pl || !x || (!y && !y_u8)) return VSR_ERR_INVALID_ARG;
   if (!pl->bound) return VSR_ERR_STATE;
   cudaStream_t st = as_stream(stream);
   const vsr_srfbn_config& c = pl->cfg;
@@ -1054,7 +1077,7 @@ extern "C" int vsr_srfbn_forward(vsr_srfbn_plan* pl, const float* x, float* y, v
     int64_t blocks = ceil_div64(ceil_div64(n, 4), 256);
     if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
     cudaError_t e = launch_pdl(fc_fuse_kernel, (int)blocks, 256, 0, st, reinterpret_cast<const float*>(pl->ws + pl->o_premix),
-                               reinterpret_cast<const float*>(pl->dev_w + pl->fc_off), y, c.num_maps, n);
+                               reinterpret_cast<const float*>(pl->dev_w + pl->fc_off), y, y_u8, c.num_maps, n);
     if (e != cudaSuccess) return cuda_status(e);
     int rc = after_launch();
     if (rc) return rc;

@@ -24,7 +24,9 @@ assemble_stack_kernel(const float* __restrict__ warped,   // (T-1,h,w,3) NHWC
                       const float* __restrict__ proj,     // (T-1,h,w,2)
                       const float* __restrict__ resid,    // (T-1,h,w)
                       const float* __restrict__ depth,    // (T-1,h,w)
-                      const float* __restrict__ estimate, // (3,h,w) NCHW or nullptr (-> centre frame)
+                      const float* __restrict__ estimate, // (3,h,w) NCHW or nullptr (-> fallback frame)
+                      const float* __restrict__ fallback, // (h,w,3) NHWC: LR frame 0 of the window
+                                                          // (video_super_resolution.py:37-38 `data_clone[0:1]`)
                       float* __restrict__ stack, int T, int centre_idx, int64_t hw) {
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < hw; p += (int64_t)gridDim.x * blockDim.x) {
     const float c0 = __ldg(centre + p * 3), c1 = __ldg(centre + p * 3 + 1), c2 = __ldg(centre + p * 3 + 2);
@@ -48,7 +50,7 @@ assemble_stack_kernel(const float* __restrict__ warped,   // (T-1,h,w,3) NHWC
     }
     float* oe = stack + (int64_t)(3 * T - 2) * 3 * hw + p;
     if (estimate) { oe[0] = __ldg(estimate + p); oe[hw] = __ldg(estimate + hw + p); oe[2 * hw] = __ldg(estimate + 2 * hw + p); }
-    else { oe[0] = c0; oe[hw] = c1; oe[2 * hw] = c2; }
+    else { oe[0] = __ldg(fallback + p * 3); oe[hw] = __ldg(fallback + p * 3 + 1); oe[2 * hw] = __ldg(fallback + p * 3 + 2); }
   }
 }
 
@@ -78,15 +80,15 @@ inline int grid_for(int64_t n) {
 using namespace vsr;
 
 extern "C" int vsr_assemble_stack(const float* warped, const float* centre, const float* proj, const float* resid,
-                                  const float* depth, const float* estimate, float* stack, int T, int centre_idx, int h,
-                                  int w, vsr_stream_t stream) {
+                                  const float* depth, const float* estimate, const float* fallback, float* stack, int T,
+                                  int centre_idx, int h, int w, vsr_stream_t stream) {
   if (!warped || !centre || !proj || !resid || !depth || !stack || T < 2 || centre_idx < 0 || centre_idx >= T ||
-      h <= 0 || w <= 0)
+      h <= 0 || w <= 0 || (!estimate && !fallback))
     return VSR_ERR_INVALID_ARG;
   if (reinterpret_cast<uintptr_t>(proj) % 8) return VSR_ERR_INVALID_ARG;
   const int64_t hw = (int64_t)h * w;
   assemble_stack_kernel<<<grid_for(hw), kThreads, 0, as_stream(stream)>>>(warped, centre, proj, resid, depth, estimate,
-                                                                         stack, T, centre_idx, hw);
+                                                                         fallback, stack, T, centre_idx, hw);
   return after_launch();
 }
 

@@ -160,7 +160,11 @@ template <bool FAST>
 __global__ void __launch_bounds__(kThreads)
 warp_nhwc3_kernel(const float* __restrict__ src, const float* __restrict__ flow, float* __restrict__ dst,
                   const float* __restrict__ ref, float* __restrict__ norm_out,
-                  int64_t n_pix, int H, int W, int bilinear, int vec_store, const PixDecode pd) {
+                  int64_t n_pix, int H, int W, int bilinear, int vec_store, const PixDecode pd,
+                  int skip, int ref_shared) {
+  // skip >= 0 (window mode): batch item b samples image b of `src` when b < skip, else image b+1 -- the
+  // neighbours of a frame window with the centre frame left out, no gathered copy of the frames needed;
+  // ref_shared: every batch item is compared with the SAME reference image (the centre frame).
   __shared__ __align__(16) float stage[kThreads * 3];
   const int64_t HW = (int64_t)H * W;
   for (int64_t base = (int64_t)blockIdx.x * kThreads; base < n_pix; base += (int64_t)gridDim.x * kThreads) {
@@ -171,7 +175,7 @@ warp_nhwc3_kernel(const float* __restrict__ src, const float* __restrict__ flow,
       decode_pix((uint32_t)i, pd, bi, y, x);
       const int64_t b = bi;
       float2 f = ldg_stream_f2(reinterpret_cast<const float2*>(flow) + i);
-      const float* s = src + b * HW * 3;
+      const float* s = src + (b + ((skip >= 0 && bi >= skip) ? 1 : 0)) * HW * 3;
       if (bilinear) {
         Taps t = bilinear_taps<FAST>(x, y, f.x, f.y, W, H);
         const float* pTL = s + ((int64_t)t.yT * W + t.xL) * 3;
@@ -192,7 +196,7 @@ warp_nhwc3_kernel(const float* __restrict__ src, const float* __restrict__ flow,
       if (norm_out != nullptr) {
         // channelnorm_kernel.cu:53-59: fp32 `result += val*val` (an FMA under nvcc's default
         // contraction) in channel order, then sqrt.
-        const float* r = ref + i * 3;
+        const float* r = ref + (ref_shared ? (i - b * HW) : i) * 3;
         float d0 = __fsub_rn(__ldg(r), v0), d1 = __fsub_rn(__ldg(r + 1), v1), d2 = __fsub_rn(__ldg(r + 2), v2);
         float acc = fmaf(d0, d0, 0.0f);
         acc = fmaf(d1, d1, acc);
@@ -378,6 +382,29 @@ channelnorm_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, i
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Flow composition: out(p) = g(p) + f(p + g(p)), f sampled bilinearly with the warp's taps and border
+// rule (fast fp32 blend).  g maps the pixels of image A to image B, f the pixels of B to C: out maps A to C.
+// The pipeline chains the projected flows of the past frames / the forward flows of the future frames into
+// centre -> neighbour flows with it, one image per call.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+compose_flow_kernel(const float2* __restrict__ g, const float2* __restrict__ f, float2* __restrict__ out,
+                    int64_t n_pix, int H, int W, const PixDecode pd) {
+  const int64_t HW = (int64_t)H * W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pix; i += (int64_t)gridDim.x * blockDim.x) {
+    int x, y, bi;
+    decode_pix((uint32_t)i, pd, bi, y, x);
+    const float2 gv = g ? ldg_stream_f2(g + i) : make_float2(0.f, 0.f);   // g == NULL: the identity, out = f (a copy)
+    const float2* s = f + (int64_t)bi * HW;
+    const Taps t = bilinear_taps<true>(x, y, gv.x, gv.y, W, H);
+    const float2 tl = __ldg(s + (int64_t)t.yT * W + t.xL), tr = __ldg(s + (int64_t)t.yT * W + t.xR);
+    const float2 bl = __ldg(s + (int64_t)t.yB * W + t.xL), br = __ldg(s + (int64_t)t.yB * W + t.xR);
+    out[i] = make_float2(__fadd_rn(gv.x, blend_fast(t, tl.x, tr.x, bl.x, br.x)),
+                         __fadd_rn(gv.y, blend_fast(t, tl.y, tr.y, bl.y, br.y)));
+  }
+}
+
 inline int grid_for(int64_t work_items, int per_block) {
   int64_t blocks = ceil_div64(work_items, per_block);
   // enough CTAs for every SM to hold its full complement of 256-thread blocks (8/SM), a whole
@@ -400,6 +427,7 @@ extern "C" int vsr_resample2d_forward(const float* input1, const float* flow, fl
   if (!input1 || !flow || !output || B <= 0 || C <= 0 || H <= 0 || W <= 0) return VSR_ERR_INVALID_ARG;
   if (kernel_size != 1) return VSR_ERR_UNSUPPORTED;  // resample2d.py:44: the only value ever used
   int64_t n = (int64_t)B * H * W;
+  if (n >= ((int64_t)1 << 32)) return VSR_ERR_UNSUPPORTED;   // 32-bit index decode
   resample2d_nchw_kernel<<<grid_for(n, kThreads), kThreads, 0, as_stream(stream)>>>(input1, flow, output, B, C, H, W,
                                                                                    bilinear ? 1 : 0, make_pixdecode(H, W));
   return after_launch();
@@ -421,10 +449,10 @@ extern "C" int vsr_warp_nhwc_f32(const float* src, const float* flow, float* dst
     int vec = aligned(dst, 16) ? 1 : 0;
     if (bilinear == kModeFast)
       warp_nhwc3_kernel<true><<<grid_for(n_pix, kThreads), kThreads, 0, st>>>(src, flow, dst, ref, norm_out, n_pix, H, W,
-                                                                              1, vec, pd);
+                                                                              1, vec, pd, -1, 0);
     else
       warp_nhwc3_kernel<false><<<grid_for(n_pix, kThreads), kThreads, 0, st>>>(src, flow, dst, ref, norm_out, n_pix, H,
-                                                                               W, bilinear, vec, pd);
+                                                                               W, bilinear, vec, pd, -1, 0);
   } else if ((C % 4) == 0 && norm_out == nullptr && aligned(src, 16) && aligned(dst, 16)) {
     if (bilinear == kModeFast)
       warp_nhwc_vec4_kernel<true><<<grid_for(n_pix * (C / 4), kThreads), kThreads, 0, st>>>(src, flow, dst, n_pix, H, W,
@@ -439,11 +467,42 @@ extern "C" int vsr_warp_nhwc_f32(const float* src, const float* flow, float* dst
   return after_launch();
 }
 
+extern "C" int vsr_warp_window_nhwc3(const float* frames, const float* flows, float* warped, float* resid, int T,
+                                     int centre, int H, int W, int bilinear, vsr_stream_t stream) {
+  if (!frames || !flows || !warped || T < 2 || centre < 0 || centre >= T || H <= 0 || W <= 0) return VSR_ERR_INVALID_ARG;
+  if (bilinear < 0 || bilinear > kModeFast || !aligned(flows, 8)) return VSR_ERR_INVALID_ARG;
+  const int64_t n_pix = (int64_t)(T - 1) * H * W;
+  if (n_pix >= ((int64_t)1 << 32)) return VSR_ERR_UNSUPPORTED;
+  const PixDecode pd = make_pixdecode(H, W);
+  const float* ref = resid ? frames + (int64_t)centre * H * W * 3 : nullptr;
+  const int vec = aligned(warped, 16) ? 1 : 0;
+  cudaStream_t st = as_stream(stream);
+  if (bilinear == kModeFast)
+    warp_nhwc3_kernel<true><<<grid_for(n_pix, kThreads), kThreads, 0, st>>>(frames, flows, warped, ref, resid, n_pix, H, W,
+                                                                            1, vec, pd, centre, 1);
+  else
+    warp_nhwc3_kernel<false><<<grid_for(n_pix, kThreads), kThreads, 0, st>>>(frames, flows, warped, ref, resid, n_pix, H,
+                                                                             W, bilinear, vec, pd, centre, 1);
+  return after_launch();
+}
+
+extern "C" int vsr_compose_flow(const float* g, const float* f, float* out, int B, int H, int W, vsr_stream_t stream) {
+  if (!f || !out || B <= 0 || H <= 0 || W <= 0) return VSR_ERR_INVALID_ARG;
+  if (!aligned(g, 8) || !aligned(f, 8) || !aligned(out, 8)) return VSR_ERR_INVALID_ARG;
+  const int64_t n_pix = (int64_t)B * H * W;
+  if (n_pix >= ((int64_t)1 << 32)) return VSR_ERR_UNSUPPORTED;
+  compose_flow_kernel<<<grid_for(n_pix, kThreads), kThreads, 0, as_stream(stream)>>>(
+      reinterpret_cast<const float2*>(g), reinterpret_cast<const float2*>(f), reinterpret_cast<float2*>(out), n_pix, H, W,
+      make_pixdecode(H, W));
+  return after_launch();
+}
+
 extern "C" int vsr_warp_labels_u8(const uint8_t* labels, const float* flow, uint8_t* dst, int B, int H, int W,
                                   vsr_stream_t stream) {
   if (!labels || !flow || !dst || B <= 0 || H <= 0 || W <= 0) return VSR_ERR_INVALID_ARG;
   if (!aligned(flow, 8)) return VSR_ERR_INVALID_ARG;
   int64_t n_pix = (int64_t)B * H * W;
+  if (n_pix >= ((int64_t)1 << 32)) return VSR_ERR_UNSUPPORTED;   // 32-bit index decode
   int vec = (aligned(flow, 16) && aligned(dst, 8)) ? 1 : 0;
   warp_labels_kernel<<<grid_for(ceil_div64(n_pix, 8), kThreads), kThreads, 0, as_stream(stream)>>>(labels, flow, dst,
                                                                                                   n_pix, H, W, vec, make_pixdecode(H, W));

@@ -150,20 +150,30 @@ class SRProjectionModule(nn.Module):
             ent["version"] = ver
         return ent
 
-    def forward(self, x):
+    def forward(self, x, out_u8=None, want_f32=True):
+        """out_u8: optional (s*h, s*w, 3) u8 CUDA tensor that additionally receives the frame as clamp(y,0,255) rounded
+        half to even (the loader's pixel format, utils/video_utils.py:23), written by the fc-fuse kernel itself;
+        want_f32=False skips the fp32 frame (then the u8 frame is the only output and is what is returned)."""
         if not x.is_cuda:
             raise RuntimeError("SRProjectionModule: CUDA tensors only (no CPU fallback)")
         if x.dim() != 4 or x.shape[1] != 3 or x.shape[0] != self.num_maps:
             raise ValueError(f"SRProjectionModule: expected ({self.num_maps},3,h,w), got {tuple(x.shape)}")
-        x = x.to(torch.float32).contiguous()
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            x = x.to(torch.float32).contiguous()
         M, _, h, w = x.shape
         ent = self._plan_for(M, h, w, x.device)
         s = self.upscale_factor
-        y = torch.empty((1, 3, s * h, s * w), dtype=torch.float32, device=x.device)
+        if out_u8 is not None and (not out_u8.is_cuda or out_u8.dtype != torch.uint8 or not out_u8.is_contiguous()
+                                   or tuple(out_u8.shape) != (s * h, s * w, 3)):
+            raise ValueError(f"SRProjectionModule: out_u8 must be a contiguous CUDA u8 tensor of shape {(s * h, s * w, 3)}")
+        if out_u8 is None and not want_f32:
+            raise ValueError("SRProjectionModule: nothing to compute")
+        y = torch.empty((1, 3, s * h, s * w), dtype=torch.float32, device=x.device) if want_f32 else None
         with torch.cuda.device(x.device):
-            _lib.check(_lib.lib().vsr_srfbn_forward(ent["plan"], x.data_ptr(), y.data_ptr(),
-                                                    torch.cuda.current_stream().cuda_stream), "srfbn_forward")
-        return y
+            _lib.check(_lib.lib().vsr_srfbn_forward_u8(ent["plan"], x.data_ptr(), y.data_ptr() if y is not None else None,
+                                                       out_u8.data_ptr() if out_u8 is not None else None,
+                                                       torch.cuda.current_stream().cuda_stream), "srfbn_forward")
+        return y if want_f32 else out_u8
 
     def premix(self, x):
         """Test hook: per-map outputs before the fc fuse, (M,3,4h,4w) (SRProjectionModule.py:143)."""

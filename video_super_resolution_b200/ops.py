@@ -151,6 +151,46 @@ def warp(src: torch.Tensor, flow: torch.Tensor, bilinear: bool | int = True, ref
     return dst if ref is None else (dst, norm)
 
 
+def warp_window(frames: torch.Tensor, flows: torch.Tensor, centre: int, bilinear: bool | int = 2, want_resid: bool = True):
+    """The neighbour warp of one window in one launch: frames (T,H,W,3), flows (T-1,H,W,2) = one centre -> neighbour
+    field per neighbour (frame order, centre left out) -> warped (T-1,H,W,3) and, with want_resid, the per-pixel L2
+    norm of (frames[centre] - warped[n]) (T-1,H,W).  No gathered copy of the neighbours, no expanded reference."""
+    _req(frames, torch.float32, "frames")
+    _req(flows, torch.float32, "flows")
+    T, H, W, C = frames.shape
+    if C != 3 or tuple(flows.shape) != (T - 1, H, W, 2) or not 0 <= centre < T:
+        raise ValueError("warp_window: frames (T,H,W,3), flows (T-1,H,W,2), 0 <= centre < T expected")
+    warped = torch.empty((T - 1, H, W, 3), dtype=torch.float32, device=frames.device)
+    resid = torch.empty((T - 1, H, W), dtype=torch.float32, device=frames.device) if want_resid else None
+    with torch.cuda.device(frames.device):
+        _lib.check(_lib.lib().vsr_warp_window_nhwc3(frames.data_ptr(), flows.data_ptr(), warped.data_ptr(),
+                                                    resid.data_ptr() if resid is not None else None, T, int(centre), H, W,
+                                                    int(bilinear), _stream()), "warp_window")
+    return warped, resid
+
+
+def compose_flow(g: torch.Tensor, f: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """out(p) = g(p) + f(p + g(p)), f sampled bilinearly (border-clamped taps): g maps image A to B, f maps B to C,
+    out maps A to C.  g, f (B,H,W,2) or (H,W,2); g=None is the identity field (out = f, a copy by our own kernel)."""
+    _req(f, torch.float32, "f")
+    if g is not None:
+        _req(g, torch.float32, "g")
+    if (g is not None and g.shape != f.shape) or f.shape[-1] != 2 or f.dim() not in (3, 4):
+        raise ValueError("compose_flow: two (B,H,W,2) or (H,W,2) fields of the same shape expected")
+    B = f.shape[0] if f.dim() == 4 else 1
+    H, W = f.shape[-3], f.shape[-2]
+    if out is None:
+        out = torch.empty_like(f)
+    else:
+        _req(out, torch.float32, "out")
+        if out.shape != f.shape:
+            raise ValueError("compose_flow: out must have the shape of f")
+    with torch.cuda.device(f.device):
+        _lib.check(_lib.lib().vsr_compose_flow(g.data_ptr() if g is not None else None, f.data_ptr(), out.data_ptr(),
+                                               B, H, W, _stream()), "compose_flow")
+    return out
+
+
 def warp_labels(labels: torch.Tensor, flow: torch.Tensor) -> torch.Tensor:
     """Nearest label warp: labels (B,H,W) u8, flow (B,H,W,2) -> (B,H,W) u8, bit-exact."""
     _req(labels, torch.uint8, "labels")
@@ -176,9 +216,11 @@ def channelnorm(x: torch.Tensor, norm_deg: int = 2) -> torch.Tensor:
     return out
 
 
-def project_flow(flow: torch.Tensor, inv_depth: torch.Tensor | None = None):
+def project_flow(flow: torch.Tensor, inv_depth: torch.Tensor | None = None, max_disp: float | None = None):
     """Forward flow projection.  flow (B,h,w,2); inv_depth (B,h,w) or None.
-    Returns proj (B,h,w,2) f32, wsum (B,h,w) f32, count (B,h,w) i32, hole (B,h,w) u8."""
+    Returns proj (B,h,w,2) f32, wsum (B,h,w) f32, count (B,h,w) i32, hole (B,h,w) u8.
+    max_disp: a promised bound on |fx|, |fy| (<= 16 px) selects the shared-memory tile path; a broken promise is
+    detected on the device and costs time, never correctness.  None: no assumption (atomic scatter path)."""
     _req(flow, torch.float32, "flow")
     B, h, w, two = flow.shape
     if two != 2:
@@ -196,17 +238,18 @@ def project_flow(flow: torch.Tensor, inv_depth: torch.Tensor | None = None):
     with torch.cuda.device(dev):
         nbytes = int(L.vsr_flow_projection_workspace_bytes(B, h, w))
         ws = _workspace(nbytes, dev)
-        _lib.check(L.vsr_flow_projection_forward(flow.data_ptr(), inv_depth.data_ptr() if inv_depth is not None else None,
-                                                 proj.data_ptr(), wsum.data_ptr(), count.data_ptr(), hole.data_ptr(),
-                                                 ws.data_ptr(), ws.numel(), B, h, w, _stream()), "project_flow")
+        _lib.check(L.vsr_flow_projection_forward_bounded(
+            flow.data_ptr(), inv_depth.data_ptr() if inv_depth is not None else None, proj.data_ptr(), wsum.data_ptr(),
+            count.data_ptr(), hole.data_ptr(), ws.data_ptr(), ws.numel(), B, h, w,
+            -1.0 if max_disp is None else float(max_disp), _stream()), "project_flow")
     return proj, wsum, count, hole
 
 
-def project_depth_flow(flow: torch.Tensor, inv_depth: torch.Tensor):
+def project_depth_flow(flow: torch.Tensor, inv_depth: torch.Tensor, max_disp: float | None = None):
     """Inverse-depth-weighted projection (nearer surfaces dominate contested targets)."""
     if inv_depth is None:
         raise ValueError("project_depth_flow: inv_depth is required")
-    return project_flow(flow, inv_depth)
+    return project_flow(flow, inv_depth, max_disp)
 
 
 def flow_to_image(flow: torch.Tensor, out_size=None, want_u8: bool = True):
@@ -264,9 +307,11 @@ def mask_fill(image: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
 
 def assemble_stack(warped: torch.Tensor, centre: torch.Tensor, proj: torch.Tensor, resid: torch.Tensor,
                    depth: torch.Tensor, estimate: torch.Tensor | None, centre_idx: int,
-                   out: torch.Tensor | None = None) -> torch.Tensor:
+                   out: torch.Tensor | None = None, fallback: torch.Tensor | None = None) -> torch.Tensor:
     """One-pass assembly of the (3T-1,3,h,w) map stack (video_super_resolution.py:33-40).
-    warped (T-1,h,w,3), centre (h,w,3), proj (T-1,h,w,2), resid/depth (T-1,h,w), estimate (3,h,w)|None."""
+    warped (T-1,h,w,3), centre (h,w,3), proj (T-1,h,w,2), resid/depth (T-1,h,w), estimate (3,h,w)|None.
+    Without an estimate the last slot receives `fallback` (h,w,3): LR frame 0 of the window, as the reference's
+    `else data_clone[0:1]` (:37-38); `fallback=None` keeps the centre frame there."""
     for t, n in ((warped, "warped"), (centre, "centre"), (proj, "proj"), (resid, "resid"), (depth, "depth")):
         _req(t, torch.float32, n)
     Tm1, h, w, _ = warped.shape
@@ -278,12 +323,18 @@ def assemble_stack(warped: torch.Tensor, centre: torch.Tensor, proj: torch.Tenso
         _req(estimate, torch.float32, "estimate")
         if tuple(estimate.shape) != (3, h, w):
             raise ValueError("assemble_stack: estimate must be (3,h,w)")
+    if fallback is None:
+        fallback = centre
+    _req(fallback, torch.float32, "fallback")
+    if tuple(fallback.shape) != (h, w, 3):
+        raise ValueError("assemble_stack: fallback must be (h,w,3)")
     if out is None:
         out = torch.empty((3 * T - 1, 3, h, w), dtype=torch.float32, device=warped.device)
     with torch.cuda.device(warped.device):
         _lib.check(_lib.lib().vsr_assemble_stack(warped.data_ptr(), centre.data_ptr(), proj.data_ptr(), resid.data_ptr(),
                                                  depth.data_ptr(), estimate.data_ptr() if estimate is not None else None,
-                                                 out.data_ptr(), T, int(centre_idx), h, w, _stream()), "assemble_stack")
+                                                 fallback.data_ptr(), out.data_ptr(), T, int(centre_idx), h, w, _stream()),
+                   "assemble_stack")
     return out
 
 

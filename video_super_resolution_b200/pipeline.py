@@ -66,8 +66,18 @@ def shard_chunks_even(chunks, world_size: int, rank: int) -> list:
 
 
 class WarpFusePipeline:
+    """Geometry: flows[n] is the optical flow frame n -> n+1 in frame n's coordinates.  Its projection
+    (a1/a2) proj[n] lives in frame n+1's coordinates and points back to frame n.  Every neighbour is warped to the
+    CENTRE frame c = T//2 with a centre -> neighbour flow G:
+        past   frames t < c:  G[c-1] = proj[c-1],  G[t] = G[t+1] + proj[t](p + G[t+1])     (chain of projected flows)
+        future frames t > c:  G[c+1] = flows[c],   G[t] = G[t-1] + flows[t-1](p + G[t-1])   (chain of forward flows)
+    so warped[t](p) = frame[t](p + G[t](p)) is aligned with the centre frame, and the residual map of neighbour t is
+    |frame[c] - warped[t]|.  The VOS mask is taken to live in frame c-1 (the frame the segmentation was propagated
+    from) and is label-warped with G[c-1].  For the reference's T = 3 no chain is needed.
+    max_disp: a promised bound on the components of `flows` (px); selects the shared-memory projection path."""
+
     def __init__(self, T: int, h: int, w: int, sr: SRProjectionModule | None = None, scale: int = 4,
-                 device="cuda:0", run_fusion: bool = True):
+                 device="cuda:0", run_fusion: bool = True, max_disp: float | None = None):
         if T < 2:
             raise ValueError("window must hold at least 2 frames")
         self.T, self.h, self.w, self.scale = T, h, w, scale
@@ -75,36 +85,54 @@ class WarpFusePipeline:
         self.centre = T // 2
         self.device = torch.device(device)
         self.run_fusion = run_fusion
+        self.max_disp = max_disp
         self.sr = sr if sr is not None else SRProjectionModule(num_maps=self.M)
         if self.sr.num_maps != self.M:
             raise ValueError(f"SRProjectionModule.num_maps={self.sr.num_maps}, window needs {self.M}")
         self.stack = torch.empty((self.M, 3, h, w), dtype=torch.float32, device=self.device)
-        self._neigh = [t for t in range(T) if t != self.centre]
+        self.centre_flows = torch.empty((T - 1, h, w, 2), dtype=torch.float32, device=self.device)
 
-    def project_and_warp(self, frames, flows, inv_depth, logits_a, logits_b, estimate=None):
-        """a1-a5 + a7: fills self.stack; returns the intermediate results (for tests)."""
+    def chain_flows(self, proj, flows):
+        """Fills self.centre_flows (T-1,h,w,2): neighbour order = frame order with the centre left out."""
+        T, c, G = self.T, self.centre, self.centre_flows
+        ops.compose_flow(None, proj[c - 1], out=G[c - 1])
+        for t in range(c - 2, -1, -1):
+            ops.compose_flow(G[t + 1], proj[t], out=G[t])
+        if c + 1 < T:
+            ops.compose_flow(None, flows[c], out=G[c])               # frame c+1 is neighbour index c
+            for t in range(c + 2, T):
+                ops.compose_flow(G[t - 2], flows[t - 1], out=G[t - 1])
+        return G
+
+    def project_and_warp(self, frames, flows, inv_depth, logits_a, logits_b, estimate=None, estimate_hr=None):
+        """a1-a5 + a7: fills self.stack; returns the intermediate results (for tests).
+        estimate: (3,h,w) LR estimate | None; estimate_hr: (3,s*h,s*w) the previous output frame, downsized here
+        (video_super_resolution.py:35-37); neither: LR frame 0 (:38)."""
         T, c = self.T, self.centre
-        proj_f, _, cnt_f, hole_f = ops.project_flow(flows)
-        proj_d, wsum, cnt_d, hole_d = ops.project_depth_flow(flows, inv_depth)
-        neigh = frames[self._neigh].contiguous()
-        ref = frames[c].unsqueeze(0).expand(T - 1, -1, -1, -1).contiguous()
-        warped, resid = ops.warp(neigh, proj_d, 2, ref=ref)      # fast fp32 blend (north star: <= 1e-3)
+        proj_f, _, cnt_f, hole_f = ops.project_flow(flows, None, self.max_disp)
+        proj_d, wsum, cnt_d, hole_d = ops.project_depth_flow(flows, inv_depth, self.max_disp)
+        G = self.chain_flows(proj_d, flows)
+        warped, resid = ops.warp_window(frames, G, c, 2)          # fast fp32 blend (north star: <= 1e-3)
         mask = ops.vos_threshold(logits_a, logits_b)
-        mask_w = ops.warp_labels(mask.unsqueeze(0), proj_d[min(c, T - 2)].unsqueeze(0))[0]
-        ops.assemble_stack(warped, frames[c], proj_f, resid, wsum, estimate, c, out=self.stack)
+        mask_w = ops.warp_labels(mask.unsqueeze(0), G[c - 1].unsqueeze(0))[0]
+        ops.assemble_stack(warped, frames[c], proj_f, resid, wsum, estimate, c, out=self.stack, fallback=frames[0])
+        if estimate is None and estimate_hr is not None:
+            ops.estimate_slot(estimate_hr, None, self.stack[self.M - 1], self.scale)
         return {"proj_flow": proj_f, "count_flow": cnt_f, "hole_flow": hole_f, "proj_depth": proj_d, "wsum": wsum,
                 "count_depth": cnt_d, "hole_depth": hole_d, "warped": warped, "resid": resid, "mask": mask,
-                "mask_warped": mask_w}
+                "mask_warped": mask_w, "centre_flows": G}
 
-    def step(self, frames, flows, inv_depth, logits_a, logits_b, estimate=None):
+    def step(self, frames, flows, inv_depth, logits_a, logits_b, estimate=None, estimate_hr=None, out_u8=None,
+             want_f32=True):
         """frames (T,h,w,3) 0..255, flows (T-1,h,w,2), inv_depth (T-1,h,w), logits (h,w) x2,
-        estimate (3,h,w)|None -> SR frame (1,3,s*h,s*w) fp32."""
-        r = self.project_and_warp(frames, flows, inv_depth, logits_a, logits_b, estimate)
+        estimate (3,h,w)|None -> SR frame (1,3,s*h,s*w) fp32 [and / or out_u8 (s*h,s*w,3) u8].
+        Every kernel between the first and the last launch of a step is this library's."""
+        r = self.project_and_warp(frames, flows, inv_depth, logits_a, logits_b, estimate, estimate_hr)
         if not self.run_fusion:
             return self.stack
         out1 = self.sr(self.stack)                                             # pass 1
         ops.estimate_slot(out1[0], r["mask_warped"], self.stack[self.M - 1], self.scale)
-        return self.sr(self.stack)                                             # pass 2 (fuse)
+        return self.sr(self.stack, out_u8=out_u8, want_f32=want_f32)           # pass 2 (fuse)
 
 
 def quantise_u8(frame: torch.Tensor) -> torch.Tensor:
@@ -162,13 +190,15 @@ def run_sequence(vsr, frames, flows, inv_depth, logits, chunks, out: torch.Tenso
     h, w = frames.shape[1:3]
     if out is None:
         out = torch.empty((len(idx), s * h, s * w, 3), dtype=torch.uint8, device=frames.device)
+    pipe = vsr._pipe(h, w, frames.device)
     i = 0
     for c in chunks:
-        est = None
+        est = None                                                   # recurrence reset at every chunk start (main.py:196)
         for k in c:
             la, lb = logits(k)
-            y = vsr.forward_geometry(frames[k:k + T], flows[k:k + T - 1], inv_depth[k:k + T - 1], la, lb, est)
-            est = y
-            out[i] = y[0].clamp(0, 255).round().to(torch.uint8)      # (H,W,3) u8, utils/video_utils.py:23
+            # the previous output frame stays planar fp32 on the device and is downsized into the estimate slot by
+            # vsr_estimate_slot; the u8 frame (utils/video_utils.py:23) is written by the fc-fuse kernel itself
+            est = pipe.step(frames[k:k + T], flows[k:k + T - 1], inv_depth[k:k + T - 1], la, lb,
+                            estimate_hr=None if est is None else est[0], out_u8=out[i])
             i += 1
     return out, idx

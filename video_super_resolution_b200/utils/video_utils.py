@@ -114,20 +114,25 @@ class PinnedFrameRing:
         self.host = [torch.empty(shape, dtype=dtype).pin_memory() for _ in range(depth)]
         self.dev = [torch.empty(shape, dtype=dtype, device=self.device) for _ in range(depth)]
         self.free_ev = [None] * depth          # compute-side event: slot's device tensor no longer read
+        self.ready_ev = [None] * depth         # copy-side event: slot's previous H2D has left the host buffer
         self.stream = torch.cuda.Stream(device=self.device)
         self.k = 0
 
     def put(self, src: torch.Tensor):
         i = self.k % len(self.host)
         self.k += 1
+        if self.ready_ev[i] is not None:
+            self.ready_ev[i].synchronize()     # the slot's previous H2D may still be reading the pinned buffer (also
+                                               # when the caller never called release() for it)
         if self.free_ev[i] is not None:
-            self.free_ev[i].synchronize()      # the host buffer is about to be overwritten
+            self.free_ev[i].synchronize()      # the device tensor is about to be overwritten
             self.stream.wait_event(self.free_ev[i])
         self.host[i].copy_(src)
         with torch.cuda.stream(self.stream):
             self.dev[i].copy_(self.host[i], non_blocking=True)
             ready = torch.cuda.Event()
             ready.record(self.stream)
+        self.ready_ev[i] = ready
         return self.dev[i], ready, i
 
     def release(self, slot: int):
