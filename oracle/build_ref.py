@@ -63,6 +63,37 @@ def build():
     return True
 
 
+PY_WRAPPERS = {"resample2d": "resample2d_package/resample2d.py", "channelnorm": "channelnorm_package/channelnorm.py",
+               "correlation": "correlation_package/correlation.py"}
+
+
+def stage_py():
+    """Stages the reference's three autograd-Function wrappers (40-60 lines each) UNMODIFIED into oracle/_ref/pyref/
+    (git-ignored like the compiled ops; it travels to the GPU box with the tree, never into history), so that
+    tests/test_integration_gpu.py can run the reference's own `Resample2d` / `ChannelNorm` / `Correlation` classes over
+    the drop-in stubs of video_super_resolution_b200/integration/ -- the recipe of INTEGRATION.md 2, executed."""
+    if not os.path.isdir(REF):
+        return False
+    dst = os.path.join(OUT, "pyref")
+    os.makedirs(dst, exist_ok=True)
+    for name, rel in PY_WRAPPERS.items():
+        shutil.copy(os.path.join(REF, rel), os.path.join(dst, name + ".py"))
+    return True
+
+
+def load_py(name):
+    """Import a staged reference wrapper (resample2d / channelnorm / correlation) as a fresh module; its
+    `import <op>_cuda` resolves through sys.modules (the caller installs either the stubs or the reference ops)."""
+    import importlib.util
+    path = os.path.join(OUT, "pyref", name + ".py")
+    if not os.path.exists(path):
+        return None
+    spec = importlib.util.spec_from_file_location("ref_" + name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def load_ref(name):
     """Import a prebuilt reference op module (resample2d_cuda / channelnorm_cuda)."""
     import importlib.util
@@ -78,4 +109,6 @@ def load_ref(name):
 
 
 if __name__ == "__main__":
-    sys.exit(0 if build() else 1)
+    ok = build()
+    stage_py()
+    sys.exit(0 if ok else 1)

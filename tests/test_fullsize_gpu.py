@@ -84,6 +84,66 @@ def test_c2_conv_stack_full_size_is_deterministic_and_tiling_consistent():
     assert (a - b).abs().max().item() <= 1e-2 * (a.abs().mean().item() + 1.0)
 
 
+def _oracle_maps_on_gpu(x, sd, steps, scale):
+    """oracle/srfbn_oracle.forward_maps as the CHECKER, on the GPU in fp32 (TF32 off: cuDNN / cuBLAS fp32 FMA),
+    one map at a time so that the six HR feature maps and their concats stay small."""
+    from oracle import srfbn_oracle as so
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        sdc = {k: v.to(DEV, torch.float32) for k, v in sd.items()}
+        with torch.no_grad():
+            return torch.cat([so.forward_maps(x[m:m + 1], sdc, num_steps=steps, upscale=scale) for m in range(x.shape[0])])
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def _psnr255(a, b):
+    import math
+    mse = ((a.double() - b.double()) ** 2).mean().item()
+    return 10 * math.log10(255.0 ** 2 / max(mse, 1e-20))
+
+
+@pytest.mark.parametrize("name,M,h,w,scale", [("C2", 20, 270, 480, 4), ("C4crop", 14, 264, 328, 2)])
+def test_conv_stack_full_size_against_fp32_oracle(name, M, h, w, scale):
+    """The conv stack at C2's FULL size (M=20, 270x480 -> 1080x1920; tile-walk carries, the (h+1)x(w+1) block ring,
+    2.67 GB strides -- what a 24x40 case cannot reach) and on a >= 256x256 LR crop of C4 (x2, M=14) against the fp32
+    oracle: per-map PSNR > 50 dB and the north star's PSNR delta <= 0.05 dB against a common target ~35 dB away.
+    Same asserts as tests/test_srfbn_gpu.py::test_full_stack_against_oracle."""
+    import gc
+    from oracle import srfbn_oracle as so
+    gc.collect()
+    torch.cuda.empty_cache()
+    sd = so.init_state_dict(num_maps=M, seed=11, gain=2.3, upscale=scale)
+    gs = torch.Generator().manual_seed(99)
+    for k in sd:
+        if k.endswith(".1.weight"):
+            sd[k] = torch.rand(1, generator=gs) * 0.4 + 0.05             # distinct slopes: a mixed-up layer shows
+    mod = SRProjectionModule(num_maps=M, upscale_factor=scale)
+    mod.load_state_dict(sd)
+    x = (torch.rand((M, 3, h, w), generator=torch.Generator().manual_seed(5)) * 255).to(DEV)
+    got = mod.premix(x)
+    want = _oracle_maps_on_gpu(x, sd, 3, scale)
+    assert got.shape == want.shape == (M, 3, scale * h, scale * w) and torch.isfinite(got).all()
+    skip = torch.nn.functional.interpolate(x, scale_factor=scale, mode="bilinear", align_corners=False)
+    assert (want - skip).abs().mean().item() > 0.05                        # the conv branch carries signal
+    noise = torch.randn(want.shape[1:], generator=torch.Generator().manual_seed(6)).to(DEV) * 4.5
+    worst_psnr, worst_delta = 1e9, 0.0
+    for m in range(M):                                                     # per map
+        p = _psnr255(got[m], want[m])
+        target = want[m] + noise
+        d = abs(_psnr255(got[m], target) - _psnr255(want[m], target))
+        worst_psnr, worst_delta = min(worst_psnr, p), max(worst_delta, d)
+    assert worst_psnr > 50.0, f"{name}: worst per-map PSNR {worst_psnr:.2f} dB"
+    assert worst_delta <= 0.05, f"{name}: worst PSNR delta {worst_delta:.4f} dB"
+    # no tile / ring / edge artefact hides in the mean: the largest single-pixel error stays at the BF16 scale
+    assert (got - want).abs().max().item() <= 0.02 * (want.abs().mean().item() + 1.0) + 0.5
+    del mod, got, want, x, skip
+    gc.collect()
+    torch.cuda.empty_cache()
+
+
 def test_c5_window_sharding_matches_single_run_at_shard_starts():
     """C5 semantics at small size: a sequence processed in one go vs in two shards.  Within a shard the
     estimate of window k feeds window k+1 (main.py:199-203); a shard starts with estimated_image=None

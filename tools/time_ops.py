@@ -51,6 +51,11 @@ def main():
             f = f.to(DEV)
             report(f"flow_projection  B={B} {name}", timeit(lambda: ops.project_flow(f)), 21 * P)
             report(f"depth_projection B={B} {name}", timeit(lambda: ops.project_flow(f, inv)), 29 * P)
+            if name == "smooth8":
+                report(f"flow_projection  B={B} {name} bounded(8)", timeit(lambda: ops.project_flow(f, None, 8.0)), 21 * P)
+                report(f"depth_projection B={B} {name} bounded(8)", timeit(lambda: ops.project_flow(f, inv, 8.0)), 29 * P)
+                report(f"depth_projection B={B} {name} bounded(16)", timeit(lambda: ops.project_flow(f, inv, 16.0)), 29 * P)
+                report(f"depth_projection B={B} {name} bounded(4: broken promise)", timeit(lambda: ops.project_flow(f, inv, 4.0)), 29 * P)
         f = flows["smooth8"].to(DEV)
         src = (torch.rand((B, h, w, 3)) * 255).to(DEV)
         report(f"warp nhwc C=3 exact    B={B}", timeit(lambda: ops.warp(src, f)), 32 * P)

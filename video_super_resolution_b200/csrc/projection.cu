@@ -29,6 +29,8 @@
 //    (memset 6 + splat 13 + normalise 15 + fill 9-19 us at 1080p) and nothing overlapped.
 #include <cooperative_groups.h>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -78,7 +80,8 @@ __device__ __forceinline__ bool normalise_target(const float4 a, float2& o) {
   const bool is_hole = !(a.w > 0.0f) || !(a.z > 0.0f);
   o = make_float2(0.f, 0.f);
   if (!is_hole) {
-    const float rz = __frcp_rn(a.z);     // one reciprocal, two products: <= 1.5 ulp from the quotients
+    float rz;                            // one approximate reciprocal (1 ulp), two products: ~2 ulp from the quotients,
+    asm("rcp.approx.f32 %0, %1;" : "=f"(rz) : "f"(a.z));   // far inside the 1e-3 contract; no slow path
     o = make_float2(a.x * rz, a.y * rz);
   }
   return is_hole;
@@ -305,159 +308,262 @@ projection_pipeline_kernel(const ProjArgs a) {
   }
 }
 
+// The same stages as stand-alone kernels, each with its own register budget / occupancy (the merged kernel above runs
+// every role at 24 warps per SM; alone the splat keeps 64 in flight).  The general path launches them per image on
+// three internal streams, so that the stages of successive images overlap (see run_general).
+__global__ void __launch_bounds__(kThreads)
+stage_zero_kernel(float4* __restrict__ acc, int64_t n) {
+  role_zero(acc, n, (int64_t)blockIdx.x * kThreads + threadIdx.x, (int64_t)gridDim.x * kThreads);
+}
+__global__ void __launch_bounds__(kThreads)
+stage_splat_kernel(const float* __restrict__ flow, const float* __restrict__ inv_depth, float4* __restrict__ acc, int h, int w) {
+  role_splat(flow, inv_depth, acc, h, w, (blockIdx.x * kThreads + threadIdx.x) >> 5, (gridDim.x * kThreads) >> 5, threadIdx.x & 31);
+}
+__global__ void __launch_bounds__(kThreads, 4)
+stage_normalise_kernel(const float4* __restrict__ acc, float* __restrict__ proj, float* __restrict__ wsum,
+                       int32_t* __restrict__ count, uint8_t* __restrict__ hole, uint32_t* __restrict__ rowmask,
+                       uint32_t* __restrict__ colmask, int* __restrict__ has_holes, int h, int w) {
+  role_normalise(acc, proj, wsum, count, hole, rowmask, colmask, has_holes, h, w, (blockIdx.x * kThreads + threadIdx.x) >> 5,
+                 (gridDim.x * kThreads) >> 5, threadIdx.x & 31);
+}
+__global__ void __launch_bounds__(kThreads)
+stage_fill_kernel(const uint32_t* rowmask, const uint32_t* colmask, const int* has_holes, float* proj, int h, int w) {
+  if (*reinterpret_cast<const volatile int*>(has_holes) == 0) return;
+  role_fill(rowmask, colmask, proj, h, w, (blockIdx.x * kThreads + threadIdx.x) >> 5, (gridDim.x * kThreads) >> 5,
+            threadIdx.x & 31);
+}
+
 // ---------------------------------------------------------------------------------------------
 // BOUNDED path: owner-computes tiles in shared memory.
 // ---------------------------------------------------------------------------------------------
-constexpr int kTileThreads = 384;                 // 12 warps
+constexpr int kTileWarps = 13;                    // 12 rectangle warps + 1 for the tile's left halo column
+constexpr int kTileThreads = 32 * kTileWarps;
 constexpr int kTileW = 192, kTileH = 64;          // targets per tile = 6 x 2 output sub-blocks of 32 x 32
 constexpr int kCellW = kTileW + 1, kCellH = kTileH + 1;   // + the column to the left and the row above
 constexpr int kCells = kCellW * kCellH;           // 12 545 cells: 200 720 B of float4 + 12 545 B of claim bytes
 constexpr int kMaxBound = 16;
-constexpr size_t kTileSmem = (size_t)kCells * 16 + ((kCells + 15) / 16) * 16;
+constexpr int kSB = 4;                            // batches of 32 sources handled together (one claim round, 4 RMWs in flight)
+constexpr size_t kTileSmem = (size_t)(kCells + 1) * 16 + ((kCells + 1 + 15) / 16) * 16;   // + the dummy cell / claim byte
+
+// A warp's source window is walked row by row, 32 lanes x `n_chunks` per row (64 wide for a bound of 8 = two full
+// chunks; the halo-column warp's window is 2*bound+1 wide: one chunk, half the lanes idle, but the same number of
+// batches as everybody else).  The batch -> (row, chunk) bookkeeping is warp-uniform and incremental; a lane adds
+// its own fixed column.  (ncu on the first versions: per-lane divisions / wrap loops, int->float conversions,
+// 64-bit index arithmetic and the branches around predicated shared-memory accesses were most of the instructions.)
+struct Walk {
+  int n_chunks, n_rows, n_cols;
+  int off0;                  // y*w + x of (first row, this lane's column in chunk 0)
+  float x0, y0;              // the same position as floats
+  int w;
+};
+struct WalkPos {             // warp-uniform cursor
+  int row, chunk;
+  __device__ __forceinline__ void step(const Walk& wk) {
+    if (++chunk == wk.n_chunks) { chunk = 0; ++row; }
+  }
+};
+
+struct SrcBatch {       // kSB x 32 sources in registers (invalid sources: flow 0, depth 1)
+  float2 f[kSB];
+  float d[kSB];
+};
+
+__device__ __forceinline__ void load_batch(SrcBatch& s, const Walk& wk, WalkPos& wp, int lane,
+                                           const float2* __restrict__ flow, const float* __restrict__ depth) {
+#pragma unroll
+  for (int u = 0; u < kSB; ++u) {
+    const bool ok = wp.row < wk.n_rows && lane + 32 * wp.chunk < wk.n_cols;
+    const int off = wk.off0 + wp.row * wk.w + 32 * wp.chunk;
+    s.f[u] = make_float2(0.f, 0.f);
+    s.d[u] = 1.0f;
+    if (ok) {
+      s.f[u] = __ldg(flow + off);
+      if (depth) s.d[u] = __ldg(depth + off);
+    }
+    wp.step(wk);
+  }
+}
+
+// Adds the batch's sources that land in [xa,xb] x [ya,yb] (= this warp's cells, inside the image) to the cells.
+// The cells are this warp's alone: plain read-modify-write, no atomics.  Sources of one batch that hit the SAME cell
+// take turns: everybody writes its id (sub-batch, lane) to the cell's claim byte, the survivor goes.  Winners
+// therefore hold distinct cells, so their four RMWs are independent and overlap.  Everything is branch-free: a source
+// with nothing to add (outside the rectangle, or it lost the claim) reads, "updates" and writes a dummy cell.
+__device__ __forceinline__ void add_batch(const SrcBatch& cur, const Walk& wk, WalkPos& wp, float4* s_cells,
+                                          uint8_t* s_claim, float xa, float xb, float ya, float yb, int cell_org,
+                                          int lane, float& vmax) {
+  int cell[kSB];
+  bool pend[kSB];
+  float vx[kSB], vy[kSB];
+#pragma unroll
+  for (int u = 0; u < kSB; ++u) {
+    const float fx = cur.f[u].x, fy = cur.f[u].y;
+    const bool ok = wp.row < wk.n_rows && lane + 32 * wp.chunk < wk.n_cols;
+    const float x2 = __fadd_rn(wk.x0 + (float)(32 * wp.chunk), fx), y2 = __fadd_rn(wk.y0 + (float)wp.row, fy);
+    wp.step(wk);
+    vmax = fmaxf(vmax, fmaxf(fabsf(fx), fabsf(fy)));
+    pend[u] = ok && x2 >= xa && x2 <= xb && y2 >= ya && y2 <= yb;
+    cell[u] = pend[u] ? (int)y2 * kCellW + (int)x2 - cell_org : kCells;     // kCells: the dummy cell / claim byte
+    vx[u] = __fmul_rn(-fx, cur.d[u]);
+    vy[u] = __fmul_rn(-fy, cur.d[u]);
+  }
+  bool again;
+  do {
+#pragma unroll
+    for (int u = 0; u < kSB; ++u) s_claim[cell[u]] = (uint8_t)(u * 32 + lane);
+    __syncwarp();
+    uint8_t who[kSB];
+#pragma unroll
+    for (int u = 0; u < kSB; ++u) who[u] = s_claim[cell[u]];
+    int idx[kSB];
+    float4 c[kSB];
+    bool left = false;
+#pragma unroll
+    for (int u = 0; u < kSB; ++u) {
+      const bool win = pend[u] && who[u] == (uint8_t)(u * 32 + lane);
+      idx[u] = win ? cell[u] : kCells;
+      pend[u] = pend[u] && !win;
+      left |= pend[u];
+    }
+#pragma unroll
+    for (int u = 0; u < kSB; ++u) c[u] = s_cells[idx[u]];
+#pragma unroll
+    for (int u = 0; u < kSB; ++u) {
+      c[u].x += vx[u]; c[u].y += vy[u]; c[u].z += cur.d[u]; c[u].w += 1.0f;
+      s_cells[idx[u]] = c[u];
+    }
+    again = __any_sync(0xffffffffu, left);
+    __syncwarp();
+  } while (again);
+}
 
 __global__ void __launch_bounds__(kTileThreads, 1)
 projection_tiled_kernel(const ProjArgs a) {
   extern __shared__ float4 s_cells[];
-  uint8_t* s_claim = reinterpret_cast<uint8_t*>(s_cells + kCells);
+  uint8_t* s_claim = reinterpret_cast<uint8_t*>(s_cells + kCells + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = a.h, w = a.w, D = a.bound;
   const int tiles_x = ceil_div(w, kTileW), tiles_y = ceil_div(h, kTileH);
   const int n_tiles = tiles_x * tiles_y * a.B;
-  const int64_t P = (int64_t)h * w;
-  const float xmax = (float)(w - 1), ymax = (float)(h - 1), fD = (float)D;
+  const int P = h * w;                            // <= 2^30
+  const float xmax = (float)(w - 1), ymax = (float)(h - 1);
   const int rw_x = ceil_div(w, 32);
-  const int64_t rw = rowmask_words(h, w), cw = colmask_words(h, w);
-  // accumulation rectangle of this warp inside the cell tile: 4 x 3 rectangles of 48(49) x 22(21) cells
+  const int rw = h * rw_x, cw = ceil_div(h, 32) * w;
+  // accumulation rectangle of this warp inside the 193 x 65 cell tile: warps 0-11 take 4 x 3 rectangles of 48 x
+  // 22(21) cells over local columns 1..192, warp 12 the left halo column (local column 0, all 65 rows)
+  const bool halo = warp == 12;
   const int bx = warp & 3, by = warp >> 2;
-  const int cx_lo = 48 * bx, cx_hi = bx == 3 ? kCellW : 48 * (bx + 1);
-  const int cy_lo = 22 * by, cy_hi = by == 2 ? kCellH : 22 * (by + 1);
-  // output sub-block of this warp: 32 x 32 targets
+  const int cx_lo = halo ? 0 : 1 + 48 * bx, cx_hi = halo ? 1 : 49 + 48 * bx;
+  const int cy_lo = halo ? 0 : 22 * by, cy_hi = halo ? kCellH : (by == 2 ? kCellH : 22 * (by + 1));
+  // output sub-block of warps 0-11: 32 x 32 targets
   const int ox = (warp % 6) * 32, oy = (warp / 6) * 32;
-  bool broke = false;
+  float vmax = 0.0f;                              // largest |flow component| this thread has looked at
 
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int tb = tile / (tiles_x * tiles_y);
     const int tr = tile - tb * tiles_x * tiles_y;
     const int tx0 = (tr % tiles_x) * kTileW, ty0 = (tr / tiles_x) * kTileH;   // first target of the tile
-    const float2* flow = reinterpret_cast<const float2*>(a.flow) + tb * P;
-    const float* depth = a.inv_depth ? a.inv_depth + tb * P : nullptr;
+    const float2* flow = reinterpret_cast<const float2*>(a.flow) + (int64_t)tb * P;
+    const float* depth = a.inv_depth ? a.inv_depth + (int64_t)tb * P : nullptr;
 
     for (int i = threadIdx.x; i < kCells; i += kTileThreads) s_cells[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
 
-    // ---- accumulate: sources of the window [rectangle - D, rectangle + D] (global cell (cy,cx) = local + (ty0-1, tx0-1))
+    // ---- accumulate: sources of the window [rectangle - D, rectangle + D]; global cell = local + (ty0-1, tx0-1)
     {
-      const int gx_lo = max(tx0 - 1 + cx_lo - D, 0), gx_hi = min(tx0 - 1 + cx_hi - 1 + D, w - 1);   // inclusive
-      const int gy_lo = max(ty0 - 1 + cy_lo - D, 0), gy_hi = min(ty0 - 1 + cy_hi - 1 + D, h - 1);
+      const int gcx_lo = tx0 - 1 + cx_lo, gcx_hi = tx0 - 1 + cx_hi;       // this warp's cells, global, hi exclusive
+      const int gcy_lo = ty0 - 1 + cy_lo, gcy_hi = ty0 - 1 + cy_hi;
+      const int gx_lo = max(gcx_lo - D, 0), gx_hi = min(gcx_hi - 1 + D, w - 1);   // source window, inclusive
+      const int gy_lo = max(gcy_lo - D, 0), gy_hi = min(gcy_hi - 1 + D, h - 1);
       const int Ws = gx_hi - gx_lo + 1, Hs = gy_hi - gy_lo + 1;
-      const int N = (Ws > 0 && Hs > 0) ? Ws * Hs : 0;
-      const float inv_ws = Ws > 0 ? 1.0f / (float)Ws : 0.f;
-      constexpr int U = 4;
-      for (int i0 = 0; i0 < N; i0 += 32 * U) {
-        float2 f[U];
-        float d[U];
-        int sx[U], sy[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int idx = i0 + u * 32 + lane;
-          // row-major walk of the window; (idx + 0.5) / Ws is never within rounding of an integer for idx < 2^20
-          const int r = (int)(((float)idx + 0.5f) * inv_ws);
-          sy[u] = gy_lo + r;
-          sx[u] = gx_lo + idx - r * Ws;
-          f[u] = make_float2(0.f, 0.f);
-          d[u] = 1.0f;
-          if (idx < N) {
-            const int64_t sp = (int64_t)sy[u] * w + sx[u];
-            f[u] = __ldg(flow + sp);
-            if (depth) d[u] = __ldg(depth + sp);
-          } else {
-            sx[u] = -1;
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (i0 + u * 32 >= N) break;      // warp-uniform
-          const bool valid = sx[u] >= 0;
-          const float x2 = __fadd_rn((float)sx[u], f[u].x);
-          const float y2 = __fadd_rn((float)sy[u], f[u].y);
-          broke |= valid && (fabsf(f[u].x) > fD || fabsf(f[u].y) > fD);
-          const bool ok = valid && x2 >= 0.0f && x2 <= xmax && y2 >= 0.0f && y2 <= ymax;
-          const int cx = (int)x2 - (tx0 - 1), cy = (int)y2 - (ty0 - 1);
-          bool pending = ok && cx >= cx_lo && cx < cx_hi && cy >= cy_lo && cy < cy_hi;
-          const int cell = cy * kCellW + cx;
-          const float4 v = make_float4(__fmul_rn(-f[u].x, d[u]), __fmul_rn(-f[u].y, d[u]), d[u], 1.0f);
-          // the rectangle's cells are this warp's alone: plain read-modify-write.  Lanes of this instruction that hit
-          // the same cell take turns: everybody writes its lane number to the cell's claim byte, the survivor goes.
-          while (__any_sync(0xffffffffu, pending)) {
-            if (pending) s_claim[cell] = (uint8_t)lane;
-            __syncwarp();
-            const bool win = pending && s_claim[cell] == (uint8_t)lane;
-            if (win) {
-              float4 c = s_cells[cell];
-              c.x += v.x; c.y += v.y; c.z += v.z; c.w += v.w;
-              s_cells[cell] = c;
-              pending = false;
-            }
-            __syncwarp();
-          }
-        }
+      const bool any = Ws > 0 && Hs > 0 && gcx_hi > 0 && gcy_hi > 0;
+      // "lands in one of my cells and inside the image" as four float compares on the target position (x2, y2):
+      // int(x2) in [lo, hi) <=> lo <= x2 < hi for x2 >= 0; `x2 < hi` is `x2 <= pred(hi)`, and at the image edge the
+      // bound is Appendix B's x2 <= w-1.  NaN fails every compare.
+      const float xa = (float)max(gcx_lo, 0), xb = gcx_hi <= w - 1 ? nextafterf((float)gcx_hi, 0.0f) : xmax;
+      const float ya = (float)max(gcy_lo, 0), yb = gcy_hi <= h - 1 ? nextafterf((float)gcy_hi, 0.0f) : ymax;
+      const int cell_org = (ty0 - 1) * kCellW + (tx0 - 1);
+      Walk wk;
+      wk.n_cols = Ws;
+      wk.n_rows = any ? Hs : 0;
+      wk.n_chunks = max(ceil_div(Ws, 32), 1);
+      wk.off0 = gy_lo * w + gx_lo + lane;
+      wk.x0 = (float)(gx_lo + lane);
+      wk.y0 = (float)gy_lo;
+      wk.w = w;
+      const int nb = wk.n_rows * wk.n_chunks;
+      // three register buffers: the loads of the next two batches fly under the arithmetic of the current one
+      // (ncu: with one batch of look-ahead a fifth of the stall samples still sat on the first use of a load)
+      SrcBatch b0, b1, b2;
+      WalkPos lp = {0, 0}, ap = {0, 0};          // load cursor, add cursor
+      if (nb > 0) load_batch(b0, wk, lp, lane, flow, depth);
+      if (nb > kSB) load_batch(b1, wk, lp, lane, flow, depth);
+      for (int j = 0; j < nb; j += 3 * kSB) {
+        if (j + 2 * kSB < nb) load_batch(b2, wk, lp, lane, flow, depth);
+        add_batch(b0, wk, ap, s_cells, s_claim, xa, xb, ya, yb, cell_org, lane, vmax);
+        if (j + kSB >= nb) break;
+        if (j + 3 * kSB < nb) load_batch(b0, wk, lp, lane, flow, depth);
+        add_batch(b1, wk, ap, s_cells, s_claim, xa, xb, ya, yb, cell_org, lane, vmax);
+        if (j + 2 * kSB >= nb) break;
+        if (j + 4 * kSB < nb) load_batch(b1, wk, lp, lane, flow, depth);
+        add_batch(b2, wk, ap, s_cells, s_claim, xa, xb, ya, yb, cell_org, lane, vmax);
       }
     }
     __syncthreads();
 
     // ---- output: 32 x 32 targets per warp, lane = column, rows walked; local cell of target (ty,tx) = (ty+1-ty0, tx+1-tx0)
-    {
+    if (!halo && ty0 + oy < h && tx0 + ox < w) {
       const int x = tx0 + ox + lane;
       const bool in_x = x < w;
       const float mx = (x == w - 1) ? 2.0f : 1.0f;
-      const int lx = ox + lane + 1;
-      float4 up = s_cells[oy * kCellW + lx];
-      float4 up_left = s_cells[oy * kCellW + lx - 1];
+      const float4* col = s_cells + oy * kCellW + ox + lane + 1;     // cell (row above the first target, this column)
+      float4 up = col[0];
+      float4 up_left = col[-1];
       uint32_t colbits = 0;
       bool any_hole = false;
-      float* proj = a.proj + tb * P * 2;
-      float* wsum = a.wsum ? a.wsum + tb * P : nullptr;
-      int32_t* count = a.count + tb * P;
-      uint8_t* hole = a.hole + tb * P;
-      if (ty0 + oy < h && tx0 + ox < w) {
-#pragma unroll 4
-        for (int r = 0; r < 32; ++r) {
-          const int y = ty0 + oy + r;
-          const float4 c11 = s_cells[(oy + r + 1) * kCellW + lx];
-          float4 c10 = shfl_up1_f4(c11);
-          if (lane == 0) c10 = s_cells[(oy + r + 1) * kCellW + lx - 1];
-          const float4 c01 = up, c00 = up_left;
-          up = c11;
-          up_left = c10;
-          const bool in_img = in_x && y < h;
-          bool is_hole = false;
-          if (in_img) {
-            const float my = (y == h - 1) ? 2.0f : 1.0f;
-            float4 t;
-            t.x = (c11.x * mx + c10.x) * my + (c01.x * mx + c00.x);
-            t.y = (c11.y * mx + c10.y) * my + (c01.y * mx + c00.y);
-            t.z = (c11.z * mx + c10.z) * my + (c01.z * mx + c00.z);
-            t.w = (c11.w * mx + c10.w) * my + (c01.w * mx + c00.w);
-            const int64_t p = (int64_t)y * w + x;
-            float2 o;
-            is_hole = normalise_target(t, o);
-            reinterpret_cast<float2*>(proj)[p] = o;
-            if (wsum) wsum[p] = is_hole ? 0.0f : t.z;
-            count[p] = (int32_t)t.w;
-            hole[p] = is_hole ? 1 : 0;
-          }
-          const uint32_t m = __ballot_sync(0xffffffffu, in_img && !is_hole);
-          if (lane == 0 && y < h) a.rowmask[tb * rw + (int64_t)y * rw_x + ((tx0 + ox) >> 5)] = m;
-          colbits |= (uint32_t)(in_img && !is_hole) << r;
-          any_hole |= in_img && is_hole;
+      const int64_t img = (int64_t)tb * P;
+      float2* proj = reinterpret_cast<float2*>(a.proj) + img;
+      float* wsum = a.wsum ? a.wsum + img : nullptr;
+      int32_t* count = a.count + img;
+      uint8_t* hole = a.hole + img;
+      uint32_t* rowm = a.rowmask + (int64_t)tb * rw + ((tx0 + ox) >> 5);
+      const int rows = min(32, h - (ty0 + oy));
+      int p = (ty0 + oy) * w + x;
+      for (int r = 0; r < rows; ++r, p += w) {
+        col += kCellW;
+        const float4 c11 = col[0];
+        float4 c10 = shfl_up1_f4(c11);
+        if (lane == 0) c10 = col[-1];
+        const float4 c01 = up, c00 = up_left;
+        up = c11;
+        up_left = c10;
+        const float my = (ty0 + oy + r == h - 1) ? 2.0f : 1.0f;
+        float4 t;
+        t.x = fmaf(fmaf(c11.x, mx, c10.x), my, fmaf(c01.x, mx, c00.x));
+        t.y = fmaf(fmaf(c11.y, mx, c10.y), my, fmaf(c01.y, mx, c00.y));
+        t.z = fmaf(fmaf(c11.z, mx, c10.z), my, fmaf(c01.z, mx, c00.z));
+        t.w = fmaf(fmaf(c11.w, mx, c10.w), my, fmaf(c01.w, mx, c00.w));
+        bool is_hole = false;
+        if (in_x) {
+          float2 o;
+          is_hole = normalise_target(t, o);
+          proj[p] = o;
+          if (wsum) wsum[p] = is_hole ? 0.0f : t.z;
+          count[p] = (int32_t)t.w;
+          hole[p] = is_hole ? 1 : 0;
         }
-        if (in_x) a.colmask[tb * cw + (int64_t)((ty0 + oy) >> 5) * w + x] = colbits;
-        if (__any_sync(0xffffffffu, any_hole) && lane == 0) *reinterpret_cast<volatile int*>(a.flags + 1 + tb) = 1;
+        const uint32_t m = __ballot_sync(0xffffffffu, in_x && !is_hole);
+        if (lane == 0) rowm[(ty0 + oy + r) * rw_x] = m;
+        colbits |= (uint32_t)(in_x && !is_hole) << r;
+        any_hole |= in_x && is_hole;
       }
+      if (in_x) a.colmask[(int64_t)tb * cw + ((ty0 + oy) >> 5) * w + x] = colbits;
+      if (__any_sync(0xffffffffu, any_hole) && lane == 0) *reinterpret_cast<volatile int*>(a.flags + 1 + tb) = 1;
     }
     __syncthreads();
   }
-  if (__any_sync(0xffffffffu, broke) && lane == 0) *reinterpret_cast<volatile int*>(a.flags) = 1;
+  // a source beyond the promised bound: the windows above may have missed cells it reaches -> redo by the general path
+  if (__any_sync(0xffffffffu, vmax > (float)D) && lane == 0) *reinterpret_cast<volatile int*>(a.flags) = 1;
 }
 
 // fill of the bounded path: all images in one launch; nothing to do for an image without holes, and nothing at all
@@ -519,6 +625,78 @@ int launch_pipeline(const ProjArgs& a, cudaStream_t st) {
   return after_launch();
 }
 
+// Internal fork/join resources of the general path, one set per device, created on first use and never destroyed.
+// (The library still owns no device MEMORY: accumulators and bitmaps live in the caller's workspace.)
+constexpr int kLanes = 3;
+struct ForkJoin {
+  bool ok = false;
+  cudaStream_t stream[kLanes];
+  cudaEvent_t start, done[kLanes];
+};
+ForkJoin* fork_join() {
+  static std::mutex mu;
+  static ForkJoin per_dev[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  ForkJoin& f = per_dev[dev];
+  if (!f.ok) {
+    for (int i = 0; i < kLanes; ++i) {
+      if (cudaStreamCreateWithFlags(&f.stream[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+      if (cudaEventCreateWithFlags(&f.done[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    if (cudaEventCreateWithFlags(&f.start, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    f.ok = true;
+  }
+  return &f;
+}
+std::mutex g_enqueue_mu;   // one enqueue at a time: the fork/join events are shared by all callers of a device
+
+// General path: per image zero -> splat -> normalise -> fill, each kernel at its own occupancy; image b runs on
+// internal stream b % 3 with cell array b % 3, forked from and joined to the caller's stream with events, so the
+// stages of three successive images are in flight together (alone they are latency- / issue-bound, not HBM-bound).
+int run_general(const ProjArgs& a, cudaStream_t user) {
+  ForkJoin* fj = fork_join();
+  if (!fj) return VSR_ERR_STATE;
+  std::lock_guard<std::mutex> lock(g_enqueue_mu);
+  const int h = a.h, w = a.w;
+  const int64_t P = (int64_t)h * w;
+  const int64_t rw = (int64_t)h * ceil_div(w, 32), cw = (int64_t)ceil_div(h, 32) * w;
+  const int lanes = a.B < kLanes ? a.B : kLanes;
+  cudaError_t e = cudaMemsetAsync(a.flags + 1, 0, (size_t)a.B * 4, user);
+  if (e != cudaSuccess) return cuda_status(e);
+  if ((e = cudaEventRecord(fj->start, user)) != cudaSuccess) return cuda_status(e);
+  for (int i = 0; i < lanes; ++i)
+    if ((e = cudaStreamWaitEvent(fj->stream[i], fj->start, 0)) != cudaSuccess) return cuda_status(e);
+  const int n_tasks = ceil_div(w, 32) * ceil_div(h, kRows);
+  const int splat_blocks = ceil_div(n_tasks, kThreads / 32);
+  const int norm_blocks = ceil_div(ceil_div(w, 32) * 2 * ceil_div(h, 32), kThreads / 32);
+  const int fill_blocks = ceil_div(h * ceil_div(w, 32), kThreads / 32);   // one warp per 32-pixel row word
+  int64_t zb = ceil_div64(P, kThreads * 4);
+  const int zero_blocks = (int)(zb > kNumSMs * 8 ? kNumSMs * 8 : (zb < 1 ? 1 : zb));
+  for (int b = 0; b < a.B; ++b) {
+    cudaStream_t st = fj->stream[b % kLanes];
+    float4* acc = a.acc + (b % kLanes) * P;
+    stage_zero_kernel<<<zero_blocks, kThreads, 0, st>>>(acc, P);
+    int rc = after_launch();
+    if (rc) return rc;
+    stage_splat_kernel<<<splat_blocks, kThreads, 0, st>>>(a.flow + b * P * 2, a.inv_depth ? a.inv_depth + b * P : nullptr, acc, h, w);
+    if ((rc = after_launch())) return rc;
+    stage_normalise_kernel<<<norm_blocks, kThreads, 0, st>>>(acc, a.proj + b * P * 2, a.wsum ? a.wsum + b * P : nullptr,
+                                                            a.count + b * P, a.hole + b * P, a.rowmask + b * rw,
+                                                            a.colmask + b * cw, a.flags + 1 + b, h, w);
+    if ((rc = after_launch())) return rc;
+    stage_fill_kernel<<<fill_blocks, kThreads, 0, st>>>(a.rowmask + b * rw, a.colmask + b * cw, a.flags + 1 + b,
+                                                       a.proj + b * P * 2, h, w);
+    if ((rc = after_launch())) return rc;
+  }
+  for (int i = 0; i < lanes; ++i) {
+    if ((e = cudaEventRecord(fj->done[i], fj->stream[i])) != cudaSuccess) return cuda_status(e);
+    if ((e = cudaStreamWaitEvent(user, fj->done[i], 0)) != cudaSuccess) return cuda_status(e);
+  }
+  return VSR_OK;
+}
+
 }  // namespace
 }  // namespace vsr
 
@@ -558,7 +736,7 @@ extern "C" int vsr_flow_projection_forward_bounded(const float* flow, const floa
   a.bound = 0;
   a.gate = 0;
   const bool bounded = max_disp >= 0.0f && max_disp <= (float)kMaxBound;    // NaN / negative / large: general path
-  if (!bounded) return launch_pipeline(a, st);
+  if (!bounded) return run_general(a, st);
 
   a.bound = (int)ceilf(max_disp);
   static PerDeviceOnce once;
