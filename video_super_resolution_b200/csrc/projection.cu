@@ -21,15 +21,13 @@
 //    global accumulator, no memset, no second pass over the cells: HBM sees the algorithmic bytes only, the L2 the
 //    sources ~2.3x.  A source that breaks the promise raises a flag and the whole batch is redone by the general
 //    path (one gated launch that exits at once otherwise).
-//  * GENERAL (config C3's +-64 px): scatter with one 16-byte red.global.add.v4.f32 per source into an L2-resident
-//    cell array, then a gather pass.  The four stages of an image (zero, splat, normalise, fill) are software-
-//    pipelined over the batch inside ONE cooperative persistent kernel: in phase p the grid zeroes the cells of image
-//    p+1, splats image p, normalises image p-1 and fills image p-2, on three rotating cell arrays (3 x 33 MB at
-//    1080p, L2-resident), with a grid barrier between phases.  Round 1 ran four dependent launches per image
-//    (memset 6 + splat 13 + normalise 15 + fill 9-19 us at 1080p) and nothing overlapped.
+//  * GENERAL (config C3's +-64 px): scatter with one 16-byte red.global.add.v4.f32 per source into ONE L2-resident
+//    cell array (33 MB at 1080p), then a gather pass (box sum + normalise + masks) and the fill, image after image on
+//    the caller's stream.  Overlapping the stages of successive images was tried three ways and measured slower (see
+//    run_general); the cooperative pipelined kernel of those experiments survives as the gated fallback of the
+//    bounded path, where what matters is that skipping it costs one empty launch.
 #include <cooperative_groups.h>
 
-#include <mutex>
 
 #include "common.cuh"
 
@@ -43,7 +41,7 @@ constexpr int kRows = 8;  // rows walked by one splat warp task (all of their fl
 
 // Reads of data another CTA wrote earlier in the SAME (persistent) kernel go to L2 (ld.global.cg): the non-coherent
 // path of __ldg / const __restrict__ may serve a line this SM cached from the previous use of a rotating buffer.
-__device__ __forceinline__ float4 ldg_f4(const float4* p) { return __ldcg(p); }
+template <bool CG> __device__ __forceinline__ float4 ldg_f4(const float4* p) { return CG ? __ldcg(p) : __ldg(p); }
 __device__ __forceinline__ float4 shfl_up1_f4(float4 v) {
   return make_float4(__shfl_up_sync(0xffffffffu, v.x, 1), __shfl_up_sync(0xffffffffu, v.y, 1),
                      __shfl_up_sync(0xffffffffu, v.z, 1), __shfl_up_sync(0xffffffffu, v.w, 1));
@@ -144,6 +142,7 @@ __device__ __forceinline__ void role_splat(const float* __restrict__ flow, const
 // pixels get (0,0) here; the fill overwrites them.
 constexpr int kStrip = 16, kBatch = 4;
 
+template <bool CG>
 __device__ __forceinline__ void role_normalise(const float4* __restrict__ acc, float* __restrict__ proj,
                                                float* __restrict__ wsum, int32_t* __restrict__ count,
                                                uint8_t* __restrict__ hole, uint32_t* __restrict__ rowmask,
@@ -158,9 +157,9 @@ __device__ __forceinline__ void role_normalise(const float4* __restrict__ acc, f
     const int x = tx * 32 + lane, y0 = strip * kStrip;
     const bool in_x = x < w;
     const float mx = (x == w - 1) ? 2.0f : 1.0f;
-    float4 up = (in_x && y0 > 0 && y0 <= h) ? ldg_f4(acc + (y0 - 1) * w + x) : zero4;            // cell (y0-1, x)
+    float4 up = (in_x && y0 > 0 && y0 <= h) ? ldg_f4<CG>(acc + (y0 - 1) * w + x) : zero4;            // cell (y0-1, x)
     float4 up_left = shfl_up1_f4(up);                                                              // cell (y0-1, x-1)
-    if (lane == 0) up_left = (x > 0 && y0 > 0 && y0 <= h) ? ldg_f4(acc + (y0 - 1) * w + x - 1) : zero4;
+    if (lane == 0) up_left = (x > 0 && y0 > 0 && y0 <= h) ? ldg_f4<CG>(acc + (y0 - 1) * w + x - 1) : zero4;
     uint32_t colbits = 0;
     bool any_hole = false;
 #pragma unroll
@@ -169,8 +168,8 @@ __device__ __forceinline__ void role_normalise(const float4* __restrict__ acc, f
 #pragma unroll
       for (int r = 0; r < kBatch; ++r) {
         const int y = y0 + r0 + r;
-        c[r] = (in_x && y < h) ? ldg_f4(acc + y * w + x) : zero4;
-        cl[r] = (lane == 0 && x > 0 && y < h) ? ldg_f4(acc + y * w + x - 1) : zero4;
+        c[r] = (in_x && y < h) ? ldg_f4<CG>(acc + y * w + x) : zero4;
+        cl[r] = (lane == 0 && x > 0 && y < h) ? ldg_f4<CG>(acc + y * w + x - 1) : zero4;
       }
 #pragma unroll
       for (int r = 0; r < kBatch; ++r) {
@@ -217,10 +216,11 @@ __device__ __forceinline__ void role_normalise(const float4* __restrict__ acc, f
 // One warp per 32-pixel row word: a word without holes costs one 4-byte load for the whole warp; the hole pixels of a
 // word are filled in parallel by their lanes.  Only non-hole pixels are read, so the result does not depend on
 // execution order.
+template <bool CG>
 __device__ __forceinline__ void role_fill(const uint32_t* rowmask_, const uint32_t* colmask_,
                                           float* proj, int h, int w, int warp0, int nw, int lane) {
-  struct CG { const uint32_t* p; __device__ __forceinline__ uint32_t operator[](int64_t i) const { return __ldcg(p + i); } };
-  const CG rowmask{rowmask_}, colmask{colmask_};
+  struct Words { const uint32_t* p; __device__ __forceinline__ uint32_t operator[](int64_t i) const { return CG ? __ldcg(p + i) : __ldg(p + i); } };
+  const Words rowmask{rowmask_}, colmask{colmask_};
   const int wpr = ceil_div(w, 32), hpr = ceil_div(h, 32);
   const float2* pin = reinterpret_cast<const float2*>(proj);   // non-hole pixels only: never written here
   const int n_words = h * wpr;
@@ -233,7 +233,7 @@ __device__ __forceinline__ void role_fill(const uint32_t* rowmask_, const uint32
     float sx = 0.f, sy = 0.f;
     int found = 0;
     auto take = [&](int yy, int xx) {
-      const float2 q = __ldcg(pin + yy * w + xx);   // the neighbour's normalised value, as written by the normalise pass
+      const float2 q = CG ? __ldcg(pin + yy * w + xx) : pin[yy * w + xx];   // the neighbour's normalised value, as written by the normalise pass
       sx += q.x;
       sy += q.y;
       ++found;
@@ -295,13 +295,13 @@ projection_pipeline_kernel(const ProjArgs a) {
       } else if (role == 2) {
         const int b = p - 1;
         if (b >= 0 && b < a.B)
-          role_normalise(a.acc + (b % 3) * P, a.proj + b * P * 2, a.wsum ? a.wsum + b * P : nullptr, a.count + b * P,
+          role_normalise<true>(a.acc + (b % 3) * P, a.proj + b * P * 2, a.wsum ? a.wsum + b * P : nullptr, a.count + b * P,
                          a.hole + b * P, a.rowmask + b * rw, a.colmask + b * cw, a.flags + 1 + b, a.h, a.w, warp0, nw,
                          lane);
       } else {
         const int b = p - 2;
         if (b >= 0 && b < a.B && *reinterpret_cast<volatile int*>(a.flags + 1 + b) != 0)
-          role_fill(a.rowmask + b * rw, a.colmask + b * cw, a.proj + b * P * 2, a.h, a.w, warp0, nw, lane);
+          role_fill<true>(a.rowmask + b * rw, a.colmask + b * cw, a.proj + b * P * 2, a.h, a.w, warp0, nw, lane);
       }
     }
     if (p <= a.B) grid.sync();
@@ -309,12 +309,7 @@ projection_pipeline_kernel(const ProjArgs a) {
 }
 
 // The same stages as stand-alone kernels, each with its own register budget / occupancy (the merged kernel above runs
-// every role at 24 warps per SM; alone the splat keeps 64 in flight).  The general path launches them per image on
-// three internal streams, so that the stages of successive images overlap (see run_general).
-__global__ void __launch_bounds__(kThreads)
-stage_zero_kernel(float4* __restrict__ acc, int64_t n) {
-  role_zero(acc, n, (int64_t)blockIdx.x * kThreads + threadIdx.x, (int64_t)gridDim.x * kThreads);
-}
+// every role at 24 warps per SM; alone the splat keeps 64 in flight): the general path (run_general).
 __global__ void __launch_bounds__(kThreads)
 stage_splat_kernel(const float* __restrict__ flow, const float* __restrict__ inv_depth, float4* __restrict__ acc, int h, int w) {
   role_splat(flow, inv_depth, acc, h, w, (blockIdx.x * kThreads + threadIdx.x) >> 5, (gridDim.x * kThreads) >> 5, threadIdx.x & 31);
@@ -323,14 +318,14 @@ __global__ void __launch_bounds__(kThreads, 4)
 stage_normalise_kernel(const float4* __restrict__ acc, float* __restrict__ proj, float* __restrict__ wsum,
                        int32_t* __restrict__ count, uint8_t* __restrict__ hole, uint32_t* __restrict__ rowmask,
                        uint32_t* __restrict__ colmask, int* __restrict__ has_holes, int h, int w) {
-  role_normalise(acc, proj, wsum, count, hole, rowmask, colmask, has_holes, h, w, (blockIdx.x * kThreads + threadIdx.x) >> 5,
+  role_normalise<false>(acc, proj, wsum, count, hole, rowmask, colmask, has_holes, h, w, (blockIdx.x * kThreads + threadIdx.x) >> 5,
                  (gridDim.x * kThreads) >> 5, threadIdx.x & 31);
 }
 __global__ void __launch_bounds__(kThreads)
 stage_fill_kernel(const uint32_t* rowmask, const uint32_t* colmask, const int* has_holes, float* proj, int h, int w) {
   if (*reinterpret_cast<const volatile int*>(has_holes) == 0) return;
-  role_fill(rowmask, colmask, proj, h, w, (blockIdx.x * kThreads + threadIdx.x) >> 5, (gridDim.x * kThreads) >> 5,
-            threadIdx.x & 31);
+  role_fill<false>(rowmask, colmask, proj, h, w, (blockIdx.x * kThreads + threadIdx.x) >> 5, (gridDim.x * kThreads) >> 5,
+                   threadIdx.x & 31);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -408,6 +403,7 @@ __device__ __forceinline__ void add_batch(const SrcBatch& cur, const Walk& wk, W
     vy[u] = __fmul_rn(-fy, cur.d[u]);
   }
   bool again;
+  int rounds = 0;
   do {
 #pragma unroll
     for (int u = 0; u < kSB; ++u) s_claim[cell[u]] = (uint8_t)(u * 32 + lane);
@@ -423,6 +419,8 @@ __device__ __forceinline__ void add_batch(const SrcBatch& cur, const Walk& wk, W
       const bool win = pend[u] && who[u] == (uint8_t)(u * 32 + lane);
       idx[u] = win ? cell[u] : kCells;
       pend[u] = pend[u] && !win;
+      if (!pend[u]) cell[u] = kCells;      // done: from now on this source only touches the dummy (a winner that kept
+                                           // writing its id to the real claim byte would starve the others for ever)
       left |= pend[u];
     }
 #pragma unroll
@@ -434,6 +432,9 @@ __device__ __forceinline__ void add_batch(const SrcBatch& cur, const Walk& wk, W
     }
     again = __any_sync(0xffffffffu, left);
     __syncwarp();
+    // every round retires at least one source per contested cell: at most kSB * 32 rounds.  The guard turns a logic
+    // error into a redo by the general path instead of a hung GPU.
+    if (++rounds > kSB * 32 + 2) { vmax = __int_as_float(0x7f800000); break; }
   } while (again);
 }
 
@@ -578,7 +579,7 @@ projection_fill_kernel(const ProjArgs a) {
   const int64_t rw = rowmask_words(a.h, a.w), cw = colmask_words(a.h, a.w);
   for (int b = 0; b < a.B; ++b)
     if (*reinterpret_cast<volatile int*>(a.flags + 1 + b) != 0)
-      role_fill(a.rowmask + b * rw, a.colmask + b * cw, a.proj + b * P * 2, a.h, a.w, warp0, nw, lane);
+      role_fill<false>(a.rowmask + b * rw, a.colmask + b * cw, a.proj + b * P * 2, a.h, a.w, warp0, nw, lane);
 }
 
 struct ProjWs {
@@ -625,74 +626,35 @@ int launch_pipeline(const ProjArgs& a, cudaStream_t st) {
   return after_launch();
 }
 
-// Internal fork/join resources of the general path, one set per device, created on first use and never destroyed.
-// (The library still owns no device MEMORY: accumulators and bitmaps live in the caller's workspace.)
-constexpr int kLanes = 3;
-struct ForkJoin {
-  bool ok = false;
-  cudaStream_t stream[kLanes];
-  cudaEvent_t start, done[kLanes];
-};
-ForkJoin* fork_join() {
-  static std::mutex mu;
-  static ForkJoin per_dev[64];
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  std::lock_guard<std::mutex> lock(mu);
-  ForkJoin& f = per_dev[dev];
-  if (!f.ok) {
-    for (int i = 0; i < kLanes; ++i) {
-      if (cudaStreamCreateWithFlags(&f.stream[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-      if (cudaEventCreateWithFlags(&f.done[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    }
-    if (cudaEventCreateWithFlags(&f.start, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    f.ok = true;
-  }
-  return &f;
-}
-std::mutex g_enqueue_mu;   // one enqueue at a time: the fork/join events are shared by all callers of a device
-
-// General path: per image zero -> splat -> normalise -> fill, each kernel at its own occupancy; image b runs on
-// internal stream b % 3 with cell array b % 3, forked from and joined to the caller's stream with events, so the
-// stages of three successive images are in flight together (alone they are latency- / issue-bound, not HBM-bound).
-int run_general(const ProjArgs& a, cudaStream_t user) {
-  ForkJoin* fj = fork_join();
-  if (!fj) return VSR_ERR_STATE;
-  std::lock_guard<std::mutex> lock(g_enqueue_mu);
+// General path: per image memset -> splat -> normalise -> fill on the caller's stream, one L2-resident cell array.
+// Measured alternatives on B200 (1080p, batch 8, us per image, smooth +-8 / i.i.d. +-64 / occlusion; profiles/
+// time_ops_r02*.log): this sequence 45 / 59 / 45; images on 2 internal streams with 2 cell arrays 50 / 88 / 49; on 3
+// streams 52 / 133 / 51 -- more than one 33 MB cell array in flight falls out of L2 under the streaming traffic and the
+// scattered reductions go to DRAM; the whole batch pipelined inside one cooperative kernel (projection_pipeline_kernel
+// above, kept as the fallback of the bounded path) 69 / 255 / 103 -- every role then runs at the merged kernel's 24
+// warps per SM.
+int run_general(const ProjArgs& a, cudaStream_t st) {
   const int h = a.h, w = a.w;
   const int64_t P = (int64_t)h * w;
   const int64_t rw = (int64_t)h * ceil_div(w, 32), cw = (int64_t)ceil_div(h, 32) * w;
-  const int lanes = a.B < kLanes ? a.B : kLanes;
-  cudaError_t e = cudaMemsetAsync(a.flags + 1, 0, (size_t)a.B * 4, user);
+  cudaError_t e = cudaMemsetAsync(a.flags + 1, 0, (size_t)a.B * 4, st);
   if (e != cudaSuccess) return cuda_status(e);
-  if ((e = cudaEventRecord(fj->start, user)) != cudaSuccess) return cuda_status(e);
-  for (int i = 0; i < lanes; ++i)
-    if ((e = cudaStreamWaitEvent(fj->stream[i], fj->start, 0)) != cudaSuccess) return cuda_status(e);
   const int n_tasks = ceil_div(w, 32) * ceil_div(h, kRows);
   const int splat_blocks = ceil_div(n_tasks, kThreads / 32);
   const int norm_blocks = ceil_div(ceil_div(w, 32) * 2 * ceil_div(h, 32), kThreads / 32);
   const int fill_blocks = ceil_div(h * ceil_div(w, 32), kThreads / 32);   // one warp per 32-pixel row word
-  int64_t zb = ceil_div64(P, kThreads * 4);
-  const int zero_blocks = (int)(zb > kNumSMs * 8 ? kNumSMs * 8 : (zb < 1 ? 1 : zb));
   for (int b = 0; b < a.B; ++b) {
-    cudaStream_t st = fj->stream[b % kLanes];
-    float4* acc = a.acc + (b % kLanes) * P;
-    stage_zero_kernel<<<zero_blocks, kThreads, 0, st>>>(acc, P);
+    if ((e = cudaMemsetAsync(a.acc, 0, (size_t)P * sizeof(float4), st)) != cudaSuccess) return cuda_status(e);
+    stage_splat_kernel<<<splat_blocks, kThreads, 0, st>>>(a.flow + b * P * 2, a.inv_depth ? a.inv_depth + b * P : nullptr, a.acc, h, w);
     int rc = after_launch();
     if (rc) return rc;
-    stage_splat_kernel<<<splat_blocks, kThreads, 0, st>>>(a.flow + b * P * 2, a.inv_depth ? a.inv_depth + b * P : nullptr, acc, h, w);
-    if ((rc = after_launch())) return rc;
-    stage_normalise_kernel<<<norm_blocks, kThreads, 0, st>>>(acc, a.proj + b * P * 2, a.wsum ? a.wsum + b * P : nullptr,
+    stage_normalise_kernel<<<norm_blocks, kThreads, 0, st>>>(a.acc, a.proj + b * P * 2, a.wsum ? a.wsum + b * P : nullptr,
                                                             a.count + b * P, a.hole + b * P, a.rowmask + b * rw,
                                                             a.colmask + b * cw, a.flags + 1 + b, h, w);
     if ((rc = after_launch())) return rc;
     stage_fill_kernel<<<fill_blocks, kThreads, 0, st>>>(a.rowmask + b * rw, a.colmask + b * cw, a.flags + 1 + b,
                                                        a.proj + b * P * 2, h, w);
     if ((rc = after_launch())) return rc;
-  }
-  for (int i = 0; i < lanes; ++i) {
-    if ((e = cudaEventRecord(fj->done[i], fj->stream[i])) != cudaSuccess) return cuda_status(e);
-    if ((e = cudaStreamWaitEvent(user, fj->done[i], 0)) != cudaSuccess) return cuda_status(e);
   }
   return VSR_OK;
 }
