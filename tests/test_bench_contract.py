@@ -25,6 +25,9 @@ def test_reference_arm_prints_one_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+    assert d["extrapolated"] is True and 0 < d["frame_fraction_measured"] < 1 and d["cpu_baseline"]["extrapolated"] is True
+    import bench
+    assert d["config"]["workload"] == bench.WORKLOAD            # both arms print the same workload string
 
 
 def test_non_zero_ranks_of_the_reference_arm_exit_quietly():
@@ -36,16 +39,20 @@ def test_non_zero_ranks_of_the_reference_arm_exit_quietly():
 
 @pytest.mark.gpu
 def test_b200_arm_prints_one_contract_line():
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "2", "--warmup", "3", "--no-cpu-baseline"],
-                       capture_output=True, text=True, timeout=900)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "2", "--warmup", "3", "--no-cpu-baseline",
+                        "--no-extras"], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert (REQUIRED - {"cpu_baseline"}) <= set(d)
     assert d["gpu_launches"] > 0 and d["dtype"] == "bf16" and d["n_gpus"] == 1
+    import bench
+    assert d["config"]["workload"] == bench.WORKLOAD
     roof = d["roofline"]
-    assert roof["bound"] in ("hbm", "tensor") and 0 < roof["frac"] <= 1.2 and roof["peak"] > 0
+    # the conv stack is bounded by the tensor cores; the HBM engineering view is a secondary key
+    assert roof["bound"] == "tensor" and roof["unit"] == "TFLOP/s" and 0 < roof["frac"] <= 1.2 and roof["peak"] > 0
     assert abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-6
+    assert 0 < roof["hbm_view"]["frac"] <= 1.2 and roof["hbm_view"]["unit"] == "GB/s"
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["value"] > 0
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}

@@ -173,7 +173,8 @@ def run_c2t3(args):
     barrier(world)
     ms = max_over_ranks(e0.elapsed_time(e1) / args.steps, world, dev)
     if rank == 0:
-        flops = 2 * M * h * w * 7.348e6
+        from oracle import srfbn_oracle as so   # FLOP accounting only (the out / conv_out of the two dead feedback steps are skipped)
+        flops = 2 * M * h * w * so.flops_per_lr_pixel_per_map(dead_steps_skipped=True)
         print(json.dumps({"config": "C2 frame size with the reference's 3-frame window (M=8): 4x VSR 480x270->1920x1080, "
                                     "one window per GPU", "metric": "sr_frames_per_s_4x_1080p_out_T3", "unit": "frames/s",
                           "n_gpus": world, "steps": args.steps, "value": world / (ms / 1e3), "ms_per_step": ms,
