@@ -105,8 +105,9 @@ def _psnr255(a, b):
     return 10 * math.log10(255.0 ** 2 / max(mse, 1e-20))
 
 
-@pytest.mark.parametrize("name,M,h,w,scale", [("C2", 20, 270, 480, 4), ("C4crop", 14, 264, 328, 2)])
-def test_conv_stack_full_size_against_fp32_oracle(name, M, h, w, scale):
+@pytest.mark.parametrize("name,M,h,w,scale,group", [("C2", 20, 270, 480, 4, "0"), ("C2group", 20, 270, 480, 4, "1"),
+                                                       ("C4crop", 14, 264, 328, 2, "0")])
+def test_conv_stack_full_size_against_fp32_oracle(name, M, h, w, scale, group, monkeypatch):
     """The conv stack at C2's FULL size (M=20, 270x480 -> 1080x1920; tile-walk carries, the (h+1)x(w+1) block ring,
     2.67 GB strides -- what a 24x40 case cannot reach) and on a >= 256x256 LR crop of C4 (x2, M=14) against the fp32
     oracle: per-map PSNR > 50 dB and the north star's PSNR delta <= 0.05 dB against a common target ~35 dB away.
@@ -115,6 +116,7 @@ def test_conv_stack_full_size_against_fp32_oracle(name, M, h, w, scale):
     from oracle import srfbn_oracle as so
     gc.collect()
     torch.cuda.empty_cache()
+    monkeypatch.setenv("VSR_GROUP", group)         # "1": the co-scheduled deconv + fused-down launches (off by default)
     sd = so.init_state_dict(num_maps=M, seed=11, gain=2.3, upscale=scale)
     gs = torch.Generator().manual_seed(99)
     for k in sd:
@@ -124,6 +126,7 @@ def test_conv_stack_full_size_against_fp32_oracle(name, M, h, w, scale):
     mod.load_state_dict(sd)
     x = (torch.rand((M, 3, h, w), generator=torch.Generator().manual_seed(5)) * 255).to(DEV)
     got = mod.premix(x)
+    assert not mod.group_error()             # the co-scheduled group launches never gave up waiting
     want = _oracle_maps_on_gpu(x, sd, 3, scale)
     assert got.shape == want.shape == (M, 3, scale * h, scale * w) and torch.isfinite(got).all()
     skip = torch.nn.functional.interpolate(x, scale_factor=scale, mode="bilinear", align_corners=False)

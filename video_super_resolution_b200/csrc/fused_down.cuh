@@ -104,9 +104,11 @@ inline size_t fused_down_smem_bytes(int nsrc, int num_stages, int wd_resident, i
          (size_t)num_stages * stage + 1024 + (xchg ? kXchgBytes : 0);
 }
 
+// The kernel body as a device function: fused_down_kernel runs it over the whole grid; group_kernel below runs it on
+// the CTAs after the deconv role's, with the tile hand-off `gs` (the newest source map is read from L2 as soon as the
+// deconv role has published the tile).
 template <bool HAS_TRAN>
-__global__ void __launch_bounds__(kFusedThreads, 1)
-fused_down_kernel(const __grid_constant__ FusedDownParams p) {
+__device__ __forceinline__ void fused_body(const FusedDownParams& p, const int cta, const int ncta, const GroupSync* gs) {
   constexpr int kStageBytes = HAS_TRAN ? 16384 : 2 * 16384;
   constexpr int kTmemCols = HAS_TRAN ? 512 : 256;
   constexpr uint32_t kDB = HAS_TRAN ? 256 : 0;       // first column of the two D_B accumulators
@@ -199,19 +201,20 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
         }
       };
       {
-        int t = blockIdx.x, hf = 0;
+        int t = cta, hf = 0;
         for (int i = 0; i < kAhead; ++i) {
           prefetch_half(t, hf);
-          if (++hf == 2) { hf = 0; t += gridDim.x; }
+          if (++hf == 2) { hf = 0; t += ncta; }
         }
       }
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = cta; tile < total_tiles; tile += ncta) {
         int x0, y0, b;
         tile_coord(tile, x0, y0, b);
+        bool newest_ready = false;
         for (int half = 0; half < 2; ++half) {
           if (kAhead > 0) {  // the half-tile kAhead units ahead of (tile, half)
             const int u = half + kAhead;
-            prefetch_half(tile + (u >> 1) * gridDim.x, u & 1);
+            prefetch_half(tile + (u >> 1) * ncta, u & 1);
           }
           if (HAS_TRAN) {
             // one box = 2 sub-positions x 128 blocks x 32 ch (16 KB): a [128 x 64] K-major tile whose K
@@ -220,13 +223,30 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
               for (int j = 0; j < p.nsrc; ++j) {
                 mbar_wait(&empty_bar[s], phase ^ 1);
                 mbar_expect_tx(&full_bar[s], kStageBytes);
-                tma_load_4d(s_a + s * kStageBytes, &p.hr_maps[j], &full_bar[s], 0, x0, y0, b * 8 + (sp >> 1));
+                if (gs != nullptr) {
+                  // group launch: the newest map's tile comes from the deconv role of this launch (L2); the older
+                  // maps stream from HBM and are marked evict-first so that they do not push it out
+                  if (j == p.nsrc - 1 && !newest_ready) {
+                    spin_until_ge(gs->tile_flags + tile, 32 * gs->epoch, gs->error);
+                    fence_proxy_async_all();
+                    newest_ready = true;
+                  }
+                  tma_load_4d_hint(s_a + s * kStageBytes, &p.hr_maps[j], &full_bar[s], 0, x0, y0, b * 8 + (sp >> 1),
+                                   kL2EvictFirst);
+                } else {
+                  tma_load_4d(s_a + s * kStageBytes, &p.hr_maps[j], &full_bar[s], 0, x0, y0, b * 8 + (sp >> 1));
+                }
                 if (++s == p.num_stages) { s = 0; phase ^= 1; }
               }
             }
           } else {
             for (int g = half * 2; g < half * 2 + 2; ++g) {
               mbar_wait(&empty_bar[s], phase ^ 1);
+              if (gs != nullptr && !newest_ready) {
+                spin_until_ge(gs->tile_flags + tile, 32 * gs->epoch, gs->error);
+                fence_proxy_async_all();
+                newest_ready = true;
+              }
               mbar_expect_tx(&full_bar[s], kStageBytes);
               tma_load_4d(s_a + s * kStageBytes, &p.h0_map, &full_bar[s], 0, x0, y0, b * 8 + 2 * g);
               tma_load_4d(s_a + s * kStageBytes + 16384, &p.h0_map, &full_bar[s], 0, x0, y0, b * 8 + 2 * g + 1);
@@ -320,7 +340,7 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
     // HAS_TRAN: this thread issues phase A only; phase B has its own issuing thread (warp kFusedBWarp), so
     // that waiting for the converted tile / the weights never holds up the consumption of TMA stages.
     // tcgen05.commit tracks the MMAs of the issuing thread, so each thread signals exactly its own work.
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = cta; tile < total_tiles; tile += ncta) {
       if (HAS_TRAN) {
         if (warp == 1) {
           for (int g = 0; g < 4; ++g) issue_a(g);
@@ -342,7 +362,7 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
       for (int kc = 0; kc < 8; ++kc) tma_load_2d(s_wd + kc * 16384, &p.wd_map, &wd_full[0], kc * 64, 0);
     } else if (lane == 0) {
       uint32_t n_wd = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x)
+      for (int tile = cta; tile < total_tiles; tile += ncta)
         for (int g = 0; g < 4; ++g) {
           const int slot = n_wd & 1;
           mbar_wait(&wd_empty[slot], ((n_wd >> 1) & 1) ^ 1);
@@ -364,7 +384,7 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
     uint32_t m_a[2] = {0, 0}, m_b[2] = {0, 0}, m_h = 0;
     int tb = 0;
     const PreluCfg pc = make_prelu(HAS_TRAN ? s_bias[32] : 1.0f, 1);
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = cta; tile < total_tiles; tile += ncta) {
       int x0, y0, b;
       tile_coord(tile, x0, y0, b);
       const int Yb = y0 + (row >> 4), Xb = x0 + (row & 15);
@@ -492,6 +512,9 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
       }
       ++m_b[tb];
       tb ^= 1;
+      // group launch: progress counter the deconv role throttles on (this warp has read the tile's accumulators, so
+      // every load of the tile has long been consumed)
+      if (gs != nullptr && warp == 2 && lane == 0) red_release_gpu_add(gs->fused_done, 1);
     }
   }
 
@@ -501,6 +524,29 @@ fused_down_kernel(const __grid_constant__ FusedDownParams p) {
     tc_fence_after();
     tmem_dealloc<kTmemCols>(tmem_base);
   }
+}
+
+template <bool HAS_TRAN>
+__global__ void __launch_bounds__(kFusedThreads, 1)
+fused_down_kernel(const __grid_constant__ FusedDownParams p) {
+  fused_body<HAS_TRAN>(p, (int)blockIdx.x, (int)gridDim.x, nullptr);
+}
+
+// One launch for a feedback group's up-projection AND its HR half: CTAs [0, n_deconv) run the transposed conv
+// (igemm_body<EPI_DECONV>) and write hr[i]; the remaining CTAs run the fused downtran + strided conv over hr[0..i] in the
+// same tile order, a few hundred tiles behind, and find hr[i]'s tile in L2 (SRProjectionModule.py:
+// 62-65 then :70-80).  Launched as two kernels every hr[i] is written to and read back from HBM: 6 of the 34 HR-map
+// transfers of a feedback step.  The roles also complement each other: alone, the deconv is bound by TMEM reads /
+// shared-memory traffic at 0.7 of the write bandwidth while the fused kernel is bound by HBM reads.
+template <bool HAS_TRAN>
+__global__ void __launch_bounds__(kFusedThreads, 1)
+group_kernel(const __grid_constant__ IgemmParams dp, const __grid_constant__ FusedDownParams fp,
+             const __grid_constant__ GroupSync gs) {
+  static_assert(kFusedThreads >= kDeconvThreads, "the launch is as wide as the wider role");
+  if ((int)blockIdx.x < gs.n_deconv)
+    igemm_body<EPI_DECONV, 32, 256>(dp, (int)blockIdx.x, gs.n_deconv, &gs);
+  else
+    fused_body<HAS_TRAN>(fp, (int)blockIdx.x - gs.n_deconv, (int)gridDim.x - gs.n_deconv, &gs);
 }
 
 // Boundary pixels (rows Y % 8 == 7 -- period 8; odd rows without the exchange -- period 2; columns X % 16 == 15;

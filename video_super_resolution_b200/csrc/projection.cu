@@ -142,7 +142,7 @@ __device__ __forceinline__ void role_splat(const float* __restrict__ flow, const
 // pixels get (0,0) here; the fill overwrites them.
 constexpr int kStrip = 16, kBatch = 4;
 
-template <bool CG>
+template <bool CG, bool LOOP>
 __device__ __forceinline__ void role_normalise(const float4* __restrict__ acc, float* __restrict__ proj,
                                                float* __restrict__ wsum, int32_t* __restrict__ count,
                                                uint8_t* __restrict__ hole, uint32_t* __restrict__ rowmask,
@@ -152,7 +152,9 @@ __device__ __forceinline__ void role_normalise(const float4* __restrict__ acc, f
   const int n_strips = 2 * ceil_div(h, 32);          // both halves of every column word get written
   const int n_tasks = tiles_x * n_strips;
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int task = warp0; task < n_tasks; task += nw) {
+  // LOOP = false: the stand-alone launch gives every warp exactly one strip (the loop's live range costs the 64-register
+  // kernel spills in its inner loop)
+  for (int task = warp0; task < n_tasks; task += LOOP ? nw : n_tasks) {
     const int tx = task % tiles_x, strip = task / tiles_x;
     const int x = tx * 32 + lane, y0 = strip * kStrip;
     const bool in_x = x < w;
@@ -295,7 +297,7 @@ projection_pipeline_kernel(const ProjArgs a) {
       } else if (role == 2) {
         const int b = p - 1;
         if (b >= 0 && b < a.B)
-          role_normalise<true>(a.acc + (b % 3) * P, a.proj + b * P * 2, a.wsum ? a.wsum + b * P : nullptr, a.count + b * P,
+          role_normalise<true, true>(a.acc + (b % 3) * P, a.proj + b * P * 2, a.wsum ? a.wsum + b * P : nullptr, a.count + b * P,
                          a.hole + b * P, a.rowmask + b * rw, a.colmask + b * cw, a.flags + 1 + b, a.h, a.w, warp0, nw,
                          lane);
       } else {
@@ -318,7 +320,7 @@ __global__ void __launch_bounds__(kThreads, 4)
 stage_normalise_kernel(const float4* __restrict__ acc, float* __restrict__ proj, float* __restrict__ wsum,
                        int32_t* __restrict__ count, uint8_t* __restrict__ hole, uint32_t* __restrict__ rowmask,
                        uint32_t* __restrict__ colmask, int* __restrict__ has_holes, int h, int w) {
-  role_normalise<false>(acc, proj, wsum, count, hole, rowmask, colmask, has_holes, h, w, (blockIdx.x * kThreads + threadIdx.x) >> 5,
+  role_normalise<false, false>(acc, proj, wsum, count, hole, rowmask, colmask, has_holes, h, w, (blockIdx.x * kThreads + threadIdx.x) >> 5,
                  (gridDim.x * kThreads) >> 5, threadIdx.x & 31);
 }
 __global__ void __launch_bounds__(kThreads)

@@ -90,11 +90,11 @@ int make_w_map(CUtensorMap* m, const void* base, int64_t K, int64_t N, int ck, i
 // ------------------------------------------------------------------------------------------------
 // kernel variants
 // ------------------------------------------------------------------------------------------------
-enum Variant : int { V_PW32 = 0, V_PW128, V_DECONV, V_CONVOUT, V_FUSED_TRAN, V_FUSED_PLAIN, V_FINALIZE, V_DECONV2, V_COUNT };
+enum Variant : int { V_PW32 = 0, V_PW128, V_DECONV, V_CONVOUT, V_FUSED_TRAN, V_FUSED_PLAIN, V_FINALIZE, V_DECONV2, V_GROUP_TRAN, V_GROUP_PLAIN, V_COUNT };
 
 // kernel classes for the per-launch accounting bench.py reads (vsr_srfbn_profile_*)
-static_assert(VSR_SRFBN_KERNEL_CLASSES == 10, "header constant");
-enum KClass : int { KC_IM2COL = 0, KC_CONV_IN, KC_PW_LR, KC_PW_HR, KC_DECONV, KC_DOWNCONV, KC_CONV_OUT, KC_FC, KC_FUSED_DOWN, KC_FINALIZE, KC_COUNT };
+static_assert(VSR_SRFBN_KERNEL_CLASSES == 11, "header constant");
+enum KClass : int { KC_IM2COL = 0, KC_CONV_IN, KC_PW_LR, KC_PW_HR, KC_DECONV, KC_DOWNCONV, KC_CONV_OUT, KC_FC, KC_FUSED_DOWN, KC_FINALIZE, KC_GROUP, KC_COUNT };
 
 struct Layer {
   int variant;
@@ -105,12 +105,25 @@ struct Layer {
   void* fin_out;
   int64_t fin_n8;
   int fin_w, fin_h, fin_b, fin_period;   // fin_period: 8 (rows Y % 8 == 7) or 2 (odd rows), matching the fused kernel's xchg mode
+  GroupSync gs;          // V_GROUP_*: p = the deconv role, f = the fused-down role
+  int group_index;       // V_GROUP_*: i of the feedback group (selects the role split)
   int grid;
   size_t smem;
   int kclass;
   double flops;   // 2*MAC of the layer as specified (padding / ring rows not counted)
   double bytes;   // compulsory HBM bytes of this launch: its inputs + outputs, each once
 };
+
+// VSR_GROUP=1: run a group's transposed conv and its fused down kernel as two ROLES of one launch (group_kernel), hr[i]
+// handed over through L2.  Off by default: measured on B200 at C2 it is SLOWER (48.8 vs 44.0 ms per pass for the 19 + 18
+// launches it replaces; profiles/group_launch_r02.log).  The fused kernel streams at ~38 GB/s per SM -- what ~112 KB of
+// TMA boxes in flight per SM yield at the loaded HBM latency -- so it only reaches the HBM roof with all 148 SMs pulling;
+// giving 30-116 SMs to the deconv role costs more read bandwidth than the L2 hits of the newest map return.  Kept
+// (bit-identical to the two launches, tests/test_srfbn_gpu.py) as the measured answer to "hand hr[i] over through L2".
+int group_enabled() {
+  const char* e = getenv("VSR_GROUP");
+  return e ? (atoi(e) != 0) : 0;
+}
 
 int fused_xchg() {   // tuning knob, see FusedDownParams::xchg
   const char* e = getenv("VSR_FUSED_XCHG");
@@ -148,8 +161,34 @@ int launch_fused(const Layer& L, cudaStream_t st) {
   return after_launch();
 }
 
+template <bool HAS_TRAN>
+int launch_group(const Layer& L, cudaStream_t st) {
+  static PerDeviceOnce once;
+  int dev;
+  if (once.needed(&dev)) {
+    cudaError_t e = cudaFuncSetAttribute(group_kernel<HAS_TRAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return cuda_status(e);
+    once.mark(dev);
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)L.grid, 1, 1);
+  cfg.blockDim = dim3((unsigned)kFusedThreads, 1, 1);
+  cfg.dynamicSmemBytes = L.smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;     // all CTAs co-resident or the launch fails: the roles wait on each other
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, group_kernel<HAS_TRAN>, L.p, L.f, L.gs);
+  if (e != cudaSuccess) return cuda_status(e);
+  return after_launch();
+}
+
 int launch_layer(const Layer& L, cudaStream_t st) {
   switch (L.variant) {
+    case V_GROUP_TRAN: return launch_group<true>(L, st);
+    case V_GROUP_PLAIN: return launch_group<false>(L, st);
     case V_FUSED_TRAN: return launch_fused<true>(L, st);
     case V_FUSED_PLAIN: return launch_fused<false>(L, st);
     case V_FINALIZE: {
@@ -529,6 +568,54 @@ int build_finalize(Layer& L, float* acc, const float* bias_dev, void* out, int64
   return VSR_OK;
 }
 
+// Co-scheduled group launch (group_kernel): `d` = the group's deconv layer, `f` = its fused-down layer, both already
+// built.  Role split: the deconv role needs ~3.9 CTA-us per spatial tile (both N halves), the fused role ~0.7 (i = 0, its
+// only map comes from L2) to ~16 (i = 5) once the newest map is an L2 hit; n_deconv is the even number of CTAs that
+// balances the two (tunable: VSR_GROUP_ND="n0,n1,..,n5").
+int group_deconv_ctas(int i) {
+  static const int dflt[6] = {116, 64, 50, 42, 36, 30};
+  int nd = dflt[i < 0 ? 0 : (i > 5 ? 5 : i)];
+  if (const char* e = getenv("VSR_GROUP_ND")) {
+    int k = 0;
+    for (const char* q = e; *q && k <= i; ++k) {
+      const int v = atoi(q);
+      if (k == i && v >= 2) nd = v;
+      while (*q && *q != ',') ++q;
+      if (*q == ',') ++q;
+    }
+  }
+  nd &= ~1;
+  if (nd < 2) nd = 2;
+  if (nd > kNumSMs - 2) nd = kNumSMs - 2;
+  return nd;
+}
+
+int build_group(Layer& L, const Layer& d, const Layer& f, int group_index, int32_t* flags, int32_t epoch, int32_t n_spatial) {
+  memset(&L, 0, sizeof(L));
+  L.variant = f.variant == V_FUSED_TRAN ? V_GROUP_TRAN : V_GROUP_PLAIN;
+  L.p = d.p;
+  L.f = f.f;
+  L.group_index = group_index;
+  L.grid = kNumSMs;
+  L.smem = d.smem > f.smem ? d.smem : f.smem;
+  L.gs.tile_flags = flags + 64;          // [0] fused_done, [1] error, then the per-tile flags
+  L.gs.fused_done = flags;
+  L.gs.error = flags + 1;
+  L.gs.epoch = epoch;
+  L.gs.done_base = (epoch - 1) * n_spatial;
+  L.gs.n_deconv = group_deconv_ctas(group_index);
+  {
+    const char* e = getenv("VSR_GROUP_WINDOW");
+    L.gs.window = e && atoi(e) > 0 ? atoi(e) : kNumSMs + 64;
+  }
+  L.kclass = KC_GROUP;
+  L.flops = d.flops + f.flops;
+  // compulsory HBM bytes of the pair: LR in, hr[i] out (write-back), hr[0..i-1] in, LR out; hr[i] is not read back
+  const double lrpx = (double)d.p.batch * d.p.lr_h * d.p.lr_w;
+  L.bytes = d.bytes + f.bytes - lrpx * 64.0 * 16.0;
+  return VSR_OK;
+}
+
 // conv_out 3x3 p1 32->3 at HR + bilinear skip + mean shifts, fp32 planar output (B,3,4h,4w)
 int build_conv_out(Layer& L, const void* xhr, int B, int h, int w, int scale, const void* w_dev,
                    const float* bias_dev, float* out) {
@@ -792,7 +879,8 @@ struct vsr_srfbn_plan {
   size_t misc_off;        // fp32: sub_mean bias (3)
   size_t weight_bytes;
   // workspace offsets
-  size_t o_a0, o_c128, o_xfeat, o_hidden, o_lr[7], o_u, o_hr[6], o_hb, o_ht, o_acc, o_premix, ws_bytes;
+  size_t o_a0, o_c128, o_xfeat, o_hidden, o_lr[7], o_u, o_hr[6], o_hb, o_ht, o_acc, o_premix, o_flags, flags_bytes, ws_bytes;
+  bool grouped;           // group launches in the layer list: the flags are zeroed at the start of every forward
   bool bound;
   const uint8_t* dev_w;
   uint8_t* ws;
@@ -853,6 +941,9 @@ static void layout_workspace(vsr_srfbn_plan* pl) {
   pl->o_ht = put(x2 ? P * s2 * 64 : 0);   // x2: downtran result (the x4 path keeps it on chip)
   pl->o_acc = put(x2 ? 0 : P * 512);   // fp32 partial slots of the fused down kernel
   pl->o_premix = put(P * s2 * 3 * 4);
+  // hand-off flags of the group launches: fused_done, error, one counter per 16 x 8-block tile
+  pl->flags_bytes = x2 ? 0 : (64 + (size_t)c.num_maps * ceil_div(c.h + 1, 8) * ceil_div(c.w + 1, 16)) * 4;
+  pl->o_flags = put(pl->flags_bytes);
   pl->ws_bytes = off;
 }
 
@@ -970,6 +1061,8 @@ extern "C" int vsr_srfbn_bind(vsr_srfbn_plan* pl, const void* dev_weights, void*
   auto Bp = [&](int id) { return reinterpret_cast<const float*>(pl->dev_w + pl->we[id].b_off); };
   int rc;
   Layer L;
+  int32_t group_epoch = 0;
+  pl->grouped = false;
 #define PUSH(expr)        \
   do {                    \
     rc = (expr);          \
@@ -1015,13 +1108,27 @@ extern "C" int vsr_srfbn_bind(vsr_srfbn_plan* pl, const void* dev_weights, void*
         PUSH(build_downconv2(L, down_in, M, h, w, Wp(W_DOWN0 + i), Bp(W_DOWN0 + i), ws + pl->o_lr[i + 1]));
         continue;
       }
-      PUSH(build_deconv(L, up_in, M, h, w, Wp(W_UP0 + i), Bp(W_UP0 + i), ws + pl->o_hr[i], 0));
-      {  // downtran(cat(hr[0..i])) + downBlocks[i], fused; sums land in the fp32 LR accumulator
+      {  // upBlocks[i], then downtran(cat(hr[0..i])) + downBlocks[i] fused; sums land in the fp32 LR accumulator
+        Layer D, F;
+        rc = build_deconv(D, up_in, M, h, w, Wp(W_UP0 + i), Bp(W_UP0 + i), ws + pl->o_hr[i], 0);
+        if (rc) return rc;
         const void* hrs[6];
         for (int j = 0; j <= i; ++j) hrs[j] = ws + pl->o_hr[j];
-        PUSH(build_fused_down(L, hrs, i + 1, M, h, w, i > 0 ? Wp(W_DOWNTRAN0 + i - 1) : nullptr,
+        rc = build_fused_down(F, hrs, i + 1, M, h, w, i > 0 ? Wp(W_DOWNTRAN0 + i - 1) : nullptr,
                               i > 0 ? Bp(W_DOWNTRAN0 + i - 1) : nullptr, Wp(W_DOWN0 + i), Bp(W_DOWN0 + i),
-                              reinterpret_cast<float*>(ws + pl->o_acc), ws + pl->o_lr[i + 1]));
+                              reinterpret_cast<float*>(ws + pl->o_acc), ws + pl->o_lr[i + 1]);
+        if (rc) return rc;
+        const int n_spatial = M * F.f.tiles_x * F.f.tiles_y;
+        if (group_enabled() && n_spatial >= 4 * kNumSMs) {
+          // one launch: the deconv role publishes hr[i] tile by tile, the fused role takes it from L2
+          PUSH(build_group(L, D, F, i, reinterpret_cast<int32_t*>(ws + pl->o_flags), ++group_epoch, n_spatial));
+          pl->grouped = true;
+        } else {
+          L = D;
+          pl->layers.push_back(L);
+          L = F;
+          pl->layers.push_back(L);
+        }
         PUSH(build_finalize(L, reinterpret_cast<float*>(ws + pl->o_acc), Bp(W_DOWN0 + i), ws + pl->o_lr[i + 1], P, h, w));
       }
     }
@@ -1056,6 +1163,10 @@ extern "C" int vsr_srfbn_forward_u8(vsr_srfbn_plan* pl, const float* x, float* y
   auto mark = [&]() {
     if (pl->profile && ev < pl->events.size()) cudaEventRecord(pl->events[ev++], st);
   };
+  if (pl->grouped) {
+    cudaError_t e = cudaMemsetAsync(pl->ws + pl->o_flags, 0, pl->flags_bytes, st);
+    if (e != cudaSuccess) return cuda_status(e);
+  }
   mark();
   {
     int64_t blocks = ceil_div64(P, 256);
@@ -1089,7 +1200,7 @@ extern "C" int vsr_srfbn_forward_u8(vsr_srfbn_plan* pl, const float* x, float* y
 extern "C" const char* vsr_srfbn_kernel_class_name(int k) {
   static const char* names[KC_COUNT] = {"im2col", "conv_in_gemm", "pointwise_lr", "pointwise_hr", "deconv8x8s4",
                                         "conv8x8s4", "conv_out3x3", "fc_fuse", "fused_downtran_conv8x8s4",
-                                        "finalize_lr"};
+                                        "finalize_lr", "group(deconv8x8s4+fused_downtran_conv8x8s4)"};
   return (k >= 0 && k < KC_COUNT) ? names[k] : "?";
 }
 
@@ -1142,6 +1253,17 @@ extern "C" int vsr_srfbn_profile_launches(vsr_srfbn_plan* pl, float* ms, int32_t
     kclass[i] = i == 0 ? KC_IM2COL : (i == n - 1 ? KC_FC : pl->layers[i - 1].kclass);
   }
   return (int)n;
+}
+
+extern "C" int vsr_srfbn_debug_group_error(const vsr_srfbn_plan* pl, vsr_stream_t stream) {
+  if (!pl) return -1;
+  if (!pl->bound) return -1;
+  if (!pl->grouped) return 0;
+  int32_t v[2] = {0, 0};
+  cudaStream_t st = as_stream(stream);
+  if (cudaMemcpyAsync(v, pl->ws + pl->o_flags, sizeof(v), cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+  if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+  return v[1];
 }
 
 extern "C" int vsr_srfbn_debug_premix(const vsr_srfbn_plan* pl, float* out_maps, vsr_stream_t stream) {
