@@ -208,7 +208,23 @@ def test_c4_2x_4k_conv_stack_full_size_is_deterministic_and_tiling_consistent():
     b = yc[:, :, 2 * m:2 * (ch - m), 2 * m:2 * (cw - m)]
     assert a.shape == b.shape and a.numel() > 0
     assert (a - b).abs().max().item() <= 1e-2 * (a.abs().mean().item() + 1.0)
-    del sr, y1, y2, yc, x
+    del sr, y2, yc
+    gc.collect()
+    torch.cuda.empty_cache()
+    # the same frame under a 40 GB workspace cap: 2 maps at a time instead of 14 (89 GB), bit-identical
+    cap = SRProjectionModule(num_maps=M, upscale_factor=2, workspace_cap_bytes=40 << 30)
+    torch.manual_seed(0)
+    fresh = SRProjectionModule(num_maps=M, upscale_factor=2)
+    with torch.no_grad():
+        for n, p in fresh.named_parameters():
+            if n.endswith(".0.weight") and not n.startswith(("sub_mean", "add_mean")):
+                p.mul_(2.3)
+    cap.load_state_dict(fresh.state_dict())
+    y3 = cap(x)
+    ent = next(iter(cap._plans.values()))
+    assert ent["chunk_maps"] == 2 and ent["workspace"].numel() <= 40 << 30
+    assert torch.equal(y3, y1)
+    del cap, fresh, y1, y3, x
     gc.collect()
     torch.cuda.empty_cache()
 

@@ -170,3 +170,32 @@ def test_group_launch_matches_separate_launches_bit_for_bit(monkeypatch):
     for _ in range(3):
         y = mod(x)
     assert torch.equal(y, outs["1"][1]) and not mod.group_error()
+
+
+@pytest.mark.parametrize("scale", [4, 2])
+def test_workspace_cap_chunks_the_maps_bit_identically(scale):
+    """vsr_srfbn_plan_set_workspace_cap: the plan sweeps its layers over chunks of maps (the largest divisor of M that
+    fits); the maps are independent until the fc fuse, so every chunking gives the unchunked result bit for bit."""
+    M, h, w = 6, 17, 26
+    sd = so.init_state_dict(num_maps=M, seed=5, gain=2.3, upscale=scale)
+    x = (torch.rand((M, 3, h, w), generator=torch.Generator().manual_seed(6)) * 255).to(DEV)
+    ref = SRProjectionModule(num_maps=M, upscale_factor=scale)
+    ref.load_state_dict(sd)
+    want_maps, want = ref.premix(x), ref(x)
+    ent = next(iter(ref._plans.values()))
+    full = ent["workspace"].numel()
+    assert ent["chunk_maps"] == M
+    for frac, chunk in ((0.75, 3), (0.45, 2), (0.22, 1)):
+        mod = SRProjectionModule(num_maps=M, upscale_factor=scale, workspace_cap_bytes=int(full * frac))
+        mod.load_state_dict(sd)
+        y = mod(x)
+        e = next(iter(mod._plans.values()))
+        assert e["chunk_maps"] == chunk and e["workspace"].numel() <= full * frac, (frac, e["chunk_maps"])
+        assert torch.equal(y, want) and torch.equal(mod.premix(x), want_maps)
+        mod.profile(True)                                   # the per-launch accounting covers every chunk sweep
+        mod(x)
+        prof = mod.profile_read()
+        mod.profile(False)
+        assert prof["im2col"]["launches"] == M // chunk and prof["fc_fuse"]["launches"] == 1
+    with pytest.raises(Exception, match="workspace"):
+        SRProjectionModule(num_maps=M, upscale_factor=scale, workspace_cap_bytes=1 << 16)(x)

@@ -73,6 +73,8 @@ SIGNATURES = {
     "vsr_estimate_slot": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "vsr_srfbn_plan_create": (c_int, [ctypes.POINTER(SrfbnConfig), ctypes.POINTER(c_void_p)]),
     "vsr_srfbn_plan_destroy": (None, [c_void_p]),
+    "vsr_srfbn_plan_set_workspace_cap": (c_int, [c_void_p, c_size_t]),
+    "vsr_srfbn_chunk_maps": (c_int, [c_void_p]),
     "vsr_srfbn_weight_bytes": (c_size_t, [c_void_p]),
     "vsr_srfbn_workspace_bytes": (c_size_t, [c_void_p]),
     "vsr_srfbn_pack_weights": (c_int, [c_void_p, ctypes.POINTER(SrfbnWeights), c_void_p]),

@@ -881,6 +881,8 @@ struct vsr_srfbn_plan {
   // workspace offsets
   size_t o_a0, o_c128, o_xfeat, o_hidden, o_lr[7], o_u, o_hr[6], o_hb, o_ht, o_acc, o_premix, o_flags, flags_bytes, ws_bytes;
   bool grouped;           // group launches in the layer list: the flags are zeroed at the start of every forward
+  int chunk_maps;         // maps processed per sweep over the layer list (a divisor of num_maps; == num_maps: no chunking)
+  size_t ws_cap;          // caller's workspace cap in bytes (0 = none)
   bool bound;
   const uint8_t* dev_w;
   uint8_t* ws;
@@ -918,10 +920,12 @@ static void layout_weights(vsr_srfbn_plan* pl) {
   pl->weight_bytes = off;
 }
 
+// Activations are laid out for `chunk_maps` maps at a time (the maps are independent until the fc fuse, so the layer
+// list is swept once per chunk); only the per-map SR images in front of the fc fuse exist for all num_maps.
 static void layout_workspace(vsr_srfbn_plan* pl) {
   const vsr_srfbn_config& c = pl->cfg;
-  const size_t P = (size_t)c.num_maps * c.h * c.w;
-  const size_t Rb = (size_t)c.num_maps * (c.h + 1) * (c.w + 1) * 16;
+  const size_t P = (size_t)pl->chunk_maps * c.h * c.w;
+  const size_t Rb = (size_t)pl->chunk_maps * (c.h + 1) * (c.w + 1) * 16;
   size_t off = 0;
   auto put = [&](size_t bytes) {
     size_t o = off;
@@ -940,9 +944,9 @@ static void layout_workspace(vsr_srfbn_plan* pl) {
   pl->o_hb = put(P * s2 * 64);   // plain-NHWC result of the `out` deconv
   pl->o_ht = put(x2 ? P * s2 * 64 : 0);   // x2: downtran result (the x4 path keeps it on chip)
   pl->o_acc = put(x2 ? 0 : P * 512);   // fp32 partial slots of the fused down kernel
-  pl->o_premix = put(P * s2 * 3 * 4);
+  pl->o_premix = put((size_t)c.num_maps * c.h * c.w * s2 * 3 * 4);
   // hand-off flags of the group launches: fused_done, error, one counter per 16 x 8-block tile
-  pl->flags_bytes = x2 ? 0 : (64 + (size_t)c.num_maps * ceil_div(c.h + 1, 8) * ceil_div(c.w + 1, 16)) * 4;
+  pl->flags_bytes = x2 ? 0 : (64 + (size_t)pl->chunk_maps * ceil_div(c.h + 1, 8) * ceil_div(c.w + 1, 16)) * 4;
   pl->o_flags = put(pl->flags_bytes);
   pl->ws_bytes = off;
 }
@@ -964,11 +968,30 @@ extern "C" int vsr_srfbn_plan_create(const vsr_srfbn_config* cfg, vsr_srfbn_plan
   pl->ws = nullptr;
   pl->conv_out_layer = -1;
   pl->profile = false;
+  pl->chunk_maps = cfg->num_maps;
+  pl->ws_cap = 0;
   layout_weights(pl);
   layout_workspace(pl);
   *out_plan = pl;
   return VSR_OK;
 }
+
+extern "C" int vsr_srfbn_plan_set_workspace_cap(vsr_srfbn_plan* pl, size_t cap_bytes) {
+  if (!pl) return VSR_ERR_INVALID_ARG;
+  if (pl->bound) return VSR_ERR_STATE;                // the layer list is built for a chunk size: set the cap before bind
+  pl->ws_cap = cap_bytes;
+  // the largest divisor of num_maps whose workspace fits under the cap (no ragged tail chunk: one layer list)
+  const int M = pl->cfg.num_maps;
+  for (int mc = M; mc >= 1; --mc) {
+    if (M % mc) continue;
+    pl->chunk_maps = mc;
+    layout_workspace(pl);
+    if (cap_bytes == 0 || pl->ws_bytes <= cap_bytes) return VSR_OK;
+  }
+  return VSR_ERR_WORKSPACE;                            // not even one map at a time fits
+}
+
+extern "C" int vsr_srfbn_chunk_maps(const vsr_srfbn_plan* pl) { return pl ? pl->chunk_maps : 0; }
 
 extern "C" void vsr_srfbn_plan_destroy(vsr_srfbn_plan* plan) {
   if (!plan) return;
@@ -1053,9 +1076,8 @@ extern "C" int vsr_srfbn_bind(vsr_srfbn_plan* pl, const void* dev_weights, void*
   pl->ws = reinterpret_cast<uint8_t*>(dev_workspace);
   pl->layers.clear();
   const vsr_srfbn_config& c = pl->cfg;
-  const int M = c.num_maps, h = c.h, w = c.w;
+  const int M = pl->chunk_maps, h = c.h, w = c.w;     // the layers are built for one chunk of maps
   const int64_t P = (int64_t)M * h * w;
-  const int64_t Rb = (int64_t)M * (h + 1) * (w + 1) * 16;
   uint8_t* ws = pl->ws;
   auto Wp = [&](int id) { return (const void*)(pl->dev_w + pl->we[id].w_off); };
   auto Bp = [&](int id) { return reinterpret_cast<const float*>(pl->dev_w + pl->we[id].b_off); };
@@ -1158,29 +1180,37 @@ extern "C" int vsr_srfbn_forward_u8(vsr_srfbn_plan* pl, const float* x, float* y
   if (!pl->bound) return VSR_ERR_STATE;
   cudaStream_t st = as_stream(stream);
   const vsr_srfbn_config& c = pl->cfg;
-  const int64_t P = (int64_t)c.num_maps * c.h * c.w;
+  const int Mc = pl->chunk_maps;
+  const int64_t P = (int64_t)Mc * c.h * c.w;
   size_t ev = 0;
   auto mark = [&]() {
     if (pl->profile && ev < pl->events.size()) cudaEventRecord(pl->events[ev++], st);
   };
-  if (pl->grouped) {
-    cudaError_t e = cudaMemsetAsync(pl->ws + pl->o_flags, 0, pl->flags_bytes, st);
-    if (e != cudaSuccess) return cuda_status(e);
-  }
-  mark();
-  {
-    int64_t blocks = ceil_div64(P, 256);
-    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-    im2col_kernel<<<(int)blocks, 256, 0, st>>>(x, reinterpret_cast<const float*>(pl->dev_w + pl->misc_off),
-                                               reinterpret_cast<uint4*>(pl->ws + pl->o_a0), c.num_maps, c.h, c.w);
-    int rc = after_launch();
-    if (rc) return rc;
-  }
-  pl->layers[pl->conv_out_layer].p.skip_src = x;
-  for (const Layer& L : pl->layers) {
+  for (int m0 = 0; m0 < c.num_maps; m0 += Mc) {        // one sweep over the layer list per chunk of maps
+    const float* xc = x + (int64_t)m0 * 3 * c.h * c.w;
+    if (pl->grouped) {
+      cudaError_t e = cudaMemsetAsync(pl->ws + pl->o_flags, 0, pl->flags_bytes, st);
+      if (e != cudaSuccess) return cuda_status(e);
+    }
     mark();
-    int rc = launch_layer(L, st);
-    if (rc) return rc;
+    {
+      int64_t blocks = ceil_div64(P, 256);
+      if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+      im2col_kernel<<<(int)blocks, 256, 0, st>>>(xc, reinterpret_cast<const float*>(pl->dev_w + pl->misc_off),
+                                                 reinterpret_cast<uint4*>(pl->ws + pl->o_a0), Mc, c.h, c.w);
+      int rc = after_launch();
+      if (rc) return rc;
+    }
+    {   // the last layer reads the network input (bilinear skip) and writes this chunk's maps of the premix buffer
+      IgemmParams& cp = pl->layers[pl->conv_out_layer].p;
+      cp.skip_src = xc;
+      cp.out = reinterpret_cast<float*>(pl->ws + pl->o_premix) + (int64_t)m0 * 3 * c.upscale * c.upscale * c.h * c.w;
+    }
+    for (const Layer& L : pl->layers) {
+      mark();
+      int rc = launch_layer(L, st);
+      if (rc) return rc;
+    }
   }
   mark();
   {
@@ -1209,7 +1239,7 @@ extern "C" int vsr_srfbn_profile_enable(vsr_srfbn_plan* pl, int enable) {
   if (!pl->bound) return VSR_ERR_STATE;
   pl->profile = enable != 0;
   if (pl->profile && pl->events.empty()) {
-    pl->events.resize(pl->layers.size() + 3);
+    pl->events.resize((pl->layers.size() + 1) * (size_t)(pl->cfg.num_maps / pl->chunk_maps) + 2);
     for (cudaEvent_t& e : pl->events) {
       cudaError_t r = cudaEventCreate(&e);
       if (r != cudaSuccess) return cuda_status(r);
@@ -1225,17 +1255,17 @@ extern "C" int vsr_srfbn_profile_read(vsr_srfbn_plan* pl, double* ms, int32_t* l
   cudaError_t r = cudaEventSynchronize(pl->events.back());
   if (r != cudaSuccess) return cuda_status(r);
   const vsr_srfbn_config& c = pl->cfg;
-  const double P = (double)c.num_maps * c.h * c.w;
-  const size_t n = pl->layers.size() + 2;
+  const double Pc = (double)pl->chunk_maps * c.h * c.w, Pall = (double)c.num_maps * c.h * c.w;
+  const size_t per = pl->layers.size() + 1, n = pl->events.size() - 1;     // launches per chunk sweep; intervals
   for (size_t i = 0; i < n; ++i) {
     float t = 0;
     r = cudaEventElapsedTime(&t, pl->events[i], pl->events[i + 1]);
     if (r != cudaSuccess) return cuda_status(r);
     int k;
     double f, b;
-    if (i == 0) { k = KC_IM2COL; f = 0; b = P * (12.0 + 64.0); }
-    else if (i == n - 1) { const double s2 = (double)c.upscale * c.upscale; k = KC_FC; f = s2 * P / c.num_maps * 3 * 2.0 * (32.0 * c.num_maps + 32.0); b = s2 * P * 12.0 + s2 * P / c.num_maps * 12.0; }
-    else { const Layer& L = pl->layers[i - 1]; k = L.kclass; f = L.flops; b = L.bytes; }
+    if (i == n - 1) { const double s2 = (double)c.upscale * c.upscale; k = KC_FC; f = s2 * Pall / c.num_maps * 3 * 2.0 * (32.0 * c.num_maps + 32.0); b = s2 * Pall * 12.0 + s2 * Pall / c.num_maps * 12.0; }
+    else if (i % per == 0) { k = KC_IM2COL; f = 0; b = Pc * (12.0 + 64.0); }
+    else { const Layer& L = pl->layers[i % per - 1]; k = L.kclass; f = L.flops; b = L.bytes; }
     ms[k] += t; launches[k] += 1; flops[k] += f; bytes[k] += b;
   }
   return VSR_OK;
@@ -1245,12 +1275,12 @@ extern "C" int vsr_srfbn_profile_launches(vsr_srfbn_plan* pl, float* ms, int32_t
   if (!pl || !ms || !kclass) return -1;
   if (!pl->bound || pl->events.empty()) return -1;
   if (cudaEventSynchronize(pl->events.back()) != cudaSuccess) return -1;
-  const size_t n = pl->layers.size() + 2;
+  const size_t per = pl->layers.size() + 1, n = pl->events.size() - 1;
   for (size_t i = 0; i < n && (int32_t)i < capacity; ++i) {
     float t = 0;
     cudaEventElapsedTime(&t, pl->events[i], pl->events[i + 1]);
     ms[i] = t;
-    kclass[i] = i == 0 ? KC_IM2COL : (i == n - 1 ? KC_FC : pl->layers[i - 1].kclass);
+    kclass[i] = i == n - 1 ? KC_FC : (i % per == 0 ? KC_IM2COL : pl->layers[i % per - 1].kclass);
   }
   return (int)n;
 }

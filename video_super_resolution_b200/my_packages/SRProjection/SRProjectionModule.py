@@ -62,7 +62,7 @@ class _FeedbackParams(nn.Module):
 
 class SRProjectionModule(nn.Module):
     def __init__(self, in_channels=3, out_channels=3, num_features=32, upscale_factor=4, num_steps=3, num_groups=6,
-                 act_type='prelu', norm_type=None, num_maps=8):
+                 act_type='prelu', norm_type=None, num_maps=8, workspace_cap_bytes=None):
         super(SRProjectionModule, self).__init__()
         if (in_channels, out_channels, num_features, num_groups) != (3, 3, 32, 6) \
                 or upscale_factor not in GEOMETRY or act_type != 'prelu' or norm_type is not None:
@@ -73,6 +73,8 @@ class SRProjectionModule(nn.Module):
         self.num_features = num_features
         self.upscale_factor = upscale_factor
         self.num_maps = num_maps
+        # optional cap on the activation workspace: the plan then processes the maps in chunks (bit-identical results)
+        self.workspace_cap_bytes = workspace_cap_bytes
         nf = num_features
         self.sub_mean = _MeanShift(RGB_MEAN, -1)
         self.conv_in = _block(nn.Conv2d(in_channels, 4 * nf, 3, padding=1))
@@ -134,7 +136,9 @@ class SRProjectionModule(nn.Module):
             cfg = _lib.SrfbnConfig(M, h, w, self.num_steps, 6, self.num_features, self.upscale_factor)
             plan = ctypes.c_void_p()
             _lib.check(L.vsr_srfbn_plan_create(ctypes.byref(cfg), ctypes.byref(plan)), "srfbn_plan_create")
-            ent = {"plan": plan, "version": None,
+            if self.workspace_cap_bytes:
+                _lib.check(L.vsr_srfbn_plan_set_workspace_cap(plan, int(self.workspace_cap_bytes)), "srfbn_plan_set_workspace_cap")
+            ent = {"plan": plan, "version": None, "chunk_maps": int(L.vsr_srfbn_chunk_maps(plan)),
                    "weights": torch.empty(int(L.vsr_srfbn_weight_bytes(plan)), dtype=torch.uint8, device=device),
                    "workspace": torch.empty(int(L.vsr_srfbn_workspace_bytes(plan)), dtype=torch.uint8, device=device)}
             self._plans[key] = ent
