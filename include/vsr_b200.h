@@ -48,7 +48,10 @@ const char* vsr_error_string(int code);
  * input1 (B,C,H,W) f32, flow (B,2,H,W) f32 (channel 0 horizontal), output (B,C,H,W) f32, all
  * NCHW contiguous.  Arithmetic is the reference's, bit for bit: fp32 coordinates, border-clamped
  * taps, tap weights formed in double, per-tap products rounded to fp32 and summed TL,TR,BL,BR.
- * kernel_size must be 1 (the only value the reference uses, resample2d.py:44).
+ * kernel_size 1 is the only value the reference uses (resample2d.py:44); 2..16 follow resample2d_kernel.cu:54-61: the
+ * four taps are summed again at every offset of a kernel_size x kernel_size window, un-normalised, with the
+ * reference's un-clamped NCHW address arithmetic (an offset past a row / plane end reads the next row / plane);
+ * addresses past the end of the tensor, where the reference reads out of bounds, are pinned to its last element.
  * ---------------------------------------------------------------------------------------- */
 int vsr_resample2d_forward(const float* input1, const float* flow, float* output,
                            int B, int C, int H, int W, int kernel_size, int bilinear,
@@ -90,6 +93,17 @@ int vsr_warp_labels_u8(const uint8_t* labels, const float* flow, uint8_t* dst,
  * and ignored exactly as the reference does (channelnorm_kernel.cu:53-59). */
 int vsr_channelnorm_forward(const float* input, float* output, int B, int C, int H, int W,
                             int norm_deg, vsr_stream_t stream);
+
+/* The other two dtypes of the reference's AT_DISPATCH_FLOATING_TYPES_AND_HALF (channelnorm_kernel.cu:111,152): fp16 and
+ * fp64 tensors, forward and backward, with the reference's arithmetic (square in the tensor's type, fp32 sum and sqrt,
+ * result cast back).  dtype: VSR_DTYPE_*; VSR_DTYPE_F32 forwards to the fp32 entry points. */
+#define VSR_DTYPE_F32 0
+#define VSR_DTYPE_F16 1
+#define VSR_DTYPE_F64 2
+int vsr_channelnorm_forward_typed(const void* input, void* output, int B, int C, int H, int W, int norm_deg, int dtype,
+                                  vsr_stream_t stream);
+int vsr_channelnorm_backward_typed(const void* input, const void* output, const void* grad_output, void* grad_input,
+                                   int B, int C, int H, int W, int norm_deg, int dtype, vsr_stream_t stream);
 
 /* Backward passes of the two autograd Functions.
  * ref: resample2d_cuda.cc:14-26 `resample2d_cuda_backward(input1, input2, gradOutput, gradInput1,

@@ -41,7 +41,7 @@ def test_host_side_entry_points_without_gpu():
     assert 3 * 1080 * 1920 * 16 <= L.vsr_flow_projection_workspace_bytes(8, 1080, 1920) < 3 * 1080 * 1920 * 17
     # argument validation happens before any CUDA call
     assert L.vsr_resample2d_forward(None, None, None, 1, 3, 4, 4, 1, 1, None) == 1
-    assert L.vsr_resample2d_forward(1, 1, 1, 1, 3, 4, 4, 3, 1, None) == 2  # kernel_size != 1
+    assert L.vsr_resample2d_forward(1, 1, 1, 1, 3, 4, 4, 17, 1, None) == 2  # kernel_size outside 1..16
 
 
 def test_ops_refuse_cpu_tensors():

@@ -210,3 +210,47 @@ def test_correlation_function_autograd():
             assert abs(num.item() - grad[0, 2, 5, 7].item()) <= 2e-2 * max(1.0, abs(num.item()))
     with pytest.raises(RuntimeError):
         ops.correlation_backward(a.detach(), b.detach(), w, 4, 1, 4, 2, 2, 1)          # stride1 != 1: unsupported
+
+
+@pytest.mark.parametrize("ks", [2, 3])
+def test_reference_resample2d_kernel_size_gt_1(ks):
+    """resample2d_kernel.cu:54-61: the taps summed over a ks x ks window with un-clamped NCHW address arithmetic.  Equal to
+    the reference binary wherever the reference stays inside its tensor (the last rows of the LAST plane read out of
+    bounds there; those outputs are excluded)."""
+    ref = _ref("resample2d_cuda")
+    B, C, H, W = 2, 3, 40, 56
+    g = torch.Generator().manual_seed(ks)
+    img = (torch.rand((B, C, H, W), generator=g) * 255).to(DEV)
+    flow = ((torch.rand((B, 2, H, W), generator=g) - 0.5) * 10).to(DEV)
+    # guard rows after the tensor so that the reference's out-of-bounds reads hit our own allocation, not a fault
+    big = torch.zeros((B * C * H + 8, W), device=DEV)
+    big[:B * C * H] = img.reshape(-1, W)
+    img_v = big[:B * C * H].view(B, C, H, W)
+    out = torch.zeros_like(img)
+    ref.forward(img_v, flow, out, ks, True)
+    torch.cuda.synchronize()
+    got = ops.resample2d(img_v, flow, ks, True)
+    ok = torch.ones((B, C, H, W), dtype=torch.bool, device=DEV)
+    ok[B - 1, C - 1, H - ks - 1:] = False                 # taps of these outputs may lie past the end of the tensor
+    assert torch.equal(got[ok], out[ok])
+    assert (got[ok] - ops.resample2d(img_v, flow, 1, True)[ok]).abs().max().item() > 1.0     # ks really matters
+    with pytest.raises(Exception):
+        ops.resample2d(img_v, flow, 17, True)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float64])
+def test_reference_channelnorm_fp16_fp64(dtype):
+    """The other dtypes of AT_DISPATCH_FLOATING_TYPES_AND_HALF (channelnorm_kernel.cu:111,152), forward and backward,
+    bit for bit against the reference binary."""
+    ref = _ref("channelnorm_cuda")
+    shape = (2, 3, 37, 50)
+    x = (torch.randn(shape, generator=torch.Generator().manual_seed(1)) * 20).to(DEV, dtype)
+    out = torch.zeros((shape[0], 1, shape[2], shape[3]), device=DEV, dtype=dtype)
+    ref.forward(x, out, 2)
+    gout = torch.randn(out.shape, generator=torch.Generator().manual_seed(2)).to(DEV, dtype)
+    gin = torch.zeros_like(x)
+    ref.backward(x, out, gout, gin, 2)
+    torch.cuda.synchronize()
+    got = ops.channelnorm(x)
+    assert got.dtype == dtype and torch.equal(got, out)
+    assert torch.equal(ops.channelnorm_backward(x, out, gout), gin)

@@ -58,6 +58,8 @@ SIGNATURES = {
     "vsr_compose_flow": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "vsr_warp_labels_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "vsr_channelnorm_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "vsr_channelnorm_forward_typed": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "vsr_channelnorm_backward_typed": (c_int, [c_void_p] * 4 + [c_int] * 6 + [c_void_p]),
     "vsr_resample2d_backward": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_void_p]),
     "vsr_channelnorm_backward": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),
     "vsr_correlation_output_shape": (c_int, [c_int] * 8 + [ctypes.POINTER(c_int)] * 3),

@@ -418,7 +418,7 @@ __device__ __forceinline__ void tma_load_4d_hint(void* smem_dst, const CUtensorM
 // the EPI_DECONV instance on CTAs [0, n_deconv) of its grid, with the tile hand-off `gs`.
 template <int MODE, int CK, int BN>
 __device__ __forceinline__ void igemm_body(const IgemmParams& p, const int cta, const int ncta, const GroupSync* gs) {
-  constexpr int kThreadsHere = MODE == EPI_DECONV ? kDeconvThreads : kIgemmThreads;
+  constexpr int kThreadsHere = (MODE == EPI_DECONV || MODE == EPI_DECONV2) ? kDeconvThreads : kIgemmThreads;
   constexpr int kEpiThreads = kThreadsHere - 64;
   static_assert(CK == 32 || CK == 64, "K chunk is 32 (64B swizzle) or 64 (128B swizzle) BF16");
   static_assert(BN == 16 || BN == 32 || BN == 128 || BN == 256, "supported N tiles");
@@ -689,15 +689,15 @@ __device__ __forceinline__ void igemm_body(const IgemmParams& p, const int cta, 
         const PreluCfg pc = make_prelu(s_bias[p.bias_n], 1);
         const int64_t W2 = 2 * (int64_t)p.lr_w;
         uint8_t* base = reinterpret_cast<uint8_t*>(p.out) + (((int64_t)t.b * 2 * p.lr_h + 2 * Y) * W2 + 2 * X) * 64;
-#pragma unroll 1
-        for (int cg = 0; cg < 4; ++cg) {
+        // 16 epilogue warps, 4 per TMEM lane quarter: each converts ONE of the four sub-positions (with 4 warps doing
+        // all four in turn the layer ran at 30 % of the write bandwidth: the epilogue, not the MMAs, was its floor)
+        {
+          const int cg = (warp - 2) >> 2;
           uint32_t v[32];
           tmem_ld32(taddr + cg * 32, v);
           tmem_ld_wait();
-          if (cg == 3) {
-            tc_fence_before();
-            mbar_arrive_warp(&tmem_empty[as]);
-          }
+          tc_fence_before();
+          mbar_arrive_warp(&tmem_empty[as]);
           if (valid) {
             uint32_t o[16];
             convert32(v, s_bias, pc, o);
@@ -776,7 +776,7 @@ __device__ __forceinline__ void igemm_body(const IgemmParams& p, const int cta, 
 }
 
 template <int MODE, int CK, int BN>
-__global__ void __launch_bounds__(MODE == EPI_DECONV ? kDeconvThreads : kIgemmThreads, 1)
+__global__ void __launch_bounds__((MODE == EPI_DECONV || MODE == EPI_DECONV2) ? kDeconvThreads : kIgemmThreads, 1)
 igemm_kernel(const __grid_constant__ IgemmParams p) {
   igemm_body<MODE, CK, BN>(p, (int)blockIdx.x, (int)gridDim.x, nullptr);
 }

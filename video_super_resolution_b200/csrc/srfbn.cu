@@ -140,7 +140,7 @@ int launch_variant(const Layer& L, cudaStream_t st) {
     if (e != cudaSuccess) return cuda_status(e);
     once.mark(dev);
   }
-  cudaError_t e = launch_pdl(igemm_kernel<MODE, CK, BN>, L.grid, MODE == EPI_DECONV ? kDeconvThreads : kIgemmThreads,
+  cudaError_t e = launch_pdl(igemm_kernel<MODE, CK, BN>, L.grid, (MODE == EPI_DECONV || MODE == EPI_DECONV2) ? kDeconvThreads : kIgemmThreads,
                              L.smem, st, L.p);
   if (e != cudaSuccess) return cuda_status(e);
   return after_launch();
@@ -453,6 +453,9 @@ int build_downconv2(Layer& L, const void* xhr, int B, int h, int w, const void* 
           c.a_off = (px * 3 + b) * kBox + a * (kTW * 64);
           c.tx = a == 0 ? kBox : 0;
         }
+  // one pipeline stage = the 18 taps of one row parity (6 boxes, 60 KB), 2 stages.  Measured (C4, per pass, 18 launches):
+  // this 121 ms; one box per stage x 14 stages 179 ms -- every stage hand-over costs the single MMA-issuing thread a
+  // barrier round trip, and 12 of them per 128-pixel tile outweigh the deeper prefetch.
   p.num_chunks = 36;
   p.cps = 18;
   p.stage_bytes = 6 * kBox;

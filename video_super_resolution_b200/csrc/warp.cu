@@ -8,6 +8,8 @@
 // of once per (pixel, channel); tap indices and weights are computed once per pixel; the
 // channels-last kernels move 16-byte vectors and stage the C=3 output through shared memory so
 // that every global store is a full 128-bit coalesced transaction.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace vsr {
@@ -77,6 +79,12 @@ __device__ __forceinline__ Taps bilinear_taps(int x, int y, float dx, float dy, 
 }
 
 // :56-59 TL,TR,BL: product in double, rounded to fp32, fp32 add; BR: one fp32 FMA
+__device__ __forceinline__ float blend_acc(const Taps& t, float v, float tl, float tr, float bl, float br) {
+  v = __fadd_rn(v, __double2float_rn(__dmul_rn(t.wTL, (double)tl)));
+  v = __fadd_rn(v, __double2float_rn(__dmul_rn(t.wTR, (double)tr)));
+  v = __fadd_rn(v, __double2float_rn(__dmul_rn(t.wBL, (double)bl)));
+  return fmaf(t.wBR, br, v);
+}
 __device__ __forceinline__ float blend(const Taps& t, float tl, float tr, float bl, float br) {
   float v = 0.0f;
   v = __fadd_rn(v, __double2float_rn(__dmul_rn(t.wTL, (double)tl)));
@@ -123,7 +131,7 @@ __device__ __forceinline__ void nearest_tap(int x, int y, float dx, float dy, in
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
 resample2d_nchw_kernel(const float* __restrict__ in1, const float* __restrict__ flow, float* __restrict__ out,
-                       int B, int C, int H, int W, int bilinear, const PixDecode pd) {
+                       int B, int C, int H, int W, int bilinear, const PixDecode pd, int ks) {
   const int64_t HW = (int64_t)H * W;
   const int64_t n = (int64_t)B * HW;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -133,7 +141,26 @@ resample2d_nchw_kernel(const float* __restrict__ in1, const float* __restrict__ 
     float dx = __ldg(fl), dy = __ldg(fl + HW);
     const float* src = in1 + (int64_t)b * C * HW;
     float* dst = out + (int64_t)b * C * HW + (int64_t)y * W + x;
-    if (bilinear) {
+    if (bilinear && ks > 1) {
+      // resample2d_kernel.cu:54-61: the four taps are summed again at every offset (fy, fx) of a ks x ks window,
+      // un-normalised and UN-CLAMPED: (yT + fy, xL + fx) is plain NCHW address arithmetic, so an offset past the row /
+      // plane end reads the next row / plane, exactly as the reference does.  Only addresses past the end of the whole
+      // tensor (the reference reads out of bounds there) are pinned to its last element.
+      Taps t = bilinear_taps(x, y, dx, dy, W, H);
+      const int64_t last = (int64_t)B * C * HW - 1;
+      for (int c = 0; c < C; ++c) {
+        const int64_t base = ((int64_t)b * C + c) * HW;
+        float val = 0.0f;
+        for (int fy = 0; fy < ks; ++fy)
+          for (int fx = 0; fx < ks; ++fx) {
+            const int64_t iTL = base + (int64_t)(t.yT + fy) * W + t.xL + fx, iTR = base + (int64_t)(t.yT + fy) * W + t.xR + fx;
+            const int64_t iBL = base + (int64_t)(t.yB + fy) * W + t.xL + fx, iBR = base + (int64_t)(t.yB + fy) * W + t.xR + fx;
+            val = blend_acc(t, val, __ldg(in1 + min(iTL, last)), __ldg(in1 + min(iTR, last)), __ldg(in1 + min(iBL, last)),
+                            __ldg(in1 + min(iBR, last)));
+          }
+        dst[(int64_t)c * HW] = val;
+      }
+    } else if (bilinear) {
       Taps t = bilinear_taps(x, y, dx, dy, W, H);
       int64_t oTL = (int64_t)t.yT * W + t.xL, oTR = (int64_t)t.yT * W + t.xR;
       int64_t oBL = (int64_t)t.yB * W + t.xL, oBR = (int64_t)t.yB * W + t.xR;
@@ -364,6 +391,43 @@ warp_labels_kernel(const uint8_t* __restrict__ labels, const float* __restrict__
   }
 }
 
+// channelnorm_kernel.cu:19-60 for the other two dtypes of its AT_DISPATCH_FLOATING_TYPES_AND_HALF (:111): `val * val` is
+// evaluated in scalar_t (c10::Half: float product rounded to half; double: double product), cast to float and summed
+// in fp32; sqrt in fp32; the result cast back to scalar_t.
+__device__ __forceinline__ float sq_as(const __half v) { return __half2float(__float2half_rn(__half2float(v) * __half2float(v))); }
+__device__ __forceinline__ float sq_as(const double v) { return __double2float_rn(__dmul_rn(v, v)); }
+__device__ __forceinline__ void store_as(__half* p, float v) { *p = __float2half_rn(v); }
+__device__ __forceinline__ void store_as(double* p, float v) { *p = (double)v; }
+__device__ __forceinline__ float load_f(const __half* p) { return __half2float(*p); }
+__device__ __forceinline__ float load_f(const double* p) { return __double2float_rn(*p); }
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+channelnorm_nchw_typed_kernel(const T* __restrict__ in, T* __restrict__ out, int B, int C, int H, int W) {
+  const int64_t HW = (int64_t)H * W;
+  const int64_t n = (int64_t)B * HW;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / HW, p = i - b * HW;
+    const T* s = in + b * C * HW + p;
+    float acc = 0.0f;
+    for (int c = 0; c < C; ++c) acc = __fadd_rn(acc, sq_as(s[(int64_t)c * HW]));
+    store_as(out + i, sqrtf(acc));
+  }
+}
+// channelnorm_kernel.cu:64-96: val = float(g) * float(x) / (float(out) + 1e-9) [the literal makes it a double division],
+// rounded to float, cast to scalar_t
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+channelnorm_backward_typed_kernel(const T* __restrict__ in, const T* __restrict__ out, const T* __restrict__ gout,
+                                  T* __restrict__ gin, int C, int64_t HW, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / (C * HW);
+    const int64_t p = i % HW;
+    const int64_t oi = b * HW + p;
+    const float num = __fmul_rn(load_f(gout + oi), load_f(in + i));
+    store_as(gin + i, __double2float_rn(__ddiv_rn((double)num, __dadd_rn((double)load_f(out + oi), 1e-9))));
+  }
+}
+
 // channelnorm_kernel.cu:19-60, NCHW: one thread per (b, y, x), coalesced plane reads.
 __global__ void __launch_bounds__(kThreads)
 channelnorm_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int C, int H, int W) {
@@ -425,11 +489,12 @@ using namespace vsr;
 extern "C" int vsr_resample2d_forward(const float* input1, const float* flow, float* output, int B, int C, int H,
                                       int W, int kernel_size, int bilinear, vsr_stream_t stream) {
   if (!input1 || !flow || !output || B <= 0 || C <= 0 || H <= 0 || W <= 0) return VSR_ERR_INVALID_ARG;
-  if (kernel_size != 1) return VSR_ERR_UNSUPPORTED;  // resample2d.py:44: the only value ever used
+  if (kernel_size < 1 || kernel_size > 16) return VSR_ERR_UNSUPPORTED;  // resample2d.py:44 only ever uses 1
   int64_t n = (int64_t)B * H * W;
   if (n >= ((int64_t)1 << 32)) return VSR_ERR_UNSUPPORTED;   // 32-bit index decode
   resample2d_nchw_kernel<<<grid_for(n, kThreads), kThreads, 0, as_stream(stream)>>>(input1, flow, output, B, C, H, W,
-                                                                                   bilinear ? 1 : 0, make_pixdecode(H, W));
+                                                                                   bilinear ? 1 : 0, make_pixdecode(H, W),
+                                                                                   kernel_size);
   return after_launch();
 }
 
@@ -645,6 +710,48 @@ extern "C" int vsr_resample2d_backward(const float* input1, const float* flow, c
   if (rc) return rc;
   resample2d_backward_input2_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(input1, flow, grad_output, grad_input2, B, C, H,
                                                                                W, pd);
+  return after_launch();
+}
+
+extern "C" int vsr_channelnorm_forward_typed(const void* input, void* output, int B, int C, int H, int W, int norm_deg,
+                                             int dtype, vsr_stream_t stream) {
+  (void)norm_deg;
+  if (dtype == VSR_DTYPE_F32)
+    return vsr_channelnorm_forward(static_cast<const float*>(input), static_cast<float*>(output), B, C, H, W, norm_deg, stream);
+  if (!input || !output || B <= 0 || C <= 0 || H <= 0 || W <= 0) return VSR_ERR_INVALID_ARG;
+  const int64_t n = (int64_t)B * H * W;
+  cudaStream_t st = as_stream(stream);
+  if (dtype == VSR_DTYPE_F16)
+    channelnorm_nchw_typed_kernel<__half><<<grid_for(n, kThreads), kThreads, 0, st>>>(static_cast<const __half*>(input),
+                                                                                  static_cast<__half*>(output), B, C, H, W);
+  else if (dtype == VSR_DTYPE_F64)
+    channelnorm_nchw_typed_kernel<double><<<grid_for(n, kThreads), kThreads, 0, st>>>(static_cast<const double*>(input),
+                                                                                  static_cast<double*>(output), B, C, H, W);
+  else
+    return VSR_ERR_UNSUPPORTED;
+  return after_launch();
+}
+
+extern "C" int vsr_channelnorm_backward_typed(const void* input, const void* output, const void* grad_output,
+                                              void* grad_input, int B, int C, int H, int W, int norm_deg, int dtype,
+                                              vsr_stream_t stream) {
+  if (dtype == VSR_DTYPE_F32)
+    return vsr_channelnorm_backward(static_cast<const float*>(input), static_cast<const float*>(output),
+                                    static_cast<const float*>(grad_output), static_cast<float*>(grad_input), B, C, H, W,
+                                    norm_deg, stream);
+  if (!input || !output || !grad_output || !grad_input || B <= 0 || C <= 0 || H <= 0 || W <= 0) return VSR_ERR_INVALID_ARG;
+  const int64_t HW = (int64_t)H * W, n = (int64_t)B * C * HW;
+  cudaStream_t st = as_stream(stream);
+  if (dtype == VSR_DTYPE_F16)
+    channelnorm_backward_typed_kernel<__half><<<grid_for(n, kThreads), kThreads, 0, st>>>(
+        static_cast<const __half*>(input), static_cast<const __half*>(output), static_cast<const __half*>(grad_output),
+        static_cast<__half*>(grad_input), C, HW, n);
+  else if (dtype == VSR_DTYPE_F64)
+    channelnorm_backward_typed_kernel<double><<<grid_for(n, kThreads), kThreads, 0, st>>>(
+        static_cast<const double*>(input), static_cast<const double*>(output), static_cast<const double*>(grad_output),
+        static_cast<double*>(grad_input), C, HW, n);
+  else
+    return VSR_ERR_UNSUPPORTED;
   return after_launch();
 }
 

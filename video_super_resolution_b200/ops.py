@@ -75,15 +75,18 @@ def resample2d_backward(input1: torch.Tensor, flow: torch.Tensor, grad_output: t
 
 def channelnorm_backward(x: torch.Tensor, out: torch.Tensor, grad_output: torch.Tensor, norm_deg: int = 2):
     """ref: ChannelNormFunction.backward (channelnorm.py:20-29)."""
+    if x.dtype not in _DTYPES:
+        raise TypeError(f"input1: expected fp32, fp16 or fp64, got {x.dtype}")
     for t, n in ((x, "input1"), (out, "output"), (grad_output, "grad_output")):
-        _req(t, torch.float32, n)
+        _req(t, x.dtype, n)
     B, C, H, W = x.shape
     if tuple(out.shape) != (B, 1, H, W) or tuple(grad_output.shape) != (B, 1, H, W):
         raise ValueError("channelnorm_backward: output / grad_output must be (B,1,H,W)")
     g = torch.empty_like(x)
     with torch.cuda.device(x.device):
-        _lib.check(_lib.lib().vsr_channelnorm_backward(x.data_ptr(), out.data_ptr(), grad_output.data_ptr(), g.data_ptr(),
-                                                       B, C, H, W, int(norm_deg), _stream()), "channelnorm_backward")
+        _lib.check(_lib.lib().vsr_channelnorm_backward_typed(x.data_ptr(), out.data_ptr(), grad_output.data_ptr(),
+                                                             g.data_ptr(), B, C, H, W, int(norm_deg), _DTYPES[x.dtype],
+                                                             _stream()), "channelnorm_backward")
     return g
 
 
@@ -205,14 +208,20 @@ def warp_labels(labels: torch.Tensor, flow: torch.Tensor) -> torch.Tensor:
     return dst
 
 
+_DTYPES = {torch.float32: 0, torch.float16: 1, torch.float64: 2}     # VSR_DTYPE_*
+
+
 def channelnorm(x: torch.Tensor, norm_deg: int = 2) -> torch.Tensor:
-    """x (B,C,H,W) -> (B,1,H,W).  ref: ChannelNormFunction.forward (channelnorm.py:8-18)."""
-    _req(x, torch.float32, "input1")
+    """x (B,C,H,W) fp32 / fp16 / fp64 -> (B,1,H,W) of the same dtype.  ref: ChannelNormFunction.forward
+    (channelnorm.py:8-18), dtypes of channelnorm_kernel.cu:111."""
+    if x.dtype not in _DTYPES:
+        raise TypeError(f"input1: expected fp32, fp16 or fp64, got {x.dtype}")
+    _req(x, x.dtype, "input1")
     B, C, H, W = x.shape
-    out = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device)
+    out = torch.empty((B, 1, H, W), dtype=x.dtype, device=x.device)
     with torch.cuda.device(x.device):
-        _lib.check(_lib.lib().vsr_channelnorm_forward(x.data_ptr(), out.data_ptr(), B, C, H, W, int(norm_deg),
-                                                      _stream()), "channelnorm")
+        _lib.check(_lib.lib().vsr_channelnorm_forward_typed(x.data_ptr(), out.data_ptr(), B, C, H, W, int(norm_deg),
+                                                            _DTYPES[x.dtype], _stream()), "channelnorm")
     return out
 
 
