@@ -209,17 +209,20 @@ class ClockSampler:
 # sub-records: the other BASELINE configurations, driver-visible
 # ------------------------------------------------------------------------------------------------
 def _median_ms(fn, iters, warm, torch):
+    """ms per call: `iters` calls back to back between two CUDA events (as the bench's steps are timed), median of 3."""
     for _ in range(warm):
         fn()
-    torch.cuda.synchronize()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
-    ev[0].record()
-    for i in range(iters):
-        fn()
-        ev[i + 1].record()
-    torch.cuda.synchronize()
-    ts = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(iters))
-    return ts[len(ts) // 2]
+    ts = []
+    for _ in range(3):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) / iters)
+    return sorted(ts)[1]
 
 
 def front_c3(dev, peaks):
@@ -237,7 +240,7 @@ def front_c3(dev, peaks):
                 "frac_hbm_8TBs": round(gb / 8000.0, 4)}
 
     out = {"config": "C3: DepthProjection (splat + normalise + hole fill) 1920x1080, batch 8, 29 B/pixel; warps at the same size",
-           "hbm_peak_measured_GBps": peaks["hbm"], "timing": "median of 20 calls after 5 warm-ups, CUDA events", "cases": {}}
+           "hbm_peak_measured_GBps": peaks["hbm"], "timing": "20 calls back to back between two CUDA events, median of 3 repeats, after 5 warm-ups", "cases": {}}
     inv = syn.inv_depth(B, h, w, seed=9).to(dev)
     smooth = syn.smooth_flow(B, h, w, 8.0, seed=1).to(dev)
     cases = {"smooth_pm8": smooth, "iid_pm64": syn.random_flow(B, h, w, 64.0, seed=8).to(dev)}

@@ -156,6 +156,31 @@ def test_step_u8_frame_from_the_fuse_kernel():
     assert r is u8b and torch.equal(u8b, u8)
 
 
+def test_graphed_step_replays_the_same_frame():
+    """The whole per-frame sequence captured into one CUDA graph: replays reproduce the eager frames bit for bit, for
+    changing inputs, on both projection paths (the gated cooperative fallback launch is part of the graph)."""
+    from video_super_resolution_b200.pipeline import GraphedStep
+    T, h, w = 5, 24, 40
+    M = 3 * T - 1
+    sr = SRProjectionModule(num_maps=M)
+    sr.load_state_dict(so.init_state_dict(num_maps=M, seed=1, gain=2.3))
+    for md in (None, 5.0):
+        pipe = WarpFusePipeline(T, h, w, sr, 4, device=DEV, max_disp=md)
+        g = GraphedStep(pipe, want_f32=True)
+        for seed in (3, 4, 5):
+            args = [t.to(DEV) for t in _inputs(T, h, w, seed=seed)]
+            u8 = torch.zeros((4 * h, 4 * w, 3), dtype=torch.uint8, device=DEV)
+            want = pipe.step(*args, out_u8=u8).clone()
+            g.load(*args)
+            got = g.replay()
+            assert torch.equal(got, want) and torch.equal(g.frame_u8, u8), (md, seed)
+    from video_super_resolution_b200 import _lib
+    _lib.launch_count_reset()
+    g.replay()
+    torch.cuda.synchronize()
+    assert _lib.launch_count() == 0          # a replay issues no launch calls of its own
+
+
 def test_module_surfaces_refuse_missing_estimators():
     from video_super_resolution_b200.my_packages.FlowProjection.FlowProjectionModule import FlowProjectionModule
     m = FlowProjectionModule()

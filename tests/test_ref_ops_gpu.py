@@ -231,7 +231,7 @@ def test_reference_resample2d_kernel_size_gt_1(ks):
     torch.cuda.synchronize()
     got = ops.resample2d(img_v, flow, ks, True)
     ok = torch.ones((B, C, H, W), dtype=torch.bool, device=DEV)
-    ok[B - 1, C - 1, H - ks - 1:] = False                 # taps of these outputs may lie past the end of the tensor
+    ok[B - 1, C - 1, H - ks - 7:] = False          # |flow| <= 5: taps of these outputs may lie past the end of the tensor
     assert torch.equal(got[ok], out[ok])
     assert (got[ok] - ops.resample2d(img_v, flow, 1, True)[ok]).abs().max().item() > 1.0     # ks really matters
     with pytest.raises(Exception):

@@ -135,6 +135,48 @@ class WarpFusePipeline:
         return self.sr(self.stack, out_u8=out_u8, want_f32=want_f32)           # pass 2 (fuse)
 
 
+class GraphedStep:
+    """The per-frame sequence of WarpFusePipeline.step captured once into a CUDA graph and replayed:
+    ~190 launches (projection stages, flow chains, warps, stack, two conv-stack passes) become one graph launch.
+    Inputs live in static device buffers (`inputs`: copy -- or H2D-copy -- each window into them, then `replay()`);
+    outputs are the static `frame_u8` (s*h, s*w, 3) and, with want_f32, `frame` (1,3,s*h,s*w).
+    The step is GPU-bound (100 ms of kernels against ~1 ms of launch calls), so this buys little at C2; it matters for
+    small frames, where the front's 40 launches of 5-10 us each are launch-latency bound."""
+
+    def __init__(self, pipe: "WarpFusePipeline", want_f32: bool = False, warmup: int = 2):
+        T, h, w, s, dev = pipe.T, pipe.h, pipe.w, pipe.scale, pipe.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.pipe = pipe
+        self.inputs = {"frames": torch.zeros((T, h, w, 3), **f32), "flows": torch.zeros((T - 1, h, w, 2), **f32),
+                       "inv_depth": torch.ones((T - 1, h, w), **f32), "logits_a": torch.zeros((h, w), **f32),
+                       "logits_b": torch.zeros((h, w), **f32)}
+        self.frame_u8 = torch.empty((s * h, s * w, 3), dtype=torch.uint8, device=dev)
+        self.frame = None
+        i = self.inputs
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):          # warm-up on the capture stream: plans, function attributes, workspaces
+            for _ in range(max(warmup, 1)):
+                pipe.step(i["frames"], i["flows"], i["inv_depth"], i["logits_a"], i["logits_b"], out_u8=self.frame_u8,
+                          want_f32=want_f32)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            y = pipe.step(i["frames"], i["flows"], i["inv_depth"], i["logits_a"], i["logits_b"], out_u8=self.frame_u8,
+                          want_f32=want_f32)
+        if want_f32:
+            self.frame = y
+
+    def load(self, frames, flows, inv_depth, logits_a, logits_b, non_blocking=True):
+        for k, v in zip(("frames", "flows", "inv_depth", "logits_a", "logits_b"), (frames, flows, inv_depth, logits_a, logits_b)):
+            self.inputs[k].copy_(v, non_blocking=non_blocking)
+
+    def replay(self):
+        self.graph.replay()
+        return self.frame if self.frame is not None else self.frame_u8
+
+
 def quantise_u8(frame: torch.Tensor) -> torch.Tensor:
     """(1,3,H,W) fp32 0..255 -> (H,W,3) u8, the format the reference's loader reads (utils/video_utils.py:23)."""
     return frame[0].clamp(0, 255).round().to(torch.uint8).permute(1, 2, 0).contiguous()
