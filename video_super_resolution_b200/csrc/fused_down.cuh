@@ -62,6 +62,7 @@ struct alignas(64) FusedDownParams {
   const float* down_bias;             // [32] biases + [1] PReLU slope of the strided conv
   float* part;                        // (B, h, w, 4 slots, 32) fp32 partial sums of the BOUNDARY pixels (see final epilogue)
   void* lr_out;                       // (B, h, w, 32) bf16: finished interior pixels
+  long long* trace;                   // VSR_KNOCKOUT builds: clock64 stamps of CTA 0's roles, [tile][32]; nullptr = off
   int32_t xchg;                       // 1: tile rows 1,3,5 are finished too (row partials exchanged between lane quarters
                                       // through shared memory); 0: only the even tile rows
 };
@@ -95,6 +96,12 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
                : "r"(taddr)
                : "memory");
 }
+
+#ifdef VSR_KNOCKOUT
+#define VSR_TRACE(slot) do { if (p.trace && cta == 0 && tile_n < 1024) p.trace[tile_n * 32 + (slot)] = clock64(); } while (0)
+#else
+#define VSR_TRACE(slot) do { } while (0)
+#endif
 
 template <bool HAS_TRAN>
 inline size_t fused_down_smem_bytes(int nsrc, int num_stages, int wd_resident, int xchg) {
@@ -207,10 +214,13 @@ __device__ __forceinline__ void fused_body(const FusedDownParams& p, const int c
           if (++hf == 2) { hf = 0; t += ncta; }
         }
       }
+      int tile_n = -1;
       for (int tile = cta; tile < total_tiles; tile += ncta) {
+        ++tile_n;
         int x0, y0, b;
         tile_coord(tile, x0, y0, b);
         bool newest_ready = false;
+        VSR_TRACE(0);
         for (int half = 0; half < 2; ++half) {
           if (kAhead > 0) {  // the half-tile kAhead units ahead of (tile, half)
             const int u = half + kAhead;
@@ -239,6 +249,7 @@ __device__ __forceinline__ void fused_body(const FusedDownParams& p, const int c
                 if (++s == p.num_stages) { s = 0; phase ^= 1; }
               }
             }
+            VSR_TRACE(1 + half);
           } else {
             for (int g = half * 2; g < half * 2 + 2; ++g) {
               mbar_wait(&empty_bar[s], phase ^ 1);
@@ -340,12 +351,14 @@ __device__ __forceinline__ void fused_body(const FusedDownParams& p, const int c
     // HAS_TRAN: this thread issues phase A only; phase B has its own issuing thread (warp kFusedBWarp), so
     // that waiting for the converted tile / the weights never holds up the consumption of TMA stages.
     // tcgen05.commit tracks the MMAs of the issuing thread, so each thread signals exactly its own work.
+    int tile_n = -1;
     for (int tile = cta; tile < total_tiles; tile += ncta) {
+      ++tile_n;
       if (HAS_TRAN) {
         if (warp == 1) {
-          for (int g = 0; g < 4; ++g) issue_a(g);
+          for (int g = 0; g < 4; ++g) { issue_a(g); VSR_TRACE(4 + g); }          // phase-A MMAs of group g issued
         } else {
-          for (int g = 0; g < 4; ++g) issue_b(g);
+          for (int g = 0; g < 4; ++g) { issue_b(g); VSR_TRACE(8 + g); }          // phase-B MMAs of group g issued
         }
       } else {
         for (int g = 0; g < 4; ++g) issue_b(g);
@@ -384,7 +397,9 @@ __device__ __forceinline__ void fused_body(const FusedDownParams& p, const int c
     uint32_t m_a[2] = {0, 0}, m_b[2] = {0, 0}, m_h = 0;
     int tb = 0;
     const PreluCfg pc = make_prelu(HAS_TRAN ? s_bias[32] : 1.0f, 1);
+    int tile_n = -1;
     for (int tile = cta; tile < total_tiles; tile += ncta) {
+      ++tile_n;
       int x0, y0, b;
       tile_coord(tile, x0, y0, b);
       const int Yb = y0 + (row >> 4), Xb = x0 + (row & 15);
@@ -395,6 +410,7 @@ __device__ __forceinline__ void fused_body(const FusedDownParams& p, const int c
           const int buf = g & 1;
           mbar_wait_sleep(&da_full[buf], m_a[buf] & 1, (uint32_t)(VSR_DBG(p) >> 8));
           tc_fence_after();
+          if (warp == 2 && lane == 0) VSR_TRACE(12 + g);                          // D_A of group g complete (seen by the epilogue)
           uint32_t o[16];
           if (VSR_DBG(p) & 2) {
             zero16(o);
@@ -413,7 +429,9 @@ __device__ __forceinline__ void fused_body(const FusedDownParams& p, const int c
             if (__builtin_expect(!(in_tensor && !ring), 0)) zero16(o);
           }
           ++m_a[buf];
+          if (warp == 2 && lane == 0) VSR_TRACE(16 + g);                          // converted, waiting for H to be free
           mbar_wait(h_empty, (m_h & 1) ^ 1);
+          if (warp == 2 && lane == 0) VSR_TRACE(20 + g);                          // H free
           // K index inside the group: k = sub*32 + c -> 64-element chunk kc = sub>>1, 16-byte piece (sub&1)*4 + j
           uint8_t* hrow = s_h + (sub >> 1) * 16384 + (row >> 3) * 1024 + (row & 7) * 128;
 #pragma unroll
@@ -439,8 +457,10 @@ __device__ __forceinline__ void fused_body(const FusedDownParams& p, const int c
       //    with exactly one writer each:  slot 2*dy   : tap (dy,0) + right neighbour's tap (dy,1)
       //                                   slot 2*dy+1 : tap (dy,1) arriving from the next tile
       //    finalize_lr_kernel sums them.  Same additions in the same order either way: deterministic.
+      if (warp == 2 && lane == 0) VSR_TRACE(24);                                  // H of the last group handed over
       mbar_wait_sleep(&db_full[tb], m_b[tb] & 1, (uint32_t)(VSR_DBG(p) >> 8));
       tc_fence_after();
+      if (warp == 2 && lane == 0) VSR_TRACE(25);                                  // D_B complete
       if (VSR_DBG(p) & 4) {
         tc_fence_before();
         mbar_arrive_warp(&db_empty[tb]);
@@ -510,6 +530,7 @@ __device__ __forceinline__ void fused_body(const FusedDownParams& p, const int c
           }
         }
       }
+      if (warp == 2 && lane == 0) VSR_TRACE(26);                                  // final epilogue of the tile done
       ++m_b[tb];
       tb ^= 1;
       // group launch: progress counter the deconv role throttles on (this warp has read the tile's accumulators, so

@@ -120,6 +120,10 @@ struct Layer {
 // TMA boxes in flight per SM yield at the loaded HBM latency -- so it only reaches the HBM roof with all 148 SMs pulling;
 // giving 30-116 SMs to the deconv role costs more read bandwidth than the L2 hits of the newest map return.  Kept
 // (bit-identical to the two launches, tests/test_srfbn_gpu.py) as the measured answer to "hand hr[i] over through L2".
+#ifdef VSR_KNOCKOUT
+long long* g_trace_buf = nullptr;
+#endif
+
 int group_enabled() {
   const char* e = getenv("VSR_GROUP");
   return e ? (atoi(e) != 0) : 0;
@@ -522,6 +526,14 @@ int build_fused_down(Layer& L, const void* const* hr, int nsrc, int B, int h, in
   {
     const char* e = getenv("VSR_FUSED_DEBUG");
     f.debug = e ? atoi(e) : 0;
+    // timeline of CTA 0 of the launch with VSR_FUSED_TRACE=<nsrc>: clock64 stamps into a debug buffer
+    e = getenv("VSR_FUSED_TRACE");
+    if (e && atoi(e) == nsrc) {
+      static long long* buf = nullptr;
+      if (!buf && cudaMalloc(&buf, 1024 * 32 * sizeof(long long)) == cudaSuccess) cudaMemset(buf, 0, 1024 * 32 * sizeof(long long));
+      f.trace = buf;
+      g_trace_buf = buf;
+    }
   }
 #endif
   {
@@ -1298,6 +1310,13 @@ extern "C" int vsr_srfbn_debug_group_error(const vsr_srfbn_plan* pl, vsr_stream_
   if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
   return v[1];
 }
+
+#ifdef VSR_KNOCKOUT
+extern "C" int vsr_debug_fused_trace(long long* host_out) {      // knock-out build only: 1024 tiles x 32 stamps
+  if (!g_trace_buf || !host_out) return -1;
+  return cuda_status(cudaMemcpy(host_out, g_trace_buf, 1024 * 32 * sizeof(long long), cudaMemcpyDeviceToHost));
+}
+#endif
 
 extern "C" int vsr_srfbn_debug_premix(const vsr_srfbn_plan* pl, float* out_maps, vsr_stream_t stream) {
   if (!pl || !out_maps) return VSR_ERR_INVALID_ARG;
