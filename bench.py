@@ -377,6 +377,11 @@ def run_b200(args, rank, world, local_rank):
         # kept (the driver reads the communicator's rank count from the INFO lines).
         os.environ.setdefault("NCCL_DEBUG", "WARN")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # NCCL prints its version banner with printf to fd 1 when the first communicator comes up: point fd 1 at
+        # stderr until the warm-up collective has run, then give stdout back to the JSON line
+        sys.stdout.flush()
+        saved_stdout_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
 
@@ -478,6 +483,10 @@ def run_b200(args, rank, world, local_rank):
         step_resident()
     if world > 1:                                 # the first collective builds NCCL's channels: not part of a step
         gather_frames(frames_u8[:1])
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os.dup2(saved_stdout_fd, 1)
+        os.close(saved_stdout_fd)
     step_e2e()
     e2e_drain()
     torch.cuda.synchronize()
