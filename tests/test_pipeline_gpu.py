@@ -32,8 +32,18 @@ def test_front_matches_oracle(T, h, w, max_disp):
     est = torch.rand((3, h, w), generator=torch.Generator().manual_seed(9)) * 255
     r = pipe.project_and_warp(fr.to(DEV), fl.to(DEV), d.to(DEV), la.to(DEV), lb.to(DEV), est.to(DEV))
     stack, want = orc.warp_fuse_front(fr.numpy(), fl.numpy(), d.numpy(), la.numpy(), lb.numpy(), est.numpy())
-    for k in ("count_flow", "hole_flow", "count_depth", "hole_depth", "mask", "mask_warped"):
+    for k in ("count_flow", "hole_flow", "count_depth", "hole_depth", "mask"):
         assert np.array_equal(r[k].cpu().numpy(), want[k]), k                  # bit-exact integer outputs
+    # the label warp is bit-exact GIVEN its flow (checked with the oracle's flow at the end); with the pipeline's own
+    # projected flow (fp32 sums in another order, <= 1e-3 px) a label may differ only where the sampling position is
+    # that close to a rounding tie of floor(v + 0.5)
+    diff = np.argwhere(r["mask_warped"].cpu().numpy() != want["mask_warped"])
+    if T > 1 and len(diff):
+        cf = want["centre_flows"][T // 2 - 1]
+        for y, x in diff:
+            fx, fy = x + cf[y, x, 0], y + cf[y, x, 1]
+            assert min(abs(fx + 0.5 - round(fx + 0.5)), abs(fy + 0.5 - round(fy + 0.5))) <= 1e-3 * T, (y, x, fx, fy)
+    assert len(diff) <= 2
     for k in ("proj_flow", "proj_depth", "wsum"):
         assert np.abs(r[k].cpu().numpy() - want[k]).max() <= 1e-3, k           # fp32 sums in atomic order
     # the chained centre -> neighbour flows: sums of (T-1)/2 sampled projected flows, each within 1e-3

@@ -85,6 +85,25 @@ __device__ __forceinline__ bool normalise_target(const float4 a, float2& o) {
   return is_hole;
 }
 
+// The same with a single MUFU for the reciprocal: rcp.approx.ftz is exact to 1 ulp for normal operands; the (never
+// seen) denormal or > 2^126 weight sums take the full division.
+__device__ __forceinline__ bool normalise_target_fast(const float4 a, float2& o) {
+  const bool is_hole = !(a.w > 0.0f) || !(a.z > 0.0f);
+  o = make_float2(0.f, 0.f);
+  if (!is_hole) {
+    if (a.z >= 1.17549435e-38f && a.z <= 8.5e37f) {
+      float rz;
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rz) : "f"(a.z));
+      o = make_float2(a.x * rz, a.y * rz);
+    } else {
+      float2 q;
+      normalise_target(a, q);
+      o = q;
+    }
+  }
+  return is_hole;
+}
+
 // ---------------------------------------------------------------------------------------------
 // GENERAL path, stage roles.  Each role spreads its work over `nw` warps (the whole grid) by a warp-stride loop.
 // ---------------------------------------------------------------------------------------------
@@ -331,242 +350,414 @@ stage_fill_kernel(const uint32_t* rowmask, const uint32_t* colmask, const int* h
 }
 
 // ---------------------------------------------------------------------------------------------
-// BOUNDED path: owner-computes tiles in shared memory.
+// BOUNDED path: owner-computes tiles in shared memory, 4-colour block phases.
 // ---------------------------------------------------------------------------------------------
-constexpr int kTileWarps = 13;                    // 12 rectangle warps + 1 for the tile's left halo column
+// Geometry (all for a displacement bound of kBD = 8 px; a smaller promise runs on the same geometry):
+//  * a CTA owns a kTW x kTH target tile = (kTW+1) x (kTH+1) cells (the box sum needs the cell column to the left and
+//    the cell row above); cells are float4 in shared memory;
+//  * the sources that can reach those cells lie in [tx0-1-kBD, tx0+kTW-1+kBD] x [ty0-1-kBD, ty0+kTH-1+kBD].  That
+//    region (x widened to 16-pixel alignment: 128-byte aligned flow rows) is cut into blocks of kBS x kBS = 16 x 16
+//    sources.  A block's sources reach at most the 32 x 32 cells around it, so two blocks whose origins differ by a
+//    multiple of 32 in x and y never touch the same cell: blocks are processed in 4 colour phases (x parity, y parity),
+//    one warp per 2x2 super-block, a block barrier between the phases -> within a phase every cell is touched by
+//    one warp only, plain LDS / STS read-modify-write, no atomics.  Candidates scanned per target: 1.5 (the previous
+//    scheme -- a warp owns a cell rectangle and scans rectangle +- bound -- scanned 2.3 and needed ~100
+//    instructions per 32 candidates);
+//  * the last source row (ty0+kTH-1+kBD: it reaches the tile only with fy == -kBD exactly) does not fill a block row;
+//    warp 15 walks it during the first phase, when no block that reaches cell row kTH is active;
+//  * inside a warp, sources of one instruction that hit the same cell take turns through a one-byte claim protocol.
+//    A lane holds 2 x 4 sources of its block (a column pair x 4 rows, one 16-byte flow load per row) and the rounds
+//    are arranged so that the 64 sources of a round are 2 apart in x and in y: smooth fields (|gradient| < 0.5)
+//    practically never collide, and the 8 lanes of a quarter warp hit 8 different 16-byte bank groups.
+constexpr int kBD = 8;                              // displacement bound of the geometry
+constexpr int kBS = 2 * kBD;                        // block side
+constexpr int kTW = 128, kTH = 80;                  // target tile
+constexpr int kCW = kTW + 1, kCH = kTH + 1;         // cells of a tile
+constexpr int kNC = kCW * kCH;                      // 10 449 cells = 167 184 B
+constexpr int kClaimPitch = 136;                    // claim bytes per cell row: rows 4 apart land 8 banks apart
+constexpr int kSX0 = -16, kSY0 = -(kBD + 1);        // origin of the scanned source region relative to (tx0, ty0)
+constexpr int kNBX = (kTW + 32) / kBS;              // 10 block columns: x in [tx0-16, tx0+144)
+constexpr int kNBY = (kTH + kBS) / kBS;             // 6 block rows: y in [ty0-9, ty0+87), + the extra row ty0+87
+static_assert(kNBX % 2 == 0 && kNBY % 2 == 0, "2x2 super-blocks");
+static_assert(kSX0 <= -1 - kBD && kSX0 + kNBX * kBS > kTW - 1 + kBD, "x coverage");
+static_assert(kSY0 + kNBY * kBS == kTH - 1 + kBD, "the extra row is the one after the last block row");
+static_assert(kTH % 16 == 0 && kTW % 32 == 0, "bitmap granularity");
+constexpr int kAccWarps = (kNBX / 2) * (kNBY / 2);  // 15 super-blocks
+constexpr int kTileWarps = 16;
 constexpr int kTileThreads = 32 * kTileWarps;
-constexpr int kTileW = 192, kTileH = 64;          // targets per tile = 6 x 2 output sub-blocks of 32 x 32
-constexpr int kCellW = kTileW + 1, kCellH = kTileH + 1;   // + the column to the left and the row above
-constexpr int kCells = kCellW * kCellH;           // 12 545 cells: 200 720 B of float4 + 12 545 B of claim bytes
-constexpr int kMaxBound = 16;
-constexpr int kSB = 4;                            // batches of 32 sources handled together (one claim round, 4 RMWs in flight)
-constexpr size_t kTileSmem = (size_t)(kCells + 1) * 16 + ((kCells + 1 + 15) / 16) * 16;   // + the dummy cell / claim byte
+static_assert(kAccWarps < kTileWarps && kTileWarps % 4 == 0 && kTH % (kTileWarps / 4) == 0, "warp roles");
+constexpr int kOutRows = kTH / (kTileWarps / 4);    // 20 target rows per output warp (4 column chunks of 32)
+constexpr int kColWords = 4;                        // staged column bitmap: bit (ty0 % 32) + row, up to 16 + 79
+constexpr int kMaxBound = kBD;
+constexpr int kExtraChunks = kNBX * kBS / 32;       // the extra source row, 32 sources at a time
+constexpr size_t kTileSmem = (size_t)(kNC + 32) * 16 + (size_t)kColWords * kTW * 4 + (size_t)kClaimPitch * kCH + 32;   // + scratch
 
-// A warp's source window is walked row by row, 32 lanes x `n_chunks` per row (64 wide for a bound of 8 = two full
-// chunks; the halo-column warp's window is 2*bound+1 wide: one chunk, half the lanes idle, but the same number of
-// batches as everybody else).  The batch -> (row, chunk) bookkeeping is warp-uniform and incremental; a lane adds
-// its own fixed column.  (ncu on the first versions: per-lane divisions / wrap loops, int->float conversions,
-// 64-bit index arithmetic and the branches around predicated shared-memory accesses were most of the instructions.)
-struct Walk {
-  int n_chunks, n_rows, n_cols;
-  int off0;                  // y*w + x of (first row, this lane's column in chunk 0)
-  float x0, y0;              // the same position as floats
-  int w;
-};
-struct WalkPos {             // warp-uniform cursor
-  int row, chunk;
-  __device__ __forceinline__ void step(const Walk& wk) {
-    if (++chunk == wk.n_chunks) { chunk = 0; ++row; }
-  }
+struct TileRect {      // the tile's cells as bounds on the target position (x2, y2), and the tile's first cell
+  float xa, xb, ya, yb;
+  float cx0f, cy0f;
 };
 
-struct SrcBatch {       // kSB x 32 sources in registers (invalid sources: flow 0, depth 1)
-  float2 f[kSB];
-  float d[kSB];
-};
-
-__device__ __forceinline__ void load_batch(SrcBatch& s, const Walk& wk, WalkPos& wp, int lane,
-                                           const float2* __restrict__ flow, const float* __restrict__ depth) {
-#pragma unroll
-  for (int u = 0; u < kSB; ++u) {
-    const bool ok = wp.row < wk.n_rows && lane + 32 * wp.chunk < wk.n_cols;
-    const int off = wk.off0 + wp.row * wk.w + 32 * wp.chunk;
-    s.f[u] = make_float2(0.f, 0.f);
-    s.d[u] = 1.0f;
-    if (ok) {
-      s.f[u] = __ldg(flow + off);
-      if (depth) s.d[u] = __ldg(depth + off);
-    }
-    wp.step(wk);
-  }
+// One claim round for two sources per lane, as one block of PTX on 32-bit shared addresses (the compiler's version
+// of the same logic rebuilt the shared window base and converted predicates to integers and back in every round).
+// pend0/pend1 (in/out, 0 or 1): the source still has to be added.  Everybody pending writes its id to the claim byte
+// of its cell, the survivor of a cell reads the cell, adds {vx, vy, d, 1} and writes it back, and stops pending.
+// Branch-free and unpredicated: a lane with nothing to add runs the same accesses on its OWN scratch cell / claim byte
+// (scr_cell, scr_claim: one per lane, so idle lanes do not pile up on one bank as they did on a shared dummy cell).
+// claim0/claim1 must already point at the scratch byte for sources that are not pending.
+__device__ __forceinline__ void claim_round2(uint32_t& pend0, uint32_t& pend1, uint32_t& claim0, uint32_t& claim1,
+                                             uint32_t id0, uint32_t id1, uint32_t cell0, uint32_t cell1, float vx0,
+                                             float vy0, float d0, float vx1, float vy1, float d1, uint32_t scr_cell,
+                                             uint32_t scr_claim) {
+  asm volatile(
+      "{\n"
+      " .reg .pred w0, w1;\n"
+      " .reg .b32 who0, who1, c0, c1;\n"
+      " .reg .f32 a0, a1, a2, a3, b0, b1, b2, b3;\n"
+      " st.shared.u8 [%2], %4;\n"
+      " st.shared.u8 [%3], %5;\n"
+      " bar.warp.sync 0xffffffff;\n"
+      " ld.shared.u8 who0, [%2];\n"
+      " ld.shared.u8 who1, [%3];\n"
+      " setp.eq.u32 w0, who0, %4;\n"
+      " setp.eq.u32 w1, who1, %5;\n"
+      " setp.ne.and.u32 w0, %0, 0, w0;\n"
+      " setp.ne.and.u32 w1, %1, 0, w1;\n"
+      " selp.u32 c0, %6, %14, w0;\n"
+      " selp.u32 c1, %7, %14, w1;\n"
+      " ld.shared.v4.f32 {a0, a1, a2, a3}, [c0];\n"
+      " ld.shared.v4.f32 {b0, b1, b2, b3}, [c1];\n"
+      " add.f32 a0, a0, %8;\n"
+      " add.f32 a1, a1, %9;\n"
+      " add.f32 a2, a2, %10;\n"
+      " add.f32 a3, a3, 0f3F800000;\n"
+      " add.f32 b0, b0, %11;\n"
+      " add.f32 b1, b1, %12;\n"
+      " add.f32 b2, b2, %13;\n"
+      " add.f32 b3, b3, 0f3F800000;\n"
+      " st.shared.v4.f32 [c0], {a0, a1, a2, a3};\n"
+      " st.shared.v4.f32 [c1], {b0, b1, b2, b3};\n"
+      " selp.u32 %0, 0, %0, w0;\n"          // a winner is done: from now on it only touches its scratch byte (a winner
+      " selp.u32 %1, 0, %1, w1;\n"          // that kept writing its id to the real claim byte would starve the others)
+      " selp.u32 %2, %15, %2, w0;\n"
+      " selp.u32 %3, %15, %3, w1;\n"
+      " bar.warp.sync 0xffffffff;\n"
+      "}\n"
+      : "+r"(pend0), "+r"(pend1), "+r"(claim0), "+r"(claim1)
+      : "r"(id0), "r"(id1), "r"(cell0), "r"(cell1), "f"(vx0), "f"(vy0), "f"(d0), "f"(vx1), "f"(vy1), "f"(d1),
+        "r"(scr_cell), "r"(scr_claim)
+      : "memory");
 }
 
-// Adds the batch's sources that land in [xa,xb] x [ya,yb] (= this warp's cells, inside the image) to the cells.
-// The cells are this warp's alone: plain read-modify-write, no atomics.  Sources of one batch that hit the SAME cell
-// take turns: everybody writes its id (sub-batch, lane) to the cell's claim byte, the survivor goes.  Winners
-// therefore hold distinct cells, so their four RMWs are independent and overlap.  Everything is branch-free: a source
-// with nothing to add (outside the rectangle, or it lost the claim) reads, "updates" and writes a dummy cell.
-__device__ __forceinline__ void add_batch(const SrcBatch& cur, const Walk& wk, WalkPos& wp, float4* s_cells,
-                                          uint8_t* s_claim, float xa, float xb, float ya, float yb, int cell_org,
-                                          int lane, float& vmax) {
-  int cell[kSB];
-  bool pend[kSB];
-  float vx[kSB], vy[kSB];
+// Adds U (1 or 2) x 32 sources (flow fx/fy, inverse depth dd, position xs/ys; NaN flow = no source) to the tile's
+// cells.  Sources of one call that hit the same cell take turns (claim_round2).
+template <int U>
+__device__ __forceinline__ void add_sources(const float (&fx)[U], const float (&fy)[U], const float (&dd)[U],
+                                            const float (&xs)[U], const float (&ys)[U], uint32_t cells_sa,
+                                            uint32_t claim_sa, const TileRect& R, int lane, float& vmax) {
+  static_assert(U == 1 || U == 2, "claim_round2");
+  const uint32_t scr_cell = cells_sa + 16u * (uint32_t)(kNC + lane), scr_claim = claim_sa + (uint32_t)(kClaimPitch * kCH + lane);
+  uint32_t cell_a[2] = {scr_cell, scr_cell}, claim_a[2] = {scr_claim, scr_claim}, pend[2] = {0, 0};
+  float vx[2] = {0.f, 0.f}, vy[2] = {0.f, 0.f}, dv[2] = {0.f, 0.f};
 #pragma unroll
-  for (int u = 0; u < kSB; ++u) {
-    const float fx = cur.f[u].x, fy = cur.f[u].y;
-    const bool ok = wp.row < wk.n_rows && lane + 32 * wp.chunk < wk.n_cols;
-    const float x2 = __fadd_rn(wk.x0 + (float)(32 * wp.chunk), fx), y2 = __fadd_rn(wk.y0 + (float)wp.row, fy);
-    wp.step(wk);
-    vmax = fmaxf(vmax, fmaxf(fabsf(fx), fabsf(fy)));
-    pend[u] = ok && x2 >= xa && x2 <= xb && y2 >= ya && y2 <= yb;
-    cell[u] = pend[u] ? (int)y2 * kCellW + (int)x2 - cell_org : kCells;     // kCells: the dummy cell / claim byte
-    vx[u] = __fmul_rn(-fx, cur.d[u]);
-    vy[u] = __fmul_rn(-fy, cur.d[u]);
+  for (int u = 0; u < U; ++u) {
+    const float x2 = __fadd_rn(xs[u], fx[u]), y2 = __fadd_rn(ys[u], fy[u]);
+    vmax = fmaxf(vmax, fmaxf(fabsf(fx[u]), fabsf(fy[u])));
+    // "lands in one of the tile's cells and inside the image" (Appendix B step 2; NaN fails every compare)
+    const bool in = x2 >= R.xa && x2 <= R.xb && y2 >= R.ya && y2 <= R.yb;
+    pend[u] = in ? 1u : 0u;
+    // local cell: x2 - cx0 is exact (an integer below 2^11 off a float below 2^24) and >= 0 where it matters
+    const int ix = (int)(x2 - R.cx0f), iy = (int)(y2 - R.cy0f);
+    cell_a[u] = cells_sa + 16u * (uint32_t)(iy * kCW + ix);
+    claim_a[u] = in ? claim_sa + (uint32_t)(iy * kClaimPitch + ix) : scr_claim;
+    vx[u] = __fmul_rn(-fx[u], dd[u]);
+    vy[u] = __fmul_rn(-fy[u], dd[u]);
+    dv[u] = dd[u];
   }
-  bool again;
   int rounds = 0;
-  do {
-#pragma unroll
-    for (int u = 0; u < kSB; ++u) s_claim[cell[u]] = (uint8_t)(u * 32 + lane);
-    __syncwarp();
-    uint8_t who[kSB];
-#pragma unroll
-    for (int u = 0; u < kSB; ++u) who[u] = s_claim[cell[u]];
-    int idx[kSB];
-    float4 c[kSB];
-    bool left = false;
-#pragma unroll
-    for (int u = 0; u < kSB; ++u) {
-      const bool win = pend[u] && who[u] == (uint8_t)(u * 32 + lane);
-      idx[u] = win ? cell[u] : kCells;
-      pend[u] = pend[u] && !win;
-      if (!pend[u]) cell[u] = kCells;      // done: from now on this source only touches the dummy (a winner that kept
-                                           // writing its id to the real claim byte would starve the others for ever)
-      left |= pend[u];
-    }
-#pragma unroll
-    for (int u = 0; u < kSB; ++u) c[u] = s_cells[idx[u]];
-#pragma unroll
-    for (int u = 0; u < kSB; ++u) {
-      c[u].x += vx[u]; c[u].y += vy[u]; c[u].z += cur.d[u]; c[u].w += 1.0f;
-      s_cells[idx[u]] = c[u];
-    }
-    again = __any_sync(0xffffffffu, left);
-    __syncwarp();
-    // every round retires at least one source per contested cell: at most kSB * 32 rounds.  The guard turns a logic
+#pragma unroll 1
+  for (;;) {
+    claim_round2(pend[0], pend[1], claim_a[0], claim_a[1], (uint32_t)lane, (uint32_t)(32 + lane), cell_a[0], cell_a[1],
+                 vx[0], vy[0], dv[0], vx[1], vy[1], dv[1], scr_cell, scr_claim);
+    if (!__any_sync(0xffffffffu, (pend[0] | pend[1]) != 0)) break;
+    // every round retires at least one source per contested cell: at most U * 32 rounds.  The guard turns a logic
     // error into a redo by the general path instead of a hung GPU.
-    if (++rounds > kSB * 32 + 2) { vmax = __int_as_float(0x7f800000); break; }
-  } while (again);
+    if (++rounds > U * 32 + 2) { vmax = __int_as_float(0x7f800000); break; }
+  }
 }
 
+// A lane's share of a 16 x 16 source block: column pair 2j, 2j+1 (j = lane & 7) of the four rows 4g .. 4g+3
+// (g = lane >> 3), held in the order k -> row 4g + ((k + rot) & 3), rot = 1 for the lanes j >= 4.  One load
+// instruction covers 16 columns of four rows 4 apart (j < 4 and j >= 4 on neighbouring rows): 128-byte row segments.
+// The rotation makes a claim round (below) bank-conflict free: the eight lanes of a quarter warp work on columns 2
+// apart, the upper four one row below / above the lower four -> eight different 16-byte bank groups (129 cells a row).
+struct BlockData {
+  float4 f[4];      // flow of the pair: (fx, fy) of column 2j, (fx, fy) of column 2j+1
+  float2 d[4];      // inverse depth of the pair
+};
+
+__device__ __forceinline__ void load_block(BlockData& s, const float2* __restrict__ flow, const float* __restrict__ depth,
+                                           int h, int w, int bx0, int by0, int lane) {
+  const int x = bx0 + 2 * (lane & 7), y0 = by0 + 4 * (lane >> 3), rot = (lane >> 2) & 1;
+  if (bx0 >= 0 && by0 >= 0 && bx0 + kBS <= w && by0 + kBS <= h) {     // warp-uniform: the whole block is inside
+    const int o0 = (y0 + rot) * w + x;
+    const int o3 = o0 + (3 - 4 * rot) * w;
+    const int off[4] = {o0, o0 + w, o0 + 2 * w, o3};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s.f[k] = __ldg(reinterpret_cast<const float4*>(flow + off[k]));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s.d[k] = depth ? __ldg(reinterpret_cast<const float2*>(depth + off[k])) : make_float2(1.0f, 1.0f);
+    return;
+  }
+  const bool okx = (unsigned)x < (unsigned)w;       // w and x are even: the pair is inside or outside together
+  const float qnan = __int_as_float(0x7fc00000);    // "no source": fails the range test, ignored by the bound check
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int y = y0 + ((k + rot) & 3);
+    s.f[k] = make_float4(qnan, qnan, qnan, qnan);
+    s.d[k] = make_float2(1.0f, 1.0f);
+    if (okx && (unsigned)y < (unsigned)h) {
+      const int off = y * w + x;
+      s.f[k] = __ldg(reinterpret_cast<const float4*>(flow + off));
+      if (depth) s.d[k] = __ldg(reinterpret_cast<const float2*>(depth + off));
+    }
+  }
+}
+
+// Four claim rounds of 2 x 32 sources: (column parity p, k parity kb).  The 64 sources of a round are 2 apart in x
+// and (within a lane group) in y: a smooth field (|gradient| < 0.5 px/px) practically never collides inside a round.
+__device__ __forceinline__ void add_block(const BlockData& s, int bx0, int by0, uint32_t cells_sa, uint32_t claim_sa,
+                                          const TileRect& R, int lane, float& vmax) {
+  const float rotf = (float)((lane >> 2) & 1);
+  const float xf0 = (float)(bx0 + 2 * (lane & 7));
+  const float yr = (float)(by0 + 4 * (lane >> 3)) + rotf;              // row of k = 0
+  const float yk[4] = {yr, yr + 1.0f, yr + 2.0f, fmaf(-4.0f, rotf, yr + 3.0f)};
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+#pragma unroll
+    for (int kb = 0; kb < 2; ++kb) {
+      float fx[2], fy[2], dd[2], xs[2], ys[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int k = kb + 2 * u;
+        fx[u] = p ? s.f[k].z : s.f[k].x;
+        fy[u] = p ? s.f[k].w : s.f[k].y;
+        dd[u] = p ? s.d[k].y : s.d[k].x;
+        xs[u] = xf0 + (float)p;
+        ys[u] = yk[k];
+      }
+      add_sources<2>(fx, fy, dd, xs, ys, cells_sa, claim_sa, R, lane, vmax);
+    }
+  }
+}
+
+struct TilePos {
+  int tb, tx0, ty0;
+};
+__device__ __forceinline__ TilePos tile_pos(int tile, int tiles_x, int tiles_xy) {
+  TilePos t;
+  t.tb = tile / tiles_xy;
+  const int tr = tile - t.tb * tiles_xy;
+  const int ty = tr / tiles_x;
+  t.tx0 = (tr - ty * tiles_x) * kTW;
+  t.ty0 = ty * kTH;
+  return t;
+}
+
+template <bool WSUM>
 __global__ void __launch_bounds__(kTileThreads, 1)
 projection_tiled_kernel(const ProjArgs a) {
   extern __shared__ float4 s_cells[];
-  uint8_t* s_claim = reinterpret_cast<uint8_t*>(s_cells + kCells + 1);
+  uint32_t* s_colm = reinterpret_cast<uint32_t*>(s_cells + kNC + 32);          // [kColWords][kTW]
+  const uint32_t cells_sa = (uint32_t)__cvta_generic_to_shared(s_cells);
+  const uint32_t claim_sa = (uint32_t)__cvta_generic_to_shared(s_colm + kColWords * kTW);    // one claim byte per cell,
+                                                                                             // kClaimPitch a row
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int h = a.h, w = a.w, D = a.bound;
-  const int tiles_x = ceil_div(w, kTileW), tiles_y = ceil_div(h, kTileH);
-  const int n_tiles = tiles_x * tiles_y * a.B;
+  const int h = a.h, w = a.w;
+  const int tiles_x = ceil_div(w, kTW), tiles_xy = tiles_x * ceil_div(h, kTH);
+  const int n_tiles = tiles_xy * a.B;
   const int P = h * w;                            // <= 2^30
   const float xmax = (float)(w - 1), ymax = (float)(h - 1);
   const int rw_x = ceil_div(w, 32);
   const int rw = h * rw_x, cw = ceil_div(h, 32) * w;
-  // accumulation rectangle of this warp inside the 193 x 65 cell tile: warps 0-11 take 4 x 3 rectangles of 48 x
-  // 22(21) cells over local columns 1..192, warp 12 the left halo column (local column 0, all 65 rows)
-  const bool halo = warp == 12;
-  const int bx = warp & 3, by = warp >> 2;
-  const int cx_lo = halo ? 0 : 1 + 48 * bx, cx_hi = halo ? 1 : 49 + 48 * bx;
-  const int cy_lo = halo ? 0 : 22 * by, cy_hi = halo ? kCellH : (by == 2 ? kCellH : 22 * (by + 1));
-  // output sub-block of warps 0-11: 32 x 32 targets
-  const int ox = (warp % 6) * 32, oy = (warp / 6) * 32;
+  const int n_halves = 2 * ceil_div(h, 32);       // 16-row halves of the column bitmap words
+  const float2* flow_all = reinterpret_cast<const float2*>(a.flow);
+  // super-block of this warp: block (2*sc + cx, 2*sr + cy) in colour phase (cx, cy)
+  const int sc = warp % (kNBX / 2), sr = warp / (kNBX / 2);
   float vmax = 0.0f;                              // largest |flow component| this thread has looked at
 
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int tb = tile / (tiles_x * tiles_y);
-    const int tr = tile - tb * tiles_x * tiles_y;
-    const int tx0 = (tr % tiles_x) * kTileW, ty0 = (tr / tiles_x) * kTileH;   // first target of the tile
-    const float2* flow = reinterpret_cast<const float2*>(a.flow) + (int64_t)tb * P;
-    const float* depth = a.inv_depth ? a.inv_depth + (int64_t)tb * P : nullptr;
+  // the block of (tile, colour): origin and image
+  auto block_org = [&](const TilePos& t, int c, int& bx0, int& by0) {
+    bx0 = t.tx0 + kSX0 + kBS * (2 * sc + (c & 1));
+    by0 = t.ty0 + kSY0 + kBS * (2 * sr + (c >> 1));
+  };
+  auto prefetch = [&](BlockData& s, int tile, int c) {
+    if (tile >= n_tiles) return;
+    const TilePos t = tile_pos(tile, tiles_x, tiles_xy);
+    int bx0, by0;
+    block_org(t, c, bx0, by0);
+    load_block(s, flow_all + (int64_t)t.tb * P, a.inv_depth ? a.inv_depth + (int64_t)t.tb * P : nullptr, h, w, bx0, by0, lane);
+  };
 
-    for (int i = threadIdx.x; i < kCells; i += kTileThreads) s_cells[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncthreads();
+  for (int i = threadIdx.x; i < kColWords * kTW; i += kTileThreads) s_colm[i] = 0;
+  BlockData bufA, bufB;                           // the next block's loads fly under the current block's arithmetic
+  if (warp < kAccWarps) prefetch(bufA, blockIdx.x, 0);
 
-    // ---- accumulate: sources of the window [rectangle - D, rectangle + D]; global cell = local + (ty0-1, tx0-1)
-    {
-      const int gcx_lo = tx0 - 1 + cx_lo, gcx_hi = tx0 - 1 + cx_hi;       // this warp's cells, global, hi exclusive
-      const int gcy_lo = ty0 - 1 + cy_lo, gcy_hi = ty0 - 1 + cy_hi;
-      const int gx_lo = max(gcx_lo - D, 0), gx_hi = min(gcx_hi - 1 + D, w - 1);   // source window, inclusive
-      const int gy_lo = max(gcy_lo - D, 0), gy_hi = min(gcy_hi - 1 + D, h - 1);
-      const int Ws = gx_hi - gx_lo + 1, Hs = gy_hi - gy_lo + 1;
-      const bool any = Ws > 0 && Hs > 0 && gcx_hi > 0 && gcy_hi > 0;
-      // "lands in one of my cells and inside the image" as four float compares on the target position (x2, y2):
-      // int(x2) in [lo, hi) <=> lo <= x2 < hi for x2 >= 0; `x2 < hi` is `x2 <= pred(hi)`, and at the image edge the
-      // bound is Appendix B's x2 <= w-1.  NaN fails every compare.
-      const float xa = (float)max(gcx_lo, 0), xb = gcx_hi <= w - 1 ? nextafterf((float)gcx_hi, 0.0f) : xmax;
-      const float ya = (float)max(gcy_lo, 0), yb = gcy_hi <= h - 1 ? nextafterf((float)gcy_hi, 0.0f) : ymax;
-      const int cell_org = (ty0 - 1) * kCellW + (tx0 - 1);
-      Walk wk;
-      wk.n_cols = Ws;
-      wk.n_rows = any ? Hs : 0;
-      wk.n_chunks = max(ceil_div(Ws, 32), 1);
-      wk.off0 = gy_lo * w + gx_lo + lane;
-      wk.x0 = (float)(gx_lo + lane);
-      wk.y0 = (float)gy_lo;
-      wk.w = w;
-      const int nb = wk.n_rows * wk.n_chunks;
-      // three register buffers: the loads of the next two batches fly under the arithmetic of the current one
-      // (ncu: with one batch of look-ahead a fifth of the stall samples still sat on the first use of a load)
-      SrcBatch b0, b1, b2;
-      WalkPos lp = {0, 0}, ap = {0, 0};          // load cursor, add cursor
-      if (nb > 0) load_batch(b0, wk, lp, lane, flow, depth);
-      if (nb > kSB) load_batch(b1, wk, lp, lane, flow, depth);
-      for (int j = 0; j < nb; j += 3 * kSB) {
-        if (j + 2 * kSB < nb) load_batch(b2, wk, lp, lane, flow, depth);
-        add_batch(b0, wk, ap, s_cells, s_claim, xa, xb, ya, yb, cell_org, lane, vmax);
-        if (j + kSB >= nb) break;
-        if (j + 3 * kSB < nb) load_batch(b0, wk, lp, lane, flow, depth);
-        add_batch(b1, wk, ap, s_cells, s_claim, xa, xb, ya, yb, cell_org, lane, vmax);
-        if (j + 2 * kSB >= nb) break;
-        if (j + 4 * kSB < nb) load_batch(b1, wk, lp, lane, flow, depth);
-        add_batch(b2, wk, ap, s_cells, s_claim, xa, xb, ya, yb, cell_org, lane, vmax);
+  // the extra source row of a tile (warp kAccWarps only): loaded one tile ahead like the blocks, added in phase 0
+  float2 ex_f[kExtraChunks];
+  float ex_d[kExtraChunks];
+  auto load_extra = [&](int tile) {
+    if (tile >= n_tiles) return;
+    const TilePos t = tile_pos(tile, tiles_x, tiles_xy);
+    const int ye = t.ty0 + kTH - 1 + kBD;
+    if (ye >= h) return;
+    const float2* flow = flow_all + (int64_t)t.tb * P;
+#pragma unroll
+    for (int ch = 0; ch < kExtraChunks; ++ch) {
+      const int x = t.tx0 + kSX0 + 32 * ch + lane;
+      ex_f[ch] = make_float2(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000));
+      ex_d[ch] = 1.0f;
+      if ((unsigned)x < (unsigned)w) {
+        ex_f[ch] = __ldg(flow + ye * w + x);
+        if (a.inv_depth) ex_d[ch] = __ldg(a.inv_depth + (int64_t)t.tb * P + ye * w + x);
       }
+    }
+  };
+  if (warp == kAccWarps) load_extra(blockIdx.x);
+
+  int prev_tile = -1;
+  auto flush_colm = [&](int tile) {               // column bitmap of a finished tile: 16-bit halves; re-zeroed
+    const TilePos t = tile_pos(tile, tiles_x, tiles_xy);
+    uint16_t* cm = reinterpret_cast<uint16_t*>(a.colmask + (int64_t)t.tb * cw);
+    for (int i = threadIdx.x; i < kColWords * kTW; i += kTileThreads) {      // one staged word per thread
+      const int wq = i / kTW, col = i - wq * kTW;
+      const uint32_t word = s_colm[i];
+      s_colm[i] = 0;
+      const int x = t.tx0 + col;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int q = 2 * wq + e - ((t.ty0 & 31) >> 4);      // 16-row half of the tile held by this half word
+        const int hy = t.ty0 / 16 + q;
+        // the last tile row also writes the (empty) halves between the image's last row and the end of its bitmap word
+        if (q >= 0 && (q < kTH / 16 || t.ty0 + kTH >= h) && x < w && hy < n_halves)
+          cm[((hy >> 1) * w + x) * 2 + (hy & 1)] = (uint16_t)(word >> (16 * e));
+      }
+    }
+  };
+
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const TilePos t = tile_pos(tile, tiles_x, tiles_xy);
+    const int tx0 = t.tx0, ty0 = t.ty0;
+    const float2* flow = flow_all + (int64_t)t.tb * P;
+    const float* depth = a.inv_depth ? a.inv_depth + (int64_t)t.tb * P : nullptr;
+    if (prev_tile >= 0) flush_colm(prev_tile);
+    prev_tile = tile;
+    const int ye = ty0 + kTH - 1 + kBD;          // the extra source row (warp kAccWarps), loaded a tile ahead
+    for (int i = threadIdx.x; i < kNC; i += kTileThreads) s_cells[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    TileRect R;
+    {
+      // int(x2) in [lo, hi) <=> lo <= x2 < hi for x2 >= 0; `x2 < hi` is `x2 <= pred(hi)`, and at the image edge the
+      // bound is Appendix B's x2 <= w-1
+      const int gcx_hi = tx0 + kTW, gcy_hi = ty0 + kTH;
+      R.xa = (float)max(tx0 - 1, 0);
+      R.xb = gcx_hi <= w - 1 ? nextafterf((float)gcx_hi, 0.0f) : xmax;
+      R.ya = (float)max(ty0 - 1, 0);
+      R.yb = gcy_hi <= h - 1 ? nextafterf((float)gcy_hi, 0.0f) : ymax;
+      R.cx0f = (float)(tx0 - 1);
+      R.cy0f = (float)(ty0 - 1);
     }
     __syncthreads();
 
-    // ---- output: 32 x 32 targets per warp, lane = column, rows walked; local cell of target (ty,tx) = (ty+1-ty0, tx+1-tx0)
-    if (!halo && ty0 + oy < h && tx0 + ox < w) {
-      const int x = tx0 + ox + lane;
-      const bool in_x = x < w;
-      const float mx = (x == w - 1) ? 2.0f : 1.0f;
-      const float4* col = s_cells + oy * kCellW + ox + lane + 1;     // cell (row above the first target, this column)
-      float4 up = col[0];
-      float4 up_left = col[-1];
-      uint32_t colbits = 0;
-      bool any_hole = false;
-      const int64_t img = (int64_t)tb * P;
-      float2* proj = reinterpret_cast<float2*>(a.proj) + img;
-      float* wsum = a.wsum ? a.wsum + img : nullptr;
-      int32_t* count = a.count + img;
-      uint8_t* hole = a.hole + img;
-      uint32_t* rowm = a.rowmask + (int64_t)tb * rw + ((tx0 + ox) >> 5);
-      const int rows = min(32, h - (ty0 + oy));
-      int p = (ty0 + oy) * w + x;
-      for (int r = 0; r < rows; ++r, p += w) {
-        col += kCellW;
-        const float4 c11 = col[0];
-        float4 c10 = shfl_up1_f4(c11);
-        if (lane == 0) c10 = col[-1];
-        const float4 c01 = up, c00 = up_left;
-        up = c11;
-        up_left = c10;
-        const float my = (ty0 + oy + r == h - 1) ? 2.0f : 1.0f;
-        float4 t;
-        t.x = fmaf(fmaf(c11.x, mx, c10.x), my, fmaf(c01.x, mx, c00.x));
-        t.y = fmaf(fmaf(c11.y, mx, c10.y), my, fmaf(c01.y, mx, c00.y));
-        t.z = fmaf(fmaf(c11.z, mx, c10.z), my, fmaf(c01.z, mx, c00.z));
-        t.w = fmaf(fmaf(c11.w, mx, c10.w), my, fmaf(c01.w, mx, c00.w));
-        bool is_hole = false;
-        if (in_x) {
-          float2 o;
-          is_hole = normalise_target(t, o);
-          proj[p] = o;
-          if (wsum) wsum[p] = is_hole ? 0.0f : t.z;
-          count[p] = (int32_t)t.w;
-          hole[p] = is_hole ? 1 : 0;
+    // ---- accumulate: 4 colour phases
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (warp < kAccWarps) {
+        BlockData& cur = (c & 1) ? bufB : bufA;
+        BlockData& nxt = (c & 1) ? bufA : bufB;
+        if (c < 3) prefetch(nxt, tile, c + 1); else prefetch(nxt, tile + gridDim.x, 0);
+        int bx0, by0;
+        block_org(t, c, bx0, by0);
+        if (bx0 < w && by0 < h && bx0 + kBS > 0 && by0 + kBS > 0)       // warp-uniform: the block touches the image
+          add_block(cur, bx0, by0, cells_sa, claim_sa, R, lane, vmax);
+      } else if (c == 0 && warp == kAccWarps && ye < h) {
+        // the extra source row; no block active in phases 0 / 1 reaches the cell row it can hit
+#pragma unroll
+        for (int ch = 0; ch < kExtraChunks; ++ch) {
+          float fx[1] = {ex_f[ch].x}, fy[1] = {ex_f[ch].y}, dd[1] = {ex_d[ch]};
+          float xs[1] = {(float)(tx0 + kSX0 + 32 * ch + lane)}, ys[1] = {(float)ye};
+          add_sources<1>(fx, fy, dd, xs, ys, cells_sa, claim_sa, R, lane, vmax);
         }
-        const uint32_t m = __ballot_sync(0xffffffffu, in_x && !is_hole);
-        if (lane == 0) rowm[(ty0 + oy + r) * rw_x] = m;
-        colbits |= (uint32_t)(in_x && !is_hole) << r;
-        any_hole |= in_x && is_hole;
       }
-      if (in_x) a.colmask[(int64_t)tb * cw + ((ty0 + oy) >> 5) * w + x] = colbits;
-      if (__any_sync(0xffffffffu, any_hole) && lane == 0) *reinterpret_cast<volatile int*>(a.flags + 1 + tb) = 1;
+      if (c == 0 && warp == kAccWarps) load_extra(tile + gridDim.x);
+      __syncthreads();
+    }
+
+    // ---- output: warp = (32-column chunk, kOutRows target rows), lane = column; local cell of target (r, c) = (r+1, c+1)
+    {
+      const int chunk = warp & 3, r0 = (warp >> 2) * kOutRows;
+      if (tx0 + 32 * chunk < w && ty0 + r0 < h) {
+        const int x = tx0 + 32 * chunk + lane;
+        const bool in_x = x < w;
+        const float mx = (x == w - 1) ? 2.0f : 1.0f;
+        const float4* col = s_cells + r0 * kCW + 32 * chunk + lane + 1;     // cell row above the first target
+        // horizontal pair sums h(r) = cell(r, x) * mx + cell(r, x-1); target = h(own row) * my + h(row above).  The
+        // clamped duplicate targets of Appendix B ("hit twice") are the multiplicities mx, my of the last column / row.
+        // Both cells come from shared memory (a second 16-byte load is cheaper than four shuffles and their moves).
+        float4 hp;
+        {
+          const float4 c1 = col[0], c0 = col[-1];
+          hp = make_float4(fmaf(c1.x, mx, c0.x), fmaf(c1.y, mx, c0.y), fmaf(c1.z, mx, c0.z), fmaf(c1.w, mx, c0.w));
+        }
+        uint32_t colbits = 0;
+        bool any_hole = false;
+        const int rows = min(kOutRows, h - (ty0 + r0));
+        const int64_t p0 = (int64_t)t.tb * P + (ty0 + r0) * w + x;
+        float2* pp = reinterpret_cast<float2*>(a.proj) + p0;
+        float* pw = WSUM ? a.wsum + p0 : nullptr;
+        int32_t* pc = a.count + p0;
+        uint8_t* ph = a.hole + p0;
+        uint32_t* pr = a.rowmask + (int64_t)t.tb * rw + (ty0 + r0) * rw_x + ((tx0 + 32 * chunk) >> 5);
+        const int r_last = h - 1 - (ty0 + r0);      // the image's last row, relative to this warp's first
+        for (int r = 0; r < rows; ++r) {
+          col += kCW;
+          const float4 c1 = col[0], c0 = col[-1];
+          const float4 hc = make_float4(fmaf(c1.x, mx, c0.x), fmaf(c1.y, mx, c0.y), fmaf(c1.z, mx, c0.z), fmaf(c1.w, mx, c0.w));
+          const float my = (r == r_last) ? 2.0f : 1.0f;
+          const float4 tg = make_float4(fmaf(hc.x, my, hp.x), fmaf(hc.y, my, hp.y), fmaf(hc.z, my, hp.z), fmaf(hc.w, my, hp.w));
+          hp = hc;
+          float2 o;
+          const bool is_hole = normalise_target_fast(tg, o);
+          if (in_x) {
+            *pp = o;
+            if (WSUM) *pw = is_hole ? 0.0f : tg.z;
+            *pc = (int32_t)tg.w;
+            *ph = is_hole ? 1 : 0;
+          }
+          const uint32_t m = __ballot_sync(0xffffffffu, in_x && !is_hole);
+          if (lane == 0) *pr = m;
+          colbits |= (uint32_t)(in_x && !is_hole) << r;
+          any_hole |= in_x && is_hole;
+          pp += w;
+          if (WSUM) pw += w;
+          pc += w;
+          ph += w;
+          pr += rw_x;
+        }
+        // this lane's column bits -> the staged column words (tile rows start at bit ty0 % 32 of the first word)
+        const int pos = (ty0 & 31) + r0;
+        const uint64_t bits = (uint64_t)colbits << (pos & 31);
+        uint32_t* cmw = s_colm + (pos >> 5) * kTW + 32 * chunk + lane;
+        if ((uint32_t)bits) atomicOr(cmw, (uint32_t)bits);
+        if ((uint32_t)(bits >> 32)) atomicOr(cmw + kTW, (uint32_t)(bits >> 32));
+        if (__any_sync(0xffffffffu, any_hole) && lane == 0) *reinterpret_cast<volatile int*>(a.flags + 1 + t.tb) = 1;
+      }
     }
     __syncthreads();
   }
-  // a source beyond the promised bound: the windows above may have missed cells it reaches -> redo by the general path
-  if (__any_sync(0xffffffffu, vmax > (float)D) && lane == 0) *reinterpret_cast<volatile int*>(a.flags) = 1;
+  if (prev_tile >= 0) flush_colm(prev_tile);
+  // a source beyond the bound: the colour phases may have raced and the scan may have missed cells it reaches -> the
+  // whole batch is redone by the general path
+  if (__any_sync(0xffffffffu, vmax > (float)kBD) && lane == 0) *reinterpret_cast<volatile int*>(a.flags) = 1;
 }
 
 // fill of the bounded path: all images in one launch; nothing to do for an image without holes, and nothing at all
@@ -699,21 +890,27 @@ extern "C" int vsr_flow_projection_forward_bounded(const float* flow, const floa
   a.w = w;
   a.bound = 0;
   a.gate = 0;
-  const bool bounded = max_disp >= 0.0f && max_disp <= (float)kMaxBound;    // NaN / negative / large: general path
+  const bool bounded = max_disp >= 0.0f && max_disp <= (float)kMaxBound && w % 2 == 0;   // NaN / negative / large, or
+                                                                                       // unaligned pixel pairs: general path
   if (!bounded) return run_general(a, st);
 
-  a.bound = (int)ceilf(max_disp);
+  a.bound = kBD;
   static PerDeviceOnce once;
   int dev;
   if (once.needed(&dev)) {
-    cudaError_t e = cudaFuncSetAttribute(projection_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmem);
+    cudaError_t e = cudaFuncSetAttribute(projection_tiled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmem);
+    if (e != cudaSuccess) return cuda_status(e);
+    e = cudaFuncSetAttribute(projection_tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmem);
     if (e != cudaSuccess) return cuda_status(e);
     once.mark(dev);
   }
   cudaError_t e = cudaMemsetAsync(a.flags, 0, (size_t)(B + 1) * 4, st);
   if (e != cudaSuccess) return cuda_status(e);
-  const int n_tiles = ceil_div(w, kTileW) * ceil_div(h, kTileH) * B;
-  projection_tiled_kernel<<<n_tiles < kNumSMs ? n_tiles : kNumSMs, kTileThreads, kTileSmem, st>>>(a);
+  const int n_tiles = ceil_div(w, kTW) * ceil_div(h, kTH) * B;
+  if (wsum)
+    projection_tiled_kernel<true><<<n_tiles < kNumSMs ? n_tiles : kNumSMs, kTileThreads, kTileSmem, st>>>(a);
+  else
+    projection_tiled_kernel<false><<<n_tiles < kNumSMs ? n_tiles : kNumSMs, kTileThreads, kTileSmem, st>>>(a);
   int rc = after_launch();
   if (rc) return rc;
   const int64_t fill_warps = (int64_t)h * ceil_div(w, 32);
