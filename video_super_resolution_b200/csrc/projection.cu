@@ -62,7 +62,8 @@ struct ProjArgs {
   float4* acc;             // 3 cell arrays of h*w float4 (general path)
   uint32_t* rowmask;       // per image: h * ceil(w/32) words, bit x%32 of word (y, x/32) = pixel has hits
   uint32_t* colmask;       // per image: ceil(h/32) * w words, bit y%32 of word (y/32, x)
-  int* flags;              // [0] promise broken (bounded path), [1 + b] image b has holes
+  int* flags;              // [0] promise broken (bounded path), [1 + b] image b has holes, [1 + B] length of holelist
+  uint32_t* holelist;      // bounded path: the row words (b * h * ceil(w/32) + word) that contain holes
   int B, h, w;
   int bound;               // bounded path: ceil(max_disp)
   int gate;                // general path: 1 = run only if flags[0] != 0 (fallback of the bounded path)
@@ -238,53 +239,57 @@ __device__ __forceinline__ void role_normalise(const float4* __restrict__ acc, f
 // word are filled in parallel by their lanes.  Only non-hole pixels are read, so the result does not depend on
 // execution order.
 template <bool CG>
-__device__ __forceinline__ void role_fill(const uint32_t* rowmask_, const uint32_t* colmask_,
-                                          float* proj, int h, int w, int warp0, int nw, int lane) {
+__device__ __forceinline__ void fill_word(const uint32_t* rowmask_, const uint32_t* colmask_, float* proj, int h, int w,
+                                          int wd, int lane) {
   struct Words { const uint32_t* p; __device__ __forceinline__ uint32_t operator[](int64_t i) const { return CG ? __ldcg(p + i) : __ldg(p + i); } };
   const Words rowmask{rowmask_}, colmask{colmask_};
   const int wpr = ceil_div(w, 32), hpr = ceil_div(h, 32);
   const float2* pin = reinterpret_cast<const float2*>(proj);   // non-hole pixels only: never written here
-  const int n_words = h * wpr;
-  for (int wd = warp0; wd < n_words; wd += nw) {
-    const int y = wd / wpr, seg0 = wd - y * wpr;
-    const int x = seg0 * 32 + lane;
-    const uint32_t hits = rowmask[wd];
-    if (x >= w || ((hits >> lane) & 1u)) continue;
-    const int p = y * w + x;
-    float sx = 0.f, sy = 0.f;
-    int found = 0;
-    auto take = [&](int yy, int xx) {
-      const float2 q = CG ? __ldcg(pin + yy * w + xx) : pin[yy * w + xx];   // the neighbour's normalised value, as written by the normalise pass
-      sx += q.x;
-      sy += q.y;
-      ++found;
-    };
-    {  // left
-      int seg = x >> 5;
-      uint32_t word = hits & ((1u << (x & 31)) - 1u);
-      while (word == 0 && seg > 0) word = rowmask[y * wpr + --seg];
-      if (word) take(y, seg * 32 + 31 - __clz(word));
-    }
-    {  // right
-      int seg = x >> 5;
-      uint32_t word = hits & ~((2u << (x & 31)) - 1u);
-      while (word == 0 && seg + 1 < wpr) word = rowmask[y * wpr + ++seg];
-      if (word) take(y, seg * 32 + __ffs(word) - 1);
-    }
-    {  // up
-      int sb = y >> 5;
-      uint32_t word = colmask[sb * w + x] & ((1u << (y & 31)) - 1u);
-      while (word == 0 && sb > 0) word = colmask[--sb * w + x];
-      if (word) take(sb * 32 + 31 - __clz(word), x);
-    }
-    {  // down
-      int sb = y >> 5;
-      uint32_t word = colmask[sb * w + x] & ~((2u << (y & 31)) - 1u);
-      while (word == 0 && sb + 1 < hpr) word = colmask[++sb * w + x];
-      if (word) take(sb * 32 + __ffs(word) - 1, x);
-    }
-    if (found > 0) reinterpret_cast<float2*>(proj)[p] = make_float2(__fdiv_rn(sx, (float)found), __fdiv_rn(sy, (float)found));
+  const int y = wd / wpr, seg0 = wd - y * wpr;
+  const int x = seg0 * 32 + lane;
+  const uint32_t hits = rowmask[wd];
+  if (x >= w || ((hits >> lane) & 1u)) return;
+  const int p = y * w + x;
+  float sx = 0.f, sy = 0.f;
+  int found = 0;
+  auto take = [&](int yy, int xx) {
+    const float2 q = CG ? __ldcg(pin + yy * w + xx) : pin[yy * w + xx];   // the neighbour's normalised value, as written by the normalise pass
+    sx += q.x;
+    sy += q.y;
+    ++found;
+  };
+  {  // left
+    int seg = x >> 5;
+    uint32_t word = hits & ((1u << (x & 31)) - 1u);
+    while (word == 0 && seg > 0) word = rowmask[y * wpr + --seg];
+    if (word) take(y, seg * 32 + 31 - __clz(word));
   }
+  {  // right
+    int seg = x >> 5;
+    uint32_t word = hits & ~((2u << (x & 31)) - 1u);
+    while (word == 0 && seg + 1 < wpr) word = rowmask[y * wpr + ++seg];
+    if (word) take(y, seg * 32 + __ffs(word) - 1);
+  }
+  {  // up
+    int sb = y >> 5;
+    uint32_t word = colmask[sb * w + x] & ((1u << (y & 31)) - 1u);
+    while (word == 0 && sb > 0) word = colmask[--sb * w + x];
+    if (word) take(sb * 32 + 31 - __clz(word), x);
+  }
+  {  // down
+    int sb = y >> 5;
+    uint32_t word = colmask[sb * w + x] & ~((2u << (y & 31)) - 1u);
+    while (word == 0 && sb + 1 < hpr) word = colmask[++sb * w + x];
+    if (word) take(sb * 32 + __ffs(word) - 1, x);
+  }
+  if (found > 0) reinterpret_cast<float2*>(proj)[p] = make_float2(__fdiv_rn(sx, (float)found), __fdiv_rn(sy, (float)found));
+}
+
+template <bool CG>
+__device__ __forceinline__ void role_fill(const uint32_t* rowmask, const uint32_t* colmask, float* proj, int h, int w,
+                                          int warp0, int nw, int lane) {
+  const int n_words = h * ceil_div(w, 32);
+  for (int wd = warp0; wd < n_words; wd += nw) fill_word<CG>(rowmask, colmask, proj, h, w, wd, lane);
 }
 
 // The general path: one cooperative persistent kernel over the whole batch.  Phase p (p = -1 .. B+1):
@@ -450,7 +455,7 @@ __device__ __forceinline__ void claim_round2(uint32_t& pend0, uint32_t& pend1, u
 
 // Adds U (1 or 2) x 32 sources (flow fx/fy, inverse depth dd, position xs/ys; NaN flow = no source) to the tile's
 // cells.  Sources of one call that hit the same cell take turns (claim_round2).
-template <int U>
+template <int U, bool VMAX>
 __device__ __forceinline__ void add_sources(const float (&fx)[U], const float (&fy)[U], const float (&dd)[U],
                                             const float (&xs)[U], const float (&ys)[U], uint32_t cells_sa,
                                             uint32_t claim_sa, const TileRect& R, int lane, float& vmax) {
@@ -461,7 +466,7 @@ __device__ __forceinline__ void add_sources(const float (&fx)[U], const float (&
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     const float x2 = __fadd_rn(xs[u], fx[u]), y2 = __fadd_rn(ys[u], fy[u]);
-    vmax = fmaxf(vmax, fmaxf(fabsf(fx[u]), fabsf(fy[u])));
+    if (VMAX) vmax = fmaxf(vmax, fmaxf(fabsf(fx[u]), fabsf(fy[u])));
     // "lands in one of the tile's cells and inside the image" (Appendix B step 2; NaN fails every compare)
     const bool in = x2 >= R.xa && x2 <= R.xb && y2 >= R.ya && y2 <= R.yb;
     pend[u] = in ? 1u : 0u;
@@ -495,6 +500,21 @@ struct BlockData {
   float2 d[4];      // inverse depth of the pair
 };
 
+// The block loads are asm volatile so that they stay where they are written: AFTER touch_block() of the block about
+// to be processed.  ncu on the first version (plain __ldg prefetch at the top of a phase): in two of the four phases
+// ptxas had put the loads of both register buffers on the same scoreboard, so the first use of the block loaded a
+// phase ago also waited for the loads issued a few instructions earlier -- ~1.8k cycles per block, every time.
+__device__ __forceinline__ float4 ldg_nc_f4_v(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float2 ldg_nc_f2_v(const float2* p) {
+  float2 r;
+  asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+  return r;
+}
+
 __device__ __forceinline__ void load_block(BlockData& s, const float2* __restrict__ flow, const float* __restrict__ depth,
                                            int h, int w, int bx0, int by0, int lane) {
   const int x = bx0 + 2 * (lane & 7), y0 = by0 + 4 * (lane >> 3), rot = (lane >> 2) & 1;
@@ -503,9 +523,9 @@ __device__ __forceinline__ void load_block(BlockData& s, const float2* __restric
     const int o3 = o0 + (3 - 4 * rot) * w;
     const int off[4] = {o0, o0 + w, o0 + 2 * w, o3};
 #pragma unroll
-    for (int k = 0; k < 4; ++k) s.f[k] = __ldg(reinterpret_cast<const float4*>(flow + off[k]));
+    for (int k = 0; k < 4; ++k) s.f[k] = ldg_nc_f4_v(reinterpret_cast<const float4*>(flow + off[k]));
 #pragma unroll
-    for (int k = 0; k < 4; ++k) s.d[k] = depth ? __ldg(reinterpret_cast<const float2*>(depth + off[k])) : make_float2(1.0f, 1.0f);
+    for (int k = 0; k < 4; ++k) s.d[k] = depth ? ldg_nc_f2_v(reinterpret_cast<const float2*>(depth + off[k])) : make_float2(1.0f, 1.0f);
     return;
   }
   const bool okx = (unsigned)x < (unsigned)w;       // w and x are even: the pair is inside or outside together
@@ -517,9 +537,25 @@ __device__ __forceinline__ void load_block(BlockData& s, const float2* __restric
     s.d[k] = make_float2(1.0f, 1.0f);
     if (okx && (unsigned)y < (unsigned)h) {
       const int off = y * w + x;
-      s.f[k] = __ldg(reinterpret_cast<const float4*>(flow + off));
-      if (depth) s.d[k] = __ldg(reinterpret_cast<const float2*>(depth + off));
+      s.f[k] = ldg_nc_f4_v(reinterpret_cast<const float4*>(flow + off));
+      if (depth) s.d[k] = ldg_nc_f2_v(reinterpret_cast<const float2*>(depth + off));
     }
+  }
+}
+
+// First use of every register of a block, as asm volatile (ordered before the next block's loads): the bound check
+// (vmax = largest |flow component| seen; max ignores the NaN of "no source") and a running minimum of the inverse
+// depths, whose only purpose is to read them here (its use at the end of the kernel can never change a result).
+__device__ __forceinline__ void touch_block(const BlockData& s, float& vmax, float& dmin) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    asm volatile(
+        "{\n .reg .f32 t0, t1;\n"
+        " abs.f32 t0, %2;\n abs.f32 t1, %3;\n max.f32 t0, t0, t1;\n max.f32 %0, %0, t0;\n"
+        " abs.f32 t0, %4;\n abs.f32 t1, %5;\n max.f32 t0, t0, t1;\n max.f32 %0, %0, t0;\n"
+        " min.f32 t0, %6, %7;\n min.f32 %1, %1, t0;\n}"
+        : "+f"(vmax), "+f"(dmin)
+        : "f"(s.f[k].x), "f"(s.f[k].y), "f"(s.f[k].z), "f"(s.f[k].w), "f"(s.d[k].x), "f"(s.d[k].y));
   }
 }
 
@@ -545,7 +581,7 @@ __device__ __forceinline__ void add_block(const BlockData& s, int bx0, int by0, 
         xs[u] = xf0 + (float)p;
         ys[u] = yk[k];
       }
-      add_sources<2>(fx, fy, dd, xs, ys, cells_sa, claim_sa, R, lane, vmax);
+      add_sources<2, false>(fx, fy, dd, xs, ys, cells_sa, claim_sa, R, lane, vmax);
     }
   }
 }
@@ -584,6 +620,7 @@ projection_tiled_kernel(const ProjArgs a) {
   // super-block of this warp: block (2*sc + cx, 2*sr + cy) in colour phase (cx, cy)
   const int sc = warp % (kNBX / 2), sr = warp / (kNBX / 2);
   float vmax = 0.0f;                              // largest |flow component| this thread has looked at
+  float dmin = __int_as_float(0x7f800000);        // see touch_block
 
   // the block of (tile, colour): origin and image
   auto block_org = [&](const TilePos& t, int c, int& bx0, int& by0) {
@@ -674,6 +711,7 @@ projection_tiled_kernel(const ProjArgs a) {
       if (warp < kAccWarps) {
         BlockData& cur = (c & 1) ? bufB : bufA;
         BlockData& nxt = (c & 1) ? bufA : bufB;
+        touch_block(cur, vmax, dmin);             // waits for the loads of a phase ago -- before the next ones go out
         if (c < 3) prefetch(nxt, tile, c + 1); else prefetch(nxt, tile + gridDim.x, 0);
         int bx0, by0;
         block_org(t, c, bx0, by0);
@@ -685,7 +723,7 @@ projection_tiled_kernel(const ProjArgs a) {
         for (int ch = 0; ch < kExtraChunks; ++ch) {
           float fx[1] = {ex_f[ch].x}, fy[1] = {ex_f[ch].y}, dd[1] = {ex_d[ch]};
           float xs[1] = {(float)(tx0 + kSX0 + 32 * ch + lane)}, ys[1] = {(float)ye};
-          add_sources<1>(fx, fy, dd, xs, ys, cells_sa, claim_sa, R, lane, vmax);
+          add_sources<1, true>(fx, fy, dd, xs, ys, cells_sa, claim_sa, R, lane, vmax);
         }
       }
       if (c == 0 && warp == kAccWarps) load_extra(tile + gridDim.x);
@@ -709,7 +747,8 @@ projection_tiled_kernel(const ProjArgs a) {
           hp = make_float4(fmaf(c1.x, mx, c0.x), fmaf(c1.y, mx, c0.y), fmaf(c1.z, mx, c0.z), fmaf(c1.w, mx, c0.w));
         }
         uint32_t colbits = 0;
-        bool any_hole = false;
+        uint32_t holerows = 0;                      // warp-uniform: rows of this chunk whose word has a hole
+        const uint32_t inx_mask = __ballot_sync(0xffffffffu, in_x);
         const int rows = min(kOutRows, h - (ty0 + r0));
         const int64_t p0 = (int64_t)t.tb * P + (ty0 + r0) * w + x;
         float2* pp = reinterpret_cast<float2*>(a.proj) + p0;
@@ -736,7 +775,7 @@ projection_tiled_kernel(const ProjArgs a) {
           const uint32_t m = __ballot_sync(0xffffffffu, in_x && !is_hole);
           if (lane == 0) *pr = m;
           colbits |= (uint32_t)(in_x && !is_hole) << r;
-          any_hole |= in_x && is_hole;
+          holerows |= (uint32_t)((inx_mask & ~m) != 0) << r;
           pp += w;
           if (WSUM) pw += w;
           pc += w;
@@ -749,7 +788,17 @@ projection_tiled_kernel(const ProjArgs a) {
         uint32_t* cmw = s_colm + (pos >> 5) * kTW + 32 * chunk + lane;
         if ((uint32_t)bits) atomicOr(cmw, (uint32_t)bits);
         if ((uint32_t)(bits >> 32)) atomicOr(cmw + kTW, (uint32_t)(bits >> 32));
-        if (__any_sync(0xffffffffu, any_hole) && lane == 0) *reinterpret_cast<volatile int*>(a.flags + 1 + t.tb) = 1;
+        // the words with holes go on the list the fill kernel walks (one atomic per warp and tile)
+        const int nh = __popc(holerows);
+        if (nh > 0) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(a.flags + 1 + a.B, nh);
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (lane < nh) {
+            const int r = __fns(holerows, 0, lane + 1);
+            a.holelist[base + lane] = (uint32_t)(t.tb * rw + (ty0 + r0 + r) * rw_x + ((tx0 + 32 * chunk) >> 5));
+          }
+        }
       }
     }
     __syncthreads();
@@ -757,11 +806,14 @@ projection_tiled_kernel(const ProjArgs a) {
   if (prev_tile >= 0) flush_colm(prev_tile);
   // a source beyond the bound: the colour phases may have raced and the scan may have missed cells it reaches -> the
   // whole batch is redone by the general path
-  if (__any_sync(0xffffffffu, vmax > (float)kBD) && lane == 0) *reinterpret_cast<volatile int*>(a.flags) = 1;
+  // (dmin: a value no sum of the comparison can produce keeps the reads of touch_block alive; if an inverse depth
+  // ever were that denormal the batch would merely take the general path)
+  if (__any_sync(0xffffffffu, vmax > (float)kBD || dmin == -1.0e-42f) && lane == 0) *reinterpret_cast<volatile int*>(a.flags) = 1;
 }
 
-// fill of the bounded path: all images in one launch; nothing to do for an image without holes, and nothing at all
-// when the promise was broken (the general path redoes the batch, its own fill included).
+// fill of the bounded path: the listed row words of all images in one launch; nothing at all when the promise was
+// broken (the general path redoes the batch, its own fill included).  (The first version walked every row word of every
+// image with holes: 64 us for eight 1080p images whose only holes sit at the image borders.)
 __global__ void __launch_bounds__(kThreads)
 projection_fill_kernel(const ProjArgs a) {
   if (*reinterpret_cast<volatile int*>(a.flags) != 0) return;
@@ -769,23 +821,28 @@ projection_fill_kernel(const ProjArgs a) {
   const int nw = (gridDim.x * kThreads) >> 5;
   const int warp0 = (blockIdx.x * kThreads + threadIdx.x) >> 5;
   const int64_t P = (int64_t)a.h * a.w;
-  const int64_t rw = rowmask_words(a.h, a.w), cw = colmask_words(a.h, a.w);
-  for (int b = 0; b < a.B; ++b)
-    if (*reinterpret_cast<volatile int*>(a.flags + 1 + b) != 0)
-      role_fill<false>(a.rowmask + b * rw, a.colmask + b * cw, a.proj + b * P * 2, a.h, a.w, warp0, nw, lane);
+  const int rw = (int)rowmask_words(a.h, a.w);
+  const int64_t cw = colmask_words(a.h, a.w);
+  const int n = *reinterpret_cast<volatile int*>(a.flags + 1 + a.B);
+  for (int i = warp0; i < n; i += nw) {
+    const uint32_t gw = __ldg(a.holelist + i);
+    const int b = (int)(gw / (uint32_t)rw), wd = (int)(gw - (uint32_t)b * (uint32_t)rw);
+    fill_word<false>(a.rowmask + (int64_t)b * rw, a.colmask + b * cw, a.proj + b * P * 2, a.h, a.w, wd, lane);
+  }
 }
 
 struct ProjWs {
-  size_t acc_bytes, flags_off, row_off, col_off, total;
+  size_t acc_bytes, flags_off, row_off, col_off, list_off, total;
 };
 inline size_t up256(size_t v) { return (v + 255) / 256 * 256; }
 inline ProjWs proj_ws(int B, int h, int w) {
   ProjWs s;
   s.acc_bytes = (size_t)h * w * sizeof(float4);
   s.flags_off = 3 * s.acc_bytes;
-  s.row_off = s.flags_off + up256((size_t)(B + 1) * 4);
+  s.row_off = s.flags_off + up256((size_t)(B + 2) * 4);
   s.col_off = s.row_off + up256((size_t)B * ceil_div(w, 32) * h * 4);
-  s.total = s.col_off + up256((size_t)B * ceil_div(h, 32) * w * 4);
+  s.list_off = s.col_off + up256((size_t)B * ceil_div(h, 32) * w * 4);
+  s.total = s.list_off + up256((size_t)B * ceil_div(w, 32) * h * 4);
   return s;
 }
 
@@ -885,12 +942,14 @@ extern "C" int vsr_flow_projection_forward_bounded(const float* flow, const floa
   a.flags = reinterpret_cast<int*>(base + ws.flags_off);
   a.rowmask = reinterpret_cast<uint32_t*>(base + ws.row_off);
   a.colmask = reinterpret_cast<uint32_t*>(base + ws.col_off);
+  a.holelist = reinterpret_cast<uint32_t*>(base + ws.list_off);
   a.B = B;
   a.h = h;
   a.w = w;
   a.bound = 0;
   a.gate = 0;
-  const bool bounded = max_disp >= 0.0f && max_disp <= (float)kMaxBound && w % 2 == 0;   // NaN / negative / large, or
+  const bool bounded = max_disp >= 0.0f && max_disp <= (float)kMaxBound && w % 2 == 0 &&
+                       (int64_t)B * h * ceil_div(w, 32) < ((int64_t)1 << 31);   // NaN / negative / large, or
                                                                                        // unaligned pixel pairs: general path
   if (!bounded) return run_general(a, st);
 
@@ -904,7 +963,7 @@ extern "C" int vsr_flow_projection_forward_bounded(const float* flow, const floa
     if (e != cudaSuccess) return cuda_status(e);
     once.mark(dev);
   }
-  cudaError_t e = cudaMemsetAsync(a.flags, 0, (size_t)(B + 1) * 4, st);
+  cudaError_t e = cudaMemsetAsync(a.flags, 0, (size_t)(B + 2) * 4, st);
   if (e != cudaSuccess) return cuda_status(e);
   const int n_tiles = ceil_div(w, kTW) * ceil_div(h, kTH) * B;
   if (wsum)
@@ -915,7 +974,7 @@ extern "C" int vsr_flow_projection_forward_bounded(const float* flow, const floa
   if (rc) return rc;
   const int64_t fill_warps = (int64_t)h * ceil_div(w, 32);
   int64_t fill_blocks = ceil_div64(fill_warps, kThreads / 32);
-  if (fill_blocks > kNumSMs * 8) fill_blocks = kNumSMs * 8;
+  if (fill_blocks > kNumSMs * 4) fill_blocks = kNumSMs * 4;
   projection_fill_kernel<<<(int)fill_blocks, kThreads, 0, st>>>(a);
   rc = after_launch();
   if (rc) return rc;
