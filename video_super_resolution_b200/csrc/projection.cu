@@ -166,8 +166,10 @@ template <bool CG, bool LOOP>
 __device__ __forceinline__ void role_normalise(const float4* __restrict__ acc, float* __restrict__ proj,
                                                float* __restrict__ wsum, int32_t* __restrict__ count,
                                                uint8_t* __restrict__ hole, uint32_t* __restrict__ rowmask,
-                                               uint32_t* __restrict__ colmask, int* __restrict__ has_holes, int h, int w,
-                                               int warp0, int nw, int lane) {
+                                               uint32_t* __restrict__ colmask, int* __restrict__ has_holes,
+                                               uint32_t* __restrict__ holelist, int h, int w, int warp0, int nw, int lane) {
+  // holelist != nullptr: *has_holes counts the row words with holes and holelist names them (the fill then visits only
+  // those); nullptr: *has_holes is a flag and the fill scans every word
   const int tiles_x = ceil_div(w, 32);
   const int n_strips = 2 * ceil_div(h, 32);          // both halves of every column word get written
   const int n_tasks = tiles_x * n_strips;
@@ -183,7 +185,8 @@ __device__ __forceinline__ void role_normalise(const float4* __restrict__ acc, f
     float4 up_left = shfl_up1_f4(up);                                                              // cell (y0-1, x-1)
     if (lane == 0) up_left = (x > 0 && y0 > 0 && y0 <= h) ? ldg_f4<CG>(acc + (y0 - 1) * w + x - 1) : zero4;
     uint32_t colbits = 0;
-    bool any_hole = false;
+    uint32_t holerows = 0;                             // warp-uniform: rows of the strip whose word has a hole
+    const uint32_t inx_mask = __ballot_sync(0xffffffffu, in_x);
 #pragma unroll
     for (int r0 = 0; r0 < kStrip; r0 += kBatch) {
       float4 c[kBatch], cl[kBatch];
@@ -224,12 +227,21 @@ __device__ __forceinline__ void role_normalise(const float4* __restrict__ acc, f
         const uint32_t m = __ballot_sync(0xffffffffu, in_img && !is_hole);
         if (lane == 0 && y < h) rowmask[y * tiles_x + tx] = m;
         colbits |= (uint32_t)(in_img && !is_hole) << (r0 + r);
-        any_hole |= in_img && is_hole;
+        holerows |= (uint32_t)(y < h && (inx_mask & ~m) != 0) << (r0 + r);
       }
     }
     if (in_x) reinterpret_cast<uint16_t*>(colmask)[((strip >> 1) * w + x) * 2 + (strip & 1)] = (uint16_t)colbits;
-    if (__any_sync(0xffffffffu, any_hole) && lane == 0)
-      *reinterpret_cast<volatile int*>(has_holes) = 1;   // a flag, not a count: plain store
+    if (holerows) {
+      if (holelist) {
+        const int nh = __popc(holerows);
+        int base = 0;
+        if (lane == 0) base = atomicAdd(has_holes, nh);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (lane < nh) holelist[base + lane] = (uint32_t)((y0 + __fns(holerows, 0, lane + 1)) * tiles_x + tx);
+      } else if (lane == 0) {
+        *reinterpret_cast<volatile int*>(has_holes) = 1;   // a flag, not a count: plain store
+      }
+    }
   }
 }
 
@@ -322,8 +334,8 @@ projection_pipeline_kernel(const ProjArgs a) {
         const int b = p - 1;
         if (b >= 0 && b < a.B)
           role_normalise<true, true>(a.acc + (b % 3) * P, a.proj + b * P * 2, a.wsum ? a.wsum + b * P : nullptr, a.count + b * P,
-                         a.hole + b * P, a.rowmask + b * rw, a.colmask + b * cw, a.flags + 1 + b, a.h, a.w, warp0, nw,
-                         lane);
+                         a.hole + b * P, a.rowmask + b * rw, a.colmask + b * cw, a.flags + 1 + b, nullptr, a.h, a.w,
+                         warp0, nw, lane);
       } else {
         const int b = p - 2;
         if (b >= 0 && b < a.B && *reinterpret_cast<volatile int*>(a.flags + 1 + b) != 0)
@@ -343,15 +355,22 @@ stage_splat_kernel(const float* __restrict__ flow, const float* __restrict__ inv
 __global__ void __launch_bounds__(kThreads, 4)
 stage_normalise_kernel(const float4* __restrict__ acc, float* __restrict__ proj, float* __restrict__ wsum,
                        int32_t* __restrict__ count, uint8_t* __restrict__ hole, uint32_t* __restrict__ rowmask,
-                       uint32_t* __restrict__ colmask, int* __restrict__ has_holes, int h, int w) {
-  role_normalise<false, false>(acc, proj, wsum, count, hole, rowmask, colmask, has_holes, h, w, (blockIdx.x * kThreads + threadIdx.x) >> 5,
-                 (gridDim.x * kThreads) >> 5, threadIdx.x & 31);
+                       uint32_t* __restrict__ colmask, int* __restrict__ n_holewords, uint32_t* __restrict__ holelist, int h,
+                       int w) {
+  role_normalise<false, false>(acc, proj, wsum, count, hole, rowmask, colmask, n_holewords, holelist, h, w,
+                               (blockIdx.x * kThreads + threadIdx.x) >> 5, (gridDim.x * kThreads) >> 5, threadIdx.x & 31);
 }
+// fill of the general path: the row words of one image that the normalise stage listed
 __global__ void __launch_bounds__(kThreads)
-stage_fill_kernel(const uint32_t* rowmask, const uint32_t* colmask, const int* has_holes, float* proj, int h, int w) {
-  if (*reinterpret_cast<const volatile int*>(has_holes) == 0) return;
-  role_fill<false>(rowmask, colmask, proj, h, w, (blockIdx.x * kThreads + threadIdx.x) >> 5, (gridDim.x * kThreads) >> 5,
-                   threadIdx.x & 31);
+stage_fill_kernel(const uint32_t* rowmask, const uint32_t* colmask, const int* n_holewords, const uint32_t* holelist,
+                  float* proj, float4* zero_acc, int h, int w) {
+  // the cell array is free once the normalise stage is through: cleared here for the next image (one launch and its gap
+  // less than a memset per image)
+  if (zero_acc) role_zero(zero_acc, (int64_t)h * w, (int64_t)blockIdx.x * kThreads + threadIdx.x, (int64_t)gridDim.x * kThreads);
+  const int n = *reinterpret_cast<const volatile int*>(n_holewords);
+  const int nw = (gridDim.x * kThreads) >> 5, lane = threadIdx.x & 31;
+  for (int i = (blockIdx.x * kThreads + threadIdx.x) >> 5; i < n; i += nw)
+    fill_word<false>(rowmask, colmask, proj, h, w, (int)__ldg(holelist + i), lane);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -892,18 +911,19 @@ int run_general(const ProjArgs& a, cudaStream_t st) {
   const int n_tasks = ceil_div(w, 32) * ceil_div(h, kRows);
   const int splat_blocks = ceil_div(n_tasks, kThreads / 32);
   const int norm_blocks = ceil_div(ceil_div(w, 32) * 2 * ceil_div(h, 32), kThreads / 32);
-  const int fill_blocks = ceil_div(h * ceil_div(w, 32), kThreads / 32);   // one warp per 32-pixel row word
+  const int fill_blocks = min(ceil_div(h * ceil_div(w, 32), kThreads / 32), kNumSMs * 16);   // warps walk the hole list
+  if ((e = cudaMemsetAsync(a.acc, 0, (size_t)P * sizeof(float4), st)) != cudaSuccess) return cuda_status(e);
   for (int b = 0; b < a.B; ++b) {
-    if ((e = cudaMemsetAsync(a.acc, 0, (size_t)P * sizeof(float4), st)) != cudaSuccess) return cuda_status(e);
     stage_splat_kernel<<<splat_blocks, kThreads, 0, st>>>(a.flow + b * P * 2, a.inv_depth ? a.inv_depth + b * P : nullptr, a.acc, h, w);
     int rc = after_launch();
     if (rc) return rc;
     stage_normalise_kernel<<<norm_blocks, kThreads, 0, st>>>(a.acc, a.proj + b * P * 2, a.wsum ? a.wsum + b * P : nullptr,
                                                             a.count + b * P, a.hole + b * P, a.rowmask + b * rw,
-                                                            a.colmask + b * cw, a.flags + 1 + b, h, w);
+                                                            a.colmask + b * cw, a.flags + 1 + b, a.holelist + b * rw, h, w);
     if ((rc = after_launch())) return rc;
     stage_fill_kernel<<<fill_blocks, kThreads, 0, st>>>(a.rowmask + b * rw, a.colmask + b * cw, a.flags + 1 + b,
-                                                       a.proj + b * P * 2, h, w);
+                                                       a.holelist + b * rw, a.proj + b * P * 2,
+                                                       b + 1 < a.B ? a.acc : nullptr, h, w);
     if ((rc = after_launch())) return rc;
   }
   return VSR_OK;
@@ -974,7 +994,7 @@ extern "C" int vsr_flow_projection_forward_bounded(const float* flow, const floa
   if (rc) return rc;
   const int64_t fill_warps = (int64_t)h * ceil_div(w, 32);
   int64_t fill_blocks = ceil_div64(fill_warps, kThreads / 32);
-  if (fill_blocks > kNumSMs * 4) fill_blocks = kNumSMs * 4;
+  if (fill_blocks > kNumSMs * 16) fill_blocks = kNumSMs * 16;
   projection_fill_kernel<<<(int)fill_blocks, kThreads, 0, st>>>(a);
   rc = after_launch();
   if (rc) return rc;
