@@ -411,6 +411,8 @@ constexpr int kTileWarps = 16;
 constexpr int kTileThreads = 32 * kTileWarps;
 static_assert(kAccWarps < kTileWarps && kTileWarps % 4 == 0 && kTH % (kTileWarps / 4) == 0, "warp roles");
 constexpr int kOutRows = kTH / (kTileWarps / 4);    // 20 target rows per output warp (4 column chunks of 32)
+constexpr int kSeamRows = kTH / kOutRows + 1;       // cell rows 0, kOutRows, 2 kOutRows, ..: read by two output warps
+constexpr int kSeamCells = kSeamRows * kCW + kCH * (kTW / 32 + 1);   // + cell columns 0, 32, 64, .. (all rows)
 constexpr int kColWords = 4;                        // staged column bitmap: bit (ty0 % 32) + row, up to 16 + 79
 constexpr int kMaxBound = kBD;
 constexpr int kExtraChunks = kNBX * kBS / 32;       // the extra source row, 32 sources at a time
@@ -425,8 +427,9 @@ struct TileRect {      // the tile's cells as bounds on the target position (x2,
 // of the same logic rebuilt the shared window base and converted predicates to integers and back in every round).
 // pend0/pend1 (in/out, 0 or 1): the source still has to be added.  Everybody pending writes its id to the claim byte
 // of its cell, the survivor of a cell reads the cell, adds {vx, vy, d, 1} and writes it back, and stops pending.
-// Branch-free and unpredicated: a lane with nothing to add runs the same accesses on its OWN scratch cell / claim byte
-// (scr_cell, scr_claim: one per lane, so idle lanes do not pile up on one bank as they did on a shared dummy cell).
+// Branch-free; the loads are unpredicated (a predicated shared load into registers that are live afterwards costs
+// ptxas a copy per register): a lane with nothing to add reads its OWN scratch cell / claim byte (scr_cell, scr_claim:
+// one per lane, so idle lanes do not pile up on one bank as they did on a shared dummy cell); the stores are predicated.
 // claim0/claim1 must already point at the scratch byte for sources that are not pending.
 __device__ __forceinline__ void claim_round2(uint32_t& pend0, uint32_t& pend1, uint32_t& claim0, uint32_t& claim1,
                                              uint32_t id0, uint32_t id1, uint32_t cell0, uint32_t cell1, float vx0,
@@ -434,18 +437,20 @@ __device__ __forceinline__ void claim_round2(uint32_t& pend0, uint32_t& pend1, u
                                              uint32_t scr_claim) {
   asm volatile(
       "{\n"
-      " .reg .pred w0, w1;\n"
+      " .reg .pred w0, w1, p0, p1;\n"
       " .reg .b32 who0, who1, c0, c1;\n"
       " .reg .f32 a0, a1, a2, a3, b0, b1, b2, b3;\n"
-      " st.shared.u8 [%2], %4;\n"
-      " st.shared.u8 [%3], %5;\n"
+      " setp.ne.u32 p0, %0, 0;\n"
+      " setp.ne.u32 p1, %1, 0;\n"
+      " @p0 st.shared.u8 [%2], %4;\n"
+      " @p1 st.shared.u8 [%3], %5;\n"
       " bar.warp.sync 0xffffffff;\n"
       " ld.shared.u8 who0, [%2];\n"
       " ld.shared.u8 who1, [%3];\n"
       " setp.eq.u32 w0, who0, %4;\n"
       " setp.eq.u32 w1, who1, %5;\n"
-      " setp.ne.and.u32 w0, %0, 0, w0;\n"
-      " setp.ne.and.u32 w1, %1, 0, w1;\n"
+      " and.pred w0, w0, p0;\n"
+      " and.pred w1, w1, p1;\n"
       " selp.u32 c0, %6, %14, w0;\n"
       " selp.u32 c1, %7, %14, w1;\n"
       " ld.shared.v4.f32 {a0, a1, a2, a3}, [c0];\n"
@@ -458,8 +463,8 @@ __device__ __forceinline__ void claim_round2(uint32_t& pend0, uint32_t& pend1, u
       " add.f32 b1, b1, %12;\n"
       " add.f32 b2, b2, %13;\n"
       " add.f32 b3, b3, 0f3F800000;\n"
-      " st.shared.v4.f32 [c0], {a0, a1, a2, a3};\n"
-      " st.shared.v4.f32 [c1], {b0, b1, b2, b3};\n"
+      " @w0 st.shared.v4.f32 [c0], {a0, a1, a2, a3};\n"
+      " @w1 st.shared.v4.f32 [c1], {b0, b1, b2, b3};\n"
       " selp.u32 %0, 0, %0, w0;\n"          // a winner is done: from now on it only touches its scratch byte (a winner
       " selp.u32 %1, 0, %1, w1;\n"          // that kept writing its id to the real claim byte would starve the others)
       " selp.u32 %2, %15, %2, w0;\n"
@@ -655,6 +660,7 @@ projection_tiled_kernel(const ProjArgs a) {
   };
 
   for (int i = threadIdx.x; i < kColWords * kTW; i += kTileThreads) s_colm[i] = 0;
+  for (int i = threadIdx.x; i < kNC; i += kTileThreads) s_cells[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   BlockData bufA, bufB;                           // the next block's loads fly under the current block's arithmetic
   if (warp < kAccWarps) prefetch(bufA, blockIdx.x, 0);
 
@@ -708,7 +714,20 @@ projection_tiled_kernel(const ProjArgs a) {
     if (prev_tile >= 0) flush_colm(prev_tile);
     prev_tile = tile;
     const int ye = ty0 + kTH - 1 + kBD;          // the extra source row (warp kAccWarps), loaded a tile ahead
-    for (int i = threadIdx.x; i < kNC; i += kTileThreads) s_cells[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // the cells: the output pass of the previous tile cleared what only one warp reads; the rest -- the rows / columns
+    // on the seams between the output warps and the halo row / column -- is cleared here
+    for (int i = threadIdx.x; i < kSeamCells; i += kTileThreads) {
+      int row, col;
+      if (i < kSeamRows * kCW) {
+        row = (i / kCW) * kOutRows;
+        col = i % kCW;
+      } else {
+        const int j = i - kSeamRows * kCW;
+        row = j / (kTW / 32 + 1);
+        col = (j % (kTW / 32 + 1)) * 32;
+      }
+      s_cells[row * kCW + col] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 
     TileRect R;
     {
@@ -756,7 +775,7 @@ projection_tiled_kernel(const ProjArgs a) {
         const int x = tx0 + 32 * chunk + lane;
         const bool in_x = x < w;
         const float mx = (x == w - 1) ? 2.0f : 1.0f;
-        const float4* col = s_cells + r0 * kCW + 32 * chunk + lane + 1;     // cell row above the first target
+        float4* col = s_cells + r0 * kCW + 32 * chunk + lane + 1;           // cell row above the first target
         // horizontal pair sums h(r) = cell(r, x) * mx + cell(r, x-1); target = h(own row) * my + h(row above).  The
         // clamped duplicate targets of Appendix B ("hit twice") are the multiplicities mx, my of the last column / row.
         // Both cells come from shared memory (a second 16-byte load is cheaper than four shuffles and their moves).
@@ -779,6 +798,11 @@ projection_tiled_kernel(const ProjArgs a) {
         for (int r = 0; r < rows; ++r) {
           col += kCW;
           const float4 c1 = col[0], c0 = col[-1];
+          // cleared for the next tile right here, except what another warp reads too (lane 31's own column is the next
+          // chunk's left neighbour, the last row the next row group's row above): those cells wait for the barrier
+          // (__syncwarp: the neighbouring lane's load of this cell as ITS left neighbour must come first)
+          __syncwarp();
+          if (lane < 31 && r < kOutRows - 1) col[0] = make_float4(0.f, 0.f, 0.f, 0.f);
           const float4 hc = make_float4(fmaf(c1.x, mx, c0.x), fmaf(c1.y, mx, c0.y), fmaf(c1.z, mx, c0.z), fmaf(c1.w, mx, c0.w));
           const float my = (r == r_last) ? 2.0f : 1.0f;
           const float4 tg = make_float4(fmaf(hc.x, my, hp.x), fmaf(hc.y, my, hp.y), fmaf(hc.z, my, hp.z), fmaf(hc.w, my, hp.w));
