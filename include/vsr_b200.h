@@ -159,10 +159,11 @@ int vsr_correlation_backward(const float* input1, const float* input2, const flo
  * cell array, the stages of successive images pipelined inside one cooperative persistent kernel.
  *
  * vsr_flow_projection_forward_bounded: the caller additionally PROMISES |fx|, |fy| <= max_disp for every pixel
- * (the smooth fields of configs C2/C4/C5: 8 px).  For 0 <= max_disp <= 16 the batch runs through shared-memory
- * tiles (target tile + halo, owner-computes accumulation without atomics, one coalesced pass out).  A broken
- * promise is detected on the device and the batch is redone by the general path: the result never depends on the
- * promise, only the speed does.  Any other max_disp (negative, NaN, > 16) selects the general path directly.
+ * (the smooth fields of configs C2/C4/C5: 8 px).  For 0 <= max_disp <= 8 (and an even w) the batch runs through
+ * shared-memory tiles (target tile + halo, owner-computes accumulation without atomics, one coalesced pass out).  A
+ * broken promise (a component beyond 8 px) is detected on the device and the batch is redone by the general path: the
+ * result never depends on the promise, only the speed does.  Any other max_disp (negative, NaN, > 8) selects the
+ * general path directly.
  * ---------------------------------------------------------------------------------------- */
 size_t vsr_flow_projection_workspace_bytes(int B, int h, int w);
 int vsr_flow_projection_forward(const float* flow, const float* inv_depth,

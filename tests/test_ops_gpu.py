@@ -140,8 +140,11 @@ def test_projection_smooth_flow(shape, weighted):
     B, h, w = shape
     flow = synthetic.smooth_flow(B, h, w, 8.0, seed=h)
     inv = synthetic.inv_depth(B, h, w, seed=w) if weighted else None
-    # 8.0 / 16.0: promises that hold (tile path); 3.0: a promise this field breaks (flag + redo by the general path)
+    # 8.0 / 3.0: the tile path (its geometry is always the 8 px one: a smaller promise this field exceeds is harmless);
+    # 16.0: beyond the tile path's bound -> the general path
     _check_projection(flow, inv, bounds=(None, 8.0, 16.0, 3.0))
+    # a promise the field breaks beyond 8 px: flagged on the device, the batch redone by the general path
+    _check_projection(flow * 1.5, inv, bounds=(8.0,))
 
 
 @pytest.mark.parametrize("shape", [(1, 200, 400), (2, 65, 193), (1, 64, 192), (3, 129, 385), (1, 80, 128), (2, 81, 130),
@@ -153,7 +156,8 @@ def test_projection_tile_path_across_tile_borders(shape):
     inv = synthetic.inv_depth(B, h, w, seed=3)
     _check_projection(synthetic.smooth_flow(B, h, w, 8.0, seed=5), inv, bounds=(8.0,))
     _check_projection(synthetic.random_flow(B, h, w, 6.0, seed=6), inv, bounds=(6.0, 7.5))
-    _check_projection(synthetic.random_flow(B, h, w, 16.0, seed=7), None, bounds=(16.0,))
+    _check_projection(synthetic.random_flow(B, h, w, 8.0, seed=7), None, bounds=(8.0,))
+    _check_projection(synthetic.random_flow(B, h, w, 12.0, seed=8), None, bounds=(8.0,))      # broken promise -> redo
 
 
 @pytest.mark.parametrize("weighted", [False, True])
@@ -161,7 +165,7 @@ def test_projection_collision_stress_random_flow(weighted):
     B, h, w = 2, 96, 160
     flow = synthetic.random_flow(B, h, w, 64.0, seed=1)
     inv = synthetic.inv_depth(B, h, w, seed=2) if weighted else None
-    count, hole = _check_projection(flow, inv, bounds=(None, 16.0))      # 16: broken promise -> general path
+    count, hole = _check_projection(flow, inv, bounds=(None, 8.0))       # 8: broken promise -> redo by the general path
     assert hole.any() and count.max() >= 4
 
 
@@ -191,7 +195,7 @@ def test_projection_edge_cases():
     # zero flow (duplicate clamped targets at the borders), all out of range, NaN flow, integer flow
     z = torch.zeros((1, 9, 11, 2))
     _check_projection(z, None, bounds=(None, 0.0, 2.0))
-    _check_projection(torch.full((1, 6, 6, 2), 500.0), None, bounds=(None, 16.0))
+    _check_projection(torch.full((1, 6, 6, 2), 500.0), None, bounds=(None, 8.0))
     n = torch.zeros((1, 6, 7, 2))
     n[0, 2, 3, 0] = float("nan")
     _check_projection(n, None, bounds=(None, 1.0))
@@ -214,7 +218,7 @@ def test_projection_degenerate_shapes_and_border_hits(shape):
     flow[:, -1, :, 1] = (h - 1 - yy[-1, :]).float()          # last row's sources stay on the last row
     flow[:, 0, 0, :] = torch.tensor([float(w - 1), float(h - 1)])   # corner source -> opposite corner exactly
     for inv in (None, synthetic.inv_depth(B, h, w, seed=h + w)):
-        _check_projection(flow, inv, bounds=(None, 16.0) if max(h, w) <= 17 else (None,))
+        _check_projection(flow, inv, bounds=(None, 8.0) if max(h, w) <= 8 else (None,))
     small = torch.randint(-3, 4, (B, h, w, 2), generator=g).float() * 0.5       # within +-1.5 px: the tile path
     small[:, :, -1, 0] = 0.0
     small[:, -1, :, 1] = 0.0

@@ -12,18 +12,19 @@
 // the count rides along as a float (exact below 2^24) and is exported as int32 -> count / hole bit-exact.
 //
 // Two paths:
-//  * BOUNDED displacement (caller promises |fx|,|fy| <= max_disp <= 16 px; the pipeline's smooth +-8 px fields):
-//    owner-computes in shared memory.  A CTA owns a 192x64 target tile; its 193x65 cells live in shared memory,
-//    split into 12 rectangles, one per warp.  A warp scans the sources that can reach its rectangle (rectangle +-
-//    bound) and adds the ones that do with plain LDS/STS read-modify-writes -- nobody else touches those cells, so
-//    there are no atomics; two lanes of one instruction that hit the same cell are serialised by a one-byte claim
-//    protocol.  Box sum + normalise + masks + bitmaps then stream out of shared memory in one coalesced pass.  No
-//    global accumulator, no memset, no second pass over the cells: HBM sees the algorithmic bytes only, the L2 the
-//    sources ~2.3x.  A source that breaks the promise raises a flag and the whole batch is redone by the general
-//    path (one gated launch that exits at once otherwise).
+//  * BOUNDED displacement (caller promises |fx|,|fy| <= max_disp <= 8 px; the pipeline's smooth +-8 px fields):
+//    owner-computes in shared memory.  A CTA owns a 128x80 target tile; its 129x81 cells live in shared memory.  The
+//    sources that can reach them (tile +- 8, 1.5 candidates per target) are cut into 16x16 blocks; blocks whose origins
+//    differ by 32 can never touch the same cell, so the blocks are processed in 4 colour phases, one warp per block,
+//    with plain LDS/STS read-modify-writes -- no atomics; lanes of one instruction that hit the same cell are
+//    serialised by a one-byte claim protocol.  Box sum + normalise + masks + bitmaps then stream out of shared memory
+//    in one coalesced pass that also lists the row words with holes for the fill.  No global accumulator, no memset,
+//    no second pass over the cells: HBM sees the algorithmic bytes only.  A source that breaks the promise raises a
+//    flag and the whole batch is redone by the general path (one gated launch that exits at once otherwise).
 //  * GENERAL (config C3's +-64 px): scatter with one 16-byte red.global.add.v4.f32 per source into ONE L2-resident
-//    cell array (33 MB at 1080p), then a gather pass (box sum + normalise + masks) and the fill, image after image on
-//    the caller's stream.  Overlapping the stages of successive images was tried three ways and measured slower (see
+//    cell array (33 MB at 1080p), then a gather pass (box sum + normalise + masks + the list of row words with holes)
+//    and the fill over that list (which also clears the cell array for the next image), image after image on the
+//    caller's stream.  Overlapping the stages of successive images was tried three ways and measured slower (see
 //    run_general); the cooperative pipelined kernel of those experiments survives as the gated fallback of the
 //    bounded path, where what matters is that skipping it costs one empty launch.
 #include <cooperative_groups.h>

@@ -228,7 +228,7 @@ def channelnorm(x: torch.Tensor, norm_deg: int = 2) -> torch.Tensor:
 def project_flow(flow: torch.Tensor, inv_depth: torch.Tensor | None = None, max_disp: float | None = None):
     """Forward flow projection.  flow (B,h,w,2); inv_depth (B,h,w) or None.
     Returns proj (B,h,w,2) f32, wsum (B,h,w) f32, count (B,h,w) i32, hole (B,h,w) u8.
-    max_disp: a promised bound on |fx|, |fy| (<= 16 px) selects the shared-memory tile path; a broken promise is
+    max_disp: a promised bound on |fx|, |fy| (<= 8 px) selects the shared-memory tile path; a broken promise is
     detected on the device and costs time, never correctness.  None: no assumption (atomic scatter path)."""
     _req(flow, torch.float32, "flow")
     B, h, w, two = flow.shape
