@@ -500,6 +500,32 @@ def run_b200(args, rank, world, local_rank):
     ms_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
+    # the same step with the fuse pass reusing what pass 1 already convolved (pipeline.WarpFusePipeline reuse=...): NOT
+    # the headline -- `value` recomputes every map in both passes, as the reference's two SRProjectionModule calls do
+    reuse = None
+    if not args.no_extras:
+        reuse = {"note": "same C2 step, inputs resident; the M maps are independent until the per-pixel fc, so maps that enter "
+                         "both passes unchanged are convolved once (bit-identical frames, tests/test_pipeline_gpu.py). "
+                         "'frames': the T frame maps (video_super_resolution.py:62 feeds `data` unchanged); 'unchanged': all "
+                         "but the estimate slot (this pipeline's flow / depth maps are inputs, not re-estimated). "
+                         "maps_convolved_per_frame counts both passes (headline: 2 M)."}
+        n_re = max(min(args.steps, 10), 2)
+        for mode, n_maps in (("frames", 2 * M_MAPS - T_WIN), ("unchanged", M_MAPS + 1)):
+            pipe_r = WarpFusePipeline(T_WIN, H_LR, W_LR, sr, SCALE, device=dev, max_disp=MAX_DISP, reuse=mode)
+
+            def step_reuse():
+                k = counters["k"]
+                counters["k"] = k + 1
+                r = res[k % SEEDS]
+                return pipe_r.step(r["frames"], r["flows"], r["inv_depth"], r["logits_a"], r["logits_b"],
+                                   out_u8=frames_u8[k % frames_u8.shape[0]], want_f32=False)
+            for _ in range(3):
+                step_reuse()
+            ms_r = timed(step_reuse, n_re)
+            reuse[mode] = {"value": world * n_re / (ms_r / 1e3), "unit": UNIT, "ms_per_step": ms_r / n_re, "steps": n_re,
+                           "maps_convolved_per_frame": n_maps}
+            del pipe_r
+
     # per-launch accounting of one more step (events recorded by the library on the launching stream)
     sr.profile(True)
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
@@ -605,6 +631,8 @@ def run_b200(args, rank, world, local_rank):
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "kernels": kernels, "tflops_per_step": flops_step / 1e12,
             "step_tensor_frac": flops_step / (ms_total / args.steps) / 1e9 / peaks["bf16_sustained"]}
+    if reuse is not None:
+        line["c2_reuse"] = reuse
     line.update(extras)
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -305,6 +305,15 @@ int vsr_srfbn_forward(vsr_srfbn_plan* plan, const float* x, float* y, vsr_stream
  * even, the format the reference's loader holds frames in (utils/video_utils.py:23) -- what a frame writer or the
  * final gather consumes.  Either of y / y_u8 may be NULL, not both. */
 int vsr_srfbn_forward_u8(vsr_srfbn_plan* plan, const float* x, float* y, uint8_t* y_u8, vsr_stream_t stream);
+/* The fuse pass of a frame (video_super_resolution.py:62) feeds `data` -- the frames -- unchanged and replaces the
+ * other maps: the M maps are independent until the per-pixel fc, so a second call whose stack differs from the previous
+ * forward's only in the maps [first_map, M) sweeps the layers over those maps alone and reuses the per-map images of
+ * the others, which are still in the workspace.  Bit-identical to vsr_srfbn_forward_u8 on the same stack.
+ * vsr_srfbn_prepare_refresh (after bind, once per first_map; not with a workspace cap) builds the second layer list;
+ * vsr_srfbn_forward_refresh_u8 needs a preceding full forward of the same plan on the same stream (VSR_ERR_STATE). */
+int vsr_srfbn_prepare_refresh(vsr_srfbn_plan* plan, int first_map);
+int vsr_srfbn_forward_refresh_u8(vsr_srfbn_plan* plan, const float* x, float* y, uint8_t* y_u8, int first_map,
+                                 vsr_stream_t stream);
 /* Per-launch accounting for bench.py: with profiling enabled, vsr_srfbn_forward brackets every
  * kernel launch with CUDA events on the caller's stream; vsr_srfbn_profile_read waits for the last
  * forward and returns, per kernel class, the summed device time (ms), the number of launches, and

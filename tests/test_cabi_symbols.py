@@ -37,8 +37,8 @@ def test_host_side_entry_points_without_gpu():
     assert b"sm_100a" in L.vsr_version()
     assert L.vsr_error_string(0) == b"ok"
     assert b"workspace" in L.vsr_error_string(3)
-    # three rotating cell arrays (16 B per pixel each) + per-image occupancy bitmaps + flags
-    assert 3 * 1080 * 1920 * 16 <= L.vsr_flow_projection_workspace_bytes(8, 1080, 1920) < 3 * 1080 * 1920 * 17
+    # three rotating cell arrays (16 B per pixel each) + per-image occupancy bitmaps + hole-word lists + flags
+    assert 3 * 1080 * 1920 * 16 <= L.vsr_flow_projection_workspace_bytes(8, 1080, 1920) < 3 * 1080 * 1920 * 16 + (8 << 20)
     # argument validation happens before any CUDA call
     assert L.vsr_resample2d_forward(None, None, None, 1, 3, 4, 4, 1, 1, None) == 1
     assert L.vsr_resample2d_forward(1, 1, 1, 1, 3, 4, 4, 17, 1, None) == 2  # kernel_size outside 1..16

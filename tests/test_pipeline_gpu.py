@@ -166,6 +166,36 @@ def test_step_u8_frame_from_the_fuse_kernel():
     assert r is u8b and torch.equal(u8b, u8)
 
 
+@pytest.mark.parametrize("T", [3, 5])
+def test_step_with_reuse_of_the_unchanged_maps_is_bit_identical(T):
+    """reuse='frames' / 'unchanged': the fuse pass convolves only the maps that changed since pass 1 and takes the
+    per-map images of the others from pass 1 -- same frame, bit for bit, eagerly and from a captured graph."""
+    from video_super_resolution_b200.pipeline import GraphedStep
+    h, w = 22, 36
+    M = 3 * T - 1
+    sr = SRProjectionModule(num_maps=M)
+    sr.load_state_dict(so.init_state_dict(num_maps=M, seed=2, gain=2.3))
+    base = WarpFusePipeline(T, h, w, sr, 4, device=DEV, max_disp=5.0)
+    for mode in ("frames", "unchanged"):
+        sr2 = SRProjectionModule(num_maps=M)
+        sr2.load_state_dict(so.init_state_dict(num_maps=M, seed=2, gain=2.3))
+        pipe = WarpFusePipeline(T, h, w, sr2, 4, device=DEV, max_disp=5.0, reuse=mode)
+        g = None
+        for seed in (7, 8, 9):
+            args = [t.to(DEV) for t in _inputs(T, h, w, seed=seed)]
+            u8a = torch.zeros((4 * h, 4 * w, 3), dtype=torch.uint8, device=DEV)
+            u8b = torch.zeros_like(u8a)
+            want = base.step(*args, out_u8=u8a)
+            got = pipe.step(*args, out_u8=u8b)
+            assert torch.equal(got, want) and torch.equal(u8a, u8b), (mode, seed)
+            if g is None:
+                g = GraphedStep(pipe, want_f32=True)
+            g.load(*args)
+            assert torch.equal(g.replay(), want), (mode, seed)
+    with pytest.raises(ValueError):
+        WarpFusePipeline(T, h, w, sr, 4, device=DEV, reuse="all")
+
+
 def test_graphed_step_replays_the_same_frame():
     """The whole per-frame sequence captured into one CUDA graph: replays reproduce the eager frames bit for bit, for
     changing inputs, on both projection paths (the gated cooperative fallback launch is part of the graph)."""

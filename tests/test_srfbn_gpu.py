@@ -199,3 +199,42 @@ def test_workspace_cap_chunks_the_maps_bit_identically(scale):
         assert prof["im2col"]["launches"] == M // chunk and prof["fc_fuse"]["launches"] == 1
     with pytest.raises(Exception, match="workspace"):
         SRProjectionModule(num_maps=M, upscale_factor=scale, workspace_cap_bytes=1 << 16)(x)
+
+
+@pytest.mark.parametrize("scale", [4, 2])
+def test_refresh_of_the_changed_maps_is_bit_identical_to_a_full_forward(scale):
+    """forward(x, changed_from=k): only the maps x[k:] go through the conv stack again, the per-map images of x[:k]
+    come from the previous forward (the maps are independent until the fc fuse) -- the frame and the per-map images
+    equal a full forward's bit for bit, for every k, repeatedly, and the call refuses to run without a preceding full
+    forward or on a chunked plan."""
+    M, h, w = 8, 19, 27
+    sd = so.init_state_dict(num_maps=M, seed=3, gain=2.3, upscale=scale)
+    g = torch.Generator().manual_seed(11)
+    x = (torch.rand((M, 3, h, w), generator=g) * 255).to(DEV)
+    ref = SRProjectionModule(num_maps=M, upscale_factor=scale)
+    ref.load_state_dict(sd)
+    mod = SRProjectionModule(num_maps=M, upscale_factor=scale)
+    mod.load_state_dict(sd)
+    with pytest.raises(RuntimeError, match="preceding full forward"):
+        mod(x, changed_from=3)
+    for k in (3, M - 1, 1, 3):
+        x2 = x.clone()
+        x2[k:] = (torch.rand((M - k, 3, h, w), generator=g) * 255).to(DEV)
+        want, want_maps = ref(x2), ref.premix(x2)
+        mod(x)                                               # pass 1 on the old stack
+        u8 = torch.zeros((scale * h, scale * w, 3), dtype=torch.uint8, device=DEV)
+        got = mod(x2, out_u8=u8, changed_from=k)             # pass 2: maps k.. changed
+        assert torch.equal(got, want), k
+        ent = next(iter(mod._plans.values()))
+        maps = torch.empty_like(want_maps)
+        from video_super_resolution_b200 import _lib
+        _lib.check(_lib.lib().vsr_srfbn_debug_premix(ent["plan"], maps.data_ptr(), torch.cuda.current_stream().cuda_stream), "premix")
+        assert torch.equal(maps, want_maps), k
+        got2 = mod(x2, changed_from=k)                       # again on top of a refreshed premix buffer: still exact
+        assert torch.equal(got2, want), k
+    capped = SRProjectionModule(num_maps=M, upscale_factor=scale,
+                                workspace_cap_bytes=next(iter(ref._plans.values()))["workspace"].numel() // 2)
+    capped.load_state_dict(sd)
+    capped(x)
+    with pytest.raises(RuntimeError, match="srfbn_prepare_refresh"):
+        capped(x, changed_from=3)

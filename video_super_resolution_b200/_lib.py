@@ -83,6 +83,8 @@ SIGNATURES = {
     "vsr_srfbn_bind": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t]),
     "vsr_srfbn_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "vsr_srfbn_forward_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vsr_srfbn_prepare_refresh": (c_int, [c_void_p, c_int]),
+    "vsr_srfbn_forward_refresh_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "vsr_srfbn_kernel_class_name": (ctypes.c_char_p, [c_int]),
     "vsr_srfbn_profile_enable": (c_int, [c_void_p, c_int]),
     "vsr_srfbn_profile_read": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

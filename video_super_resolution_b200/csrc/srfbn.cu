@@ -903,6 +903,12 @@ struct vsr_srfbn_plan {
   uint8_t* ws;
   std::vector<Layer> layers;
   int conv_out_layer;
+  // a second layer list over the maps [refresh_first, num_maps) only (vsr_srfbn_forward_refresh_u8): same buffers,
+  // fewer maps; built by vsr_srfbn_prepare_refresh
+  std::vector<Layer> refresh_layers;
+  int refresh_first, refresh_conv_out_layer;
+  bool refresh_grouped;
+  bool premix_valid;      // a full forward has filled the per-map images of every map
   std::vector<cudaEvent_t> events;   // profiling: one before every launch + one after the last
   bool profile;
 };
@@ -982,6 +988,10 @@ extern "C" int vsr_srfbn_plan_create(const vsr_srfbn_config* cfg, vsr_srfbn_plan
   pl->dev_w = nullptr;
   pl->ws = nullptr;
   pl->conv_out_layer = -1;
+  pl->refresh_first = -1;
+  pl->refresh_conv_out_layer = -1;
+  pl->refresh_grouped = false;
+  pl->premix_valid = false;
   pl->profile = false;
   pl->chunk_maps = cfg->num_maps;
   pl->ws_cap = 0;
@@ -1080,6 +1090,8 @@ extern "C" int vsr_srfbn_pack_weights(const vsr_srfbn_plan* pl, const vsr_srfbn_
   return VSR_OK;
 }
 
+static int build_layer_list(vsr_srfbn_plan* pl, int M, std::vector<Layer>& layers, int& conv_out_layer, bool& grouped);
+
 extern "C" int vsr_srfbn_bind(vsr_srfbn_plan* pl, const void* dev_weights, void* dev_workspace,
                               size_t workspace_bytes) {
   if (!pl || !dev_weights || !dev_workspace) return VSR_ERR_INVALID_ARG;
@@ -1089,9 +1101,21 @@ extern "C" int vsr_srfbn_bind(vsr_srfbn_plan* pl, const void* dev_weights, void*
   pl->bound = false;
   pl->dev_w = reinterpret_cast<const uint8_t*>(dev_weights);
   pl->ws = reinterpret_cast<uint8_t*>(dev_workspace);
-  pl->layers.clear();
+  pl->refresh_layers.clear();
+  pl->refresh_first = -1;
+  pl->premix_valid = false;
+  int rc = build_layer_list(pl, pl->chunk_maps, pl->layers, pl->conv_out_layer, pl->grouped);
+  if (rc) return rc;
+  pl->bound = true;
+  return VSR_OK;
+}
+
+// The layer list of the stack for M maps at a time (M <= chunk_maps: the buffers are laid out for chunk_maps maps and a
+// list over fewer maps uses their heads).
+static int build_layer_list(vsr_srfbn_plan* pl, int M, std::vector<Layer>& layers, int& conv_out_layer, bool& grouped) {
+  layers.clear();
   const vsr_srfbn_config& c = pl->cfg;
-  const int M = pl->chunk_maps, h = c.h, w = c.w;     // the layers are built for one chunk of maps
+  const int h = c.h, w = c.w;
   const int64_t P = (int64_t)M * h * w;
   uint8_t* ws = pl->ws;
   auto Wp = [&](int id) { return (const void*)(pl->dev_w + pl->we[id].w_off); };
@@ -1099,12 +1123,12 @@ extern "C" int vsr_srfbn_bind(vsr_srfbn_plan* pl, const void* dev_weights, void*
   int rc;
   Layer L;
   int32_t group_epoch = 0;
-  pl->grouped = false;
+  grouped = false;
 #define PUSH(expr)        \
   do {                    \
     rc = (expr);          \
     if (rc) return rc;    \
-    pl->layers.push_back(L); \
+    layers.push_back(L);  \
   } while (0)
 
   {  // conv_in: A0 [P,32] -> C128 [P,128]
@@ -1139,7 +1163,7 @@ extern "C" int vsr_srfbn_bind(vsr_srfbn_plan* pl, const void* dev_weights, void*
                                ws + pl->o_ht, 64, 0, 0, h, w);
           if (rc) return rc;
           L.kclass = KC_PW_HR;
-          pl->layers.push_back(L);
+          layers.push_back(L);
           down_in = ws + pl->o_ht;
         }
         PUSH(build_downconv2(L, down_in, M, h, w, Wp(W_DOWN0 + i), Bp(W_DOWN0 + i), ws + pl->o_lr[i + 1]));
@@ -1159,12 +1183,12 @@ extern "C" int vsr_srfbn_bind(vsr_srfbn_plan* pl, const void* dev_weights, void*
         if (group_enabled() && n_spatial >= 4 * kNumSMs) {
           // one launch: the deconv role publishes hr[i] tile by tile, the fused role takes it from L2
           PUSH(build_group(L, D, F, i, reinterpret_cast<int32_t*>(ws + pl->o_flags), ++group_epoch, n_spatial));
-          pl->grouped = true;
+          grouped = true;
         } else {
           L = D;
-          pl->layers.push_back(L);
+          layers.push_back(L);
           L = F;
-          pl->layers.push_back(L);
+          layers.push_back(L);
         }
         PUSH(build_finalize(L, reinterpret_cast<float*>(ws + pl->o_acc), Bp(W_DOWN0 + i), ws + pl->o_lr[i + 1], P, h, w));
       }
@@ -1180,14 +1204,75 @@ extern "C" int vsr_srfbn_bind(vsr_srfbn_plan* pl, const void* dev_weights, void*
   else PUSH(build_deconv(L, ws + pl->o_hidden, M, h, w, Wp(W_OUT), Bp(W_OUT), ws + pl->o_hb, 1));
   PUSH(build_conv_out(L, ws + pl->o_hb, M, h, w, c.upscale, Wp(W_CONV_OUT), Bp(W_CONV_OUT),
                       reinterpret_cast<float*>(ws + pl->o_premix)));
-  pl->conv_out_layer = (int)pl->layers.size() - 1;
+  conv_out_layer = (int)layers.size() - 1;
 #undef PUSH
-  pl->bound = true;
+  return VSR_OK;
+}
+
+// Prepares vsr_srfbn_forward_refresh_u8 for the maps [first_map, num_maps).
+extern "C" int vsr_srfbn_prepare_refresh(vsr_srfbn_plan* pl, int first_map) {
+  if (!pl) return VSR_ERR_INVALID_ARG;
+  if (!pl->bound) return VSR_ERR_STATE;
+  if (first_map < 1 || first_map >= pl->cfg.num_maps) return VSR_ERR_INVALID_ARG;
+  if (pl->chunk_maps != pl->cfg.num_maps) return VSR_ERR_UNSUPPORTED;     // not with a workspace cap (chunked sweeps)
+  if (pl->refresh_first == first_map) return VSR_OK;
+  pl->refresh_first = -1;
+  const int rc = build_layer_list(pl, pl->cfg.num_maps - first_map, pl->refresh_layers, pl->refresh_conv_out_layer,
+                                  pl->refresh_grouped);
+  if (rc) return rc;
+  pl->refresh_first = first_map;
   return VSR_OK;
 }
 
 extern "C" int vsr_srfbn_forward(vsr_srfbn_plan* pl, const float* x, float* y, vsr_stream_t stream) {
   return vsr_srfbn_forward_u8(pl, x, y, nullptr, stream);
+}
+
+// One sweep of a layer list over the maps [m0, m0 + Mc) of the stack x; the per-map images land in the premix buffer.
+static int sweep_maps(vsr_srfbn_plan* pl, std::vector<Layer>& layers, int conv_out_layer, bool grouped, const float* x,
+                      int m0, int Mc, cudaStream_t st, size_t* ev) {
+  const vsr_srfbn_config& c = pl->cfg;
+  const int64_t P = (int64_t)Mc * c.h * c.w;
+  auto mark = [&]() {
+    if (ev && pl->profile && *ev < pl->events.size()) cudaEventRecord(pl->events[(*ev)++], st);
+  };
+  const float* xc = x + (int64_t)m0 * 3 * c.h * c.w;
+  if (grouped) {
+    cudaError_t e = cudaMemsetAsync(pl->ws + pl->o_flags, 0, pl->flags_bytes, st);
+    if (e != cudaSuccess) return cuda_status(e);
+  }
+  mark();
+  {
+    int64_t blocks = ceil_div64(P, 256);
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    im2col_kernel<<<(int)blocks, 256, 0, st>>>(xc, reinterpret_cast<const float*>(pl->dev_w + pl->misc_off),
+                                               reinterpret_cast<uint4*>(pl->ws + pl->o_a0), Mc, c.h, c.w);
+    int rc = after_launch();
+    if (rc) return rc;
+  }
+  {   // the last layer reads the network input (bilinear skip) and writes these maps of the premix buffer
+    IgemmParams& cp = layers[conv_out_layer].p;
+    cp.skip_src = xc;
+    cp.out = reinterpret_cast<float*>(pl->ws + pl->o_premix) + (int64_t)m0 * 3 * c.upscale * c.upscale * c.h * c.w;
+  }
+  for (const Layer& L : layers) {
+    mark();
+    int rc = launch_layer(L, st);
+    if (rc) return rc;
+  }
+  return VSR_OK;
+}
+
+// the per-pixel fc across the num_maps per-map images (SRProjectionModule.py:146)
+static int fuse_maps(vsr_srfbn_plan* pl, float* y, uint8_t* y_u8, cudaStream_t st) {
+  const vsr_srfbn_config& c = pl->cfg;
+  const int64_t n = (int64_t)3 * c.upscale * c.upscale * c.h * c.w;
+  int64_t blocks = ceil_div64(ceil_div64(n, 4), 256);
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  cudaError_t e = launch_pdl(fc_fuse_kernel, (int)blocks, 256, 0, st, reinterpret_cast<const float*>(pl->ws + pl->o_premix),
+                             reinterpret_cast<const float*>(pl->dev_w + pl->fc_off), y, y_u8, c.num_maps, n);
+  if (e != cudaSuccess) return cuda_status(e);
+  return after_launch();
 }
 
 extern "C" int vsr_srfbn_forward_u8(vsr_srfbn_plan* pl, const float* x, float* y, uint8_t* y_u8, vsr_stream_t stream) {
@@ -1196,50 +1281,33 @@ extern "C" int vsr_srfbn_forward_u8(vsr_srfbn_plan* pl, const float* x, float* y
   cudaStream_t st = as_stream(stream);
   const vsr_srfbn_config& c = pl->cfg;
   const int Mc = pl->chunk_maps;
-  const int64_t P = (int64_t)Mc * c.h * c.w;
   size_t ev = 0;
-  auto mark = [&]() {
-    if (pl->profile && ev < pl->events.size()) cudaEventRecord(pl->events[ev++], st);
-  };
   for (int m0 = 0; m0 < c.num_maps; m0 += Mc) {        // one sweep over the layer list per chunk of maps
-    const float* xc = x + (int64_t)m0 * 3 * c.h * c.w;
-    if (pl->grouped) {
-      cudaError_t e = cudaMemsetAsync(pl->ws + pl->o_flags, 0, pl->flags_bytes, st);
-      if (e != cudaSuccess) return cuda_status(e);
-    }
-    mark();
-    {
-      int64_t blocks = ceil_div64(P, 256);
-      if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-      im2col_kernel<<<(int)blocks, 256, 0, st>>>(xc, reinterpret_cast<const float*>(pl->dev_w + pl->misc_off),
-                                                 reinterpret_cast<uint4*>(pl->ws + pl->o_a0), Mc, c.h, c.w);
-      int rc = after_launch();
-      if (rc) return rc;
-    }
-    {   // the last layer reads the network input (bilinear skip) and writes this chunk's maps of the premix buffer
-      IgemmParams& cp = pl->layers[pl->conv_out_layer].p;
-      cp.skip_src = xc;
-      cp.out = reinterpret_cast<float*>(pl->ws + pl->o_premix) + (int64_t)m0 * 3 * c.upscale * c.upscale * c.h * c.w;
-    }
-    for (const Layer& L : pl->layers) {
-      mark();
-      int rc = launch_layer(L, st);
-      if (rc) return rc;
-    }
-  }
-  mark();
-  {
-    const int64_t n = (int64_t)3 * c.upscale * c.upscale * c.h * c.w;
-    int64_t blocks = ceil_div64(ceil_div64(n, 4), 256);
-    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-    cudaError_t e = launch_pdl(fc_fuse_kernel, (int)blocks, 256, 0, st, reinterpret_cast<const float*>(pl->ws + pl->o_premix),
-                               reinterpret_cast<const float*>(pl->dev_w + pl->fc_off), y, y_u8, c.num_maps, n);
-    if (e != cudaSuccess) return cuda_status(e);
-    int rc = after_launch();
+    int rc = sweep_maps(pl, pl->layers, pl->conv_out_layer, pl->grouped, x, m0, Mc, st, &ev);
     if (rc) return rc;
   }
-  mark();
+  if (pl->profile && ev < pl->events.size()) cudaEventRecord(pl->events[ev++], st);
+  int rc = fuse_maps(pl, y, y_u8, st);
+  if (rc) return rc;
+  if (pl->profile && ev < pl->events.size()) cudaEventRecord(pl->events[ev++], st);
+  pl->premix_valid = true;
   return VSR_OK;
+}
+
+// A second call on a stack of which only the maps [first_map, num_maps) changed since the last forward of this plan
+// (the fuse pass of network/video_super_resolution.py:62: `data`, the frames, goes in unchanged): the maps are
+// independent until the per-pixel fc, so the per-map images of the unchanged maps are still in the workspace and only
+// the changed ones are swept again -- bit-identical to a full forward on the same stack.  Needs
+// vsr_srfbn_prepare_refresh(plan, first_map) and a preceding vsr_srfbn_forward[_u8] on the same stream.
+extern "C" int vsr_srfbn_forward_refresh_u8(vsr_srfbn_plan* pl, const float* x, float* y, uint8_t* y_u8, int first_map,
+                                            vsr_stream_t stream) {
+  if (!pl || !x || (!y && !y_u8)) return VSR_ERR_INVALID_ARG;
+  if (!pl->bound || !pl->premix_valid || pl->refresh_first != first_map || first_map < 1) return VSR_ERR_STATE;
+  cudaStream_t st = as_stream(stream);
+  int rc = sweep_maps(pl, pl->refresh_layers, pl->refresh_conv_out_layer, pl->refresh_grouped, x, first_map,
+                      pl->cfg.num_maps - first_map, st, nullptr);
+  if (rc) return rc;
+  return fuse_maps(pl, y, y_u8, st);
 }
 
 extern "C" const char* vsr_srfbn_kernel_class_name(int k) {

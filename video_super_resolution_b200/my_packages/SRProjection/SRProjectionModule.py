@@ -152,12 +152,18 @@ class SRProjectionModule(nn.Module):
             _lib.check(L.vsr_srfbn_bind(ent["plan"], ent["weights"].data_ptr(), ent["workspace"].data_ptr(),
                                         ent["workspace"].numel()), "srfbn_bind")
             ent["version"] = ver
+            ent["have_premix"] = False          # bind drops the second layer list and the per-map images
+            ent["refresh_first"] = None
         return ent
 
-    def forward(self, x, out_u8=None, want_f32=True):
+    def forward(self, x, out_u8=None, want_f32=True, changed_from=None):
         """out_u8: optional (s*h, s*w, 3) u8 CUDA tensor that additionally receives the frame as clamp(y,0,255) rounded
         half to even (the loader's pixel format, utils/video_utils.py:23), written by the fc-fuse kernel itself;
-        want_f32=False skips the fp32 frame (then the u8 frame is the only output and is what is returned)."""
+        want_f32=False skips the fp32 frame (then the u8 frame is the only output and is what is returned).
+        changed_from=k: the caller states that, since the previous forward of this module on a stack of this shape, only
+        the maps x[k:] changed (the fuse pass, network/video_super_resolution.py:62, feeds the frames unchanged): the
+        maps are independent until the per-pixel fc, so only x[k:] go through the conv stack again and the per-map images
+        of x[:k] are reused -- bit-identical to a full forward."""
         if not x.is_cuda:
             raise RuntimeError("SRProjectionModule: CUDA tensors only (no CPU fallback)")
         if x.dim() != 4 or x.shape[1] != 3 or x.shape[0] != self.num_maps:
@@ -173,10 +179,22 @@ class SRProjectionModule(nn.Module):
         if out_u8 is None and not want_f32:
             raise ValueError("SRProjectionModule: nothing to compute")
         y = torch.empty((1, 3, s * h, s * w), dtype=torch.float32, device=x.device) if want_f32 else None
+        L = _lib.lib()
         with torch.cuda.device(x.device):
-            _lib.check(_lib.lib().vsr_srfbn_forward_u8(ent["plan"], x.data_ptr(), y.data_ptr() if y is not None else None,
-                                                       out_u8.data_ptr() if out_u8 is not None else None,
-                                                       torch.cuda.current_stream().cuda_stream), "srfbn_forward")
+            yp = y.data_ptr() if y is not None else None
+            up = out_u8.data_ptr() if out_u8 is not None else None
+            st = torch.cuda.current_stream().cuda_stream
+            if changed_from is None or changed_from <= 0:
+                _lib.check(L.vsr_srfbn_forward_u8(ent["plan"], x.data_ptr(), yp, up, st), "srfbn_forward")
+                ent["have_premix"] = True
+            else:
+                if not ent.get("have_premix"):
+                    raise RuntimeError("SRProjectionModule: changed_from needs a preceding full forward on this shape")
+                if ent.get("refresh_first") != int(changed_from):
+                    _lib.check(L.vsr_srfbn_prepare_refresh(ent["plan"], int(changed_from)), "srfbn_prepare_refresh")
+                    ent["refresh_first"] = int(changed_from)
+                _lib.check(L.vsr_srfbn_forward_refresh_u8(ent["plan"], x.data_ptr(), yp, up, int(changed_from), st),
+                           "srfbn_forward_refresh")
         return y if want_f32 else out_u8
 
     def premix(self, x):

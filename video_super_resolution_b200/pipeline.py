@@ -74,12 +74,22 @@ class WarpFusePipeline:
     so warped[t](p) = frame[t](p + G[t](p)) is aligned with the centre frame, and the residual map of neighbour t is
     |frame[c] - warped[t]|.  The VOS mask is taken to live in frame c-1 (the frame the segmentation was propagated
     from) and is label-warped with G[c-1].  For the reference's T = 3 no chain is needed.
-    max_disp: a promised bound on the components of `flows` (px); selects the shared-memory projection path."""
+    max_disp: a promised bound on the components of `flows` (px); selects the shared-memory projection path.
+    reuse: what the fuse pass (pass 2) takes over from pass 1.  The M maps go through the conv stack independently
+    until the per-pixel fc, so a map that enters both passes unchanged need not be convolved twice (bit-identical):
+        None         every map again (the default: the reference's two full SRProjectionModule calls)
+        "frames"     the T frame maps, which network/video_super_resolution.py:62 feeds unchanged (`data`), are reused;
+                     the 2(T-1) flow / depth maps, which the reference re-estimates for pass 2, and the estimate are not
+        "unchanged"  every map this pipeline leaves unchanged: all but the estimate slot (flow and depth are inputs
+                     here, not re-estimated)."""
 
     def __init__(self, T: int, h: int, w: int, sr: SRProjectionModule | None = None, scale: int = 4,
-                 device="cuda:0", run_fusion: bool = True, max_disp: float | None = None):
+                 device="cuda:0", run_fusion: bool = True, max_disp: float | None = None, reuse: str | None = None):
         if T < 2:
             raise ValueError("window must hold at least 2 frames")
+        if reuse not in (None, "frames", "unchanged"):
+            raise ValueError("reuse must be None, 'frames' or 'unchanged'")
+        self.reuse = reuse
         self.T, self.h, self.w, self.scale = T, h, w, scale
         self.M = 3 * T - 1
         self.centre = T // 2
@@ -132,7 +142,8 @@ class WarpFusePipeline:
             return self.stack
         out1 = self.sr(self.stack)                                             # pass 1
         ops.estimate_slot(out1[0], r["mask_warped"], self.stack[self.M - 1], self.scale)
-        return self.sr(self.stack, out_u8=out_u8, want_f32=want_f32)           # pass 2 (fuse)
+        changed_from = {None: None, "frames": self.T, "unchanged": self.M - 1}[self.reuse]
+        return self.sr(self.stack, out_u8=out_u8, want_f32=want_f32, changed_from=changed_from)   # pass 2 (fuse)
 
 
 class GraphedStep:
