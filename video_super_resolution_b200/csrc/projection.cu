@@ -347,10 +347,37 @@ projection_pipeline_kernel(const ProjArgs a) {
   }
 }
 
+// The stage kernels of the general path are short (5-15 us) and strictly dependent, so their launch gaps count: they
+// are launched with programmatic stream serialization -- the next stage's CTAs may become resident while the last CTAs
+// of this one drain -- and every stage starts by letting its successor launch and then waiting for its predecessor to
+// have completed and flushed (griddepcontrol.wait).  (The layers of the conv stack, 0.1-2 ms each, measured no gain
+// from this: api.cu.)
+__device__ __forceinline__ void chain_enter() {
+  griddep_launch_dependents();
+  griddep_wait();
+}
+template <typename... KArgs, typename... Args>
+inline int launch_chained(void (*kernel)(KArgs...), int grid, int block, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3((unsigned)block, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+  if (e != cudaSuccess) return cuda_status(e);
+  return after_launch();
+}
+
 // The same stages as stand-alone kernels, each with its own register budget / occupancy (the merged kernel above runs
 // every role at 24 warps per SM; alone the splat keeps 64 in flight): the general path (run_general).
 __global__ void __launch_bounds__(kThreads)
 stage_splat_kernel(const float* __restrict__ flow, const float* __restrict__ inv_depth, float4* __restrict__ acc, int h, int w) {
+  chain_enter();
   role_splat(flow, inv_depth, acc, h, w, (blockIdx.x * kThreads + threadIdx.x) >> 5, (gridDim.x * kThreads) >> 5, threadIdx.x & 31);
 }
 __global__ void __launch_bounds__(kThreads, 4)
@@ -358,6 +385,7 @@ stage_normalise_kernel(const float4* __restrict__ acc, float* __restrict__ proj,
                        int32_t* __restrict__ count, uint8_t* __restrict__ hole, uint32_t* __restrict__ rowmask,
                        uint32_t* __restrict__ colmask, int* __restrict__ n_holewords, uint32_t* __restrict__ holelist, int h,
                        int w) {
+  chain_enter();
   role_normalise<false, false>(acc, proj, wsum, count, hole, rowmask, colmask, n_holewords, holelist, h, w,
                                (blockIdx.x * kThreads + threadIdx.x) >> 5, (gridDim.x * kThreads) >> 5, threadIdx.x & 31);
 }
@@ -365,6 +393,7 @@ stage_normalise_kernel(const float4* __restrict__ acc, float* __restrict__ proj,
 __global__ void __launch_bounds__(kThreads)
 stage_fill_kernel(const uint32_t* rowmask, const uint32_t* colmask, const int* n_holewords, const uint32_t* holelist,
                   float* proj, float4* zero_acc, int h, int w) {
+  chain_enter();
   // the cell array is free once the normalise stage is through: cleared here for the next image (one launch and its gap
   // less than a memset per image)
   if (zero_acc) role_zero(zero_acc, (int64_t)h * w, (int64_t)blockIdx.x * kThreads + threadIdx.x, (int64_t)gridDim.x * kThreads);
@@ -939,17 +968,17 @@ int run_general(const ProjArgs& a, cudaStream_t st) {
   const int fill_blocks = min(ceil_div(h * ceil_div(w, 32), kThreads / 32), kNumSMs * 16);   // warps walk the hole list
   if ((e = cudaMemsetAsync(a.acc, 0, (size_t)P * sizeof(float4), st)) != cudaSuccess) return cuda_status(e);
   for (int b = 0; b < a.B; ++b) {
-    stage_splat_kernel<<<splat_blocks, kThreads, 0, st>>>(a.flow + b * P * 2, a.inv_depth ? a.inv_depth + b * P : nullptr, a.acc, h, w);
-    int rc = after_launch();
+    int rc = launch_chained(stage_splat_kernel, splat_blocks, kThreads, st, a.flow + b * P * 2,
+                            a.inv_depth ? a.inv_depth + b * P : nullptr, a.acc, h, w);
     if (rc) return rc;
-    stage_normalise_kernel<<<norm_blocks, kThreads, 0, st>>>(a.acc, a.proj + b * P * 2, a.wsum ? a.wsum + b * P : nullptr,
-                                                            a.count + b * P, a.hole + b * P, a.rowmask + b * rw,
-                                                            a.colmask + b * cw, a.flags + 1 + b, a.holelist + b * rw, h, w);
-    if ((rc = after_launch())) return rc;
-    stage_fill_kernel<<<fill_blocks, kThreads, 0, st>>>(a.rowmask + b * rw, a.colmask + b * cw, a.flags + 1 + b,
-                                                       a.holelist + b * rw, a.proj + b * P * 2,
-                                                       b + 1 < a.B ? a.acc : nullptr, h, w);
-    if ((rc = after_launch())) return rc;
+    rc = launch_chained(stage_normalise_kernel, norm_blocks, kThreads, st, (const float4*)a.acc, a.proj + b * P * 2,
+                        a.wsum ? a.wsum + b * P : nullptr, a.count + b * P, a.hole + b * P, a.rowmask + b * rw,
+                        a.colmask + b * cw, a.flags + 1 + b, a.holelist + b * rw, h, w);
+    if (rc) return rc;
+    rc = launch_chained(stage_fill_kernel, fill_blocks, kThreads, st, (const uint32_t*)(a.rowmask + b * rw),
+                        (const uint32_t*)(a.colmask + b * cw), (const int*)(a.flags + 1 + b),
+                        (const uint32_t*)(a.holelist + b * rw), a.proj + b * P * 2, b + 1 < a.B ? a.acc : (float4*)nullptr, h, w);
+    if (rc) return rc;
   }
   return VSR_OK;
 }
