@@ -161,7 +161,7 @@ __device__ __forceinline__ void role_splat(const float* __restrict__ flow, const
 // loaded once; 4 rows of loads are in flight at a time.  The ballot of "has hits" is the row word; each lane collects
 // its own column bits and writes its 16-bit half of the column word -- no shared memory, no block barrier.  Hole
 // pixels get (0,0) here; the fill overwrites them.
-constexpr int kStrip = 16, kBatch = 4;
+constexpr int kStrip = 8, kBatch = 4;      // 8 rows per warp task: twice the warps of 16-row strips for the same loads in flight
 
 template <bool CG, bool LOOP>
 __device__ __forceinline__ void role_normalise(const float4* __restrict__ acc, float* __restrict__ proj,
@@ -172,7 +172,7 @@ __device__ __forceinline__ void role_normalise(const float4* __restrict__ acc, f
   // holelist != nullptr: *has_holes counts the row words with holes and holelist names them (the fill then visits only
   // those); nullptr: *has_holes is a flag and the fill scans every word
   const int tiles_x = ceil_div(w, 32);
-  const int n_strips = 2 * ceil_div(h, 32);          // both halves of every column word get written
+  const int n_strips = (32 / kStrip) * ceil_div(h, 32);   // every byte of every column word gets written
   const int n_tasks = tiles_x * n_strips;
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   // LOOP = false: the stand-alone launch gives every warp exactly one strip (the loop's live range costs the 64-register
@@ -231,7 +231,7 @@ __device__ __forceinline__ void role_normalise(const float4* __restrict__ acc, f
         holerows |= (uint32_t)(y < h && (inx_mask & ~m) != 0) << (r0 + r);
       }
     }
-    if (in_x) reinterpret_cast<uint16_t*>(colmask)[((strip >> 1) * w + x) * 2 + (strip & 1)] = (uint16_t)colbits;
+    if (in_x) reinterpret_cast<uint8_t*>(colmask)[((strip >> 2) * w + x) * 4 + (strip & 3)] = (uint8_t)colbits;
     if (holerows) {
       if (holelist) {
         const int nh = __popc(holerows);
@@ -964,7 +964,7 @@ int run_general(const ProjArgs& a, cudaStream_t st) {
   if (e != cudaSuccess) return cuda_status(e);
   const int n_tasks = ceil_div(w, 32) * ceil_div(h, kRows);
   const int splat_blocks = ceil_div(n_tasks, kThreads / 32);
-  const int norm_blocks = ceil_div(ceil_div(w, 32) * 2 * ceil_div(h, 32), kThreads / 32);
+  const int norm_blocks = ceil_div(ceil_div(w, 32) * (32 / kStrip) * ceil_div(h, 32), kThreads / 32);
   const int fill_blocks = min(ceil_div(h * ceil_div(w, 32), kThreads / 32), kNumSMs * 16);   // warps walk the hole list
   if ((e = cudaMemsetAsync(a.acc, 0, (size_t)P * sizeof(float4), st)) != cudaSuccess) return cuda_status(e);
   for (int b = 0; b < a.B; ++b) {
