@@ -272,3 +272,27 @@ def test_launches_are_counted():
     x = torch.zeros((1, 3, 8, 8), device=DEV)
     ops.channelnorm(x)
     assert _lib.launch_count() == 1
+
+
+def test_projection_random_shapes_and_fields_against_oracle():
+    """Seeded sweep over shapes (around the tile / block / strip sizes, odd and even widths), batch sizes, weighted and
+    unweighted, smooth / i.i.d. / mixed fields, kept and broken promises -- every path must reproduce the oracle
+    (count / hole bit for bit), starting from a poisoned workspace."""
+    rng = np.random.default_rng(1234)
+    for it in range(24):
+        B = int(rng.integers(1, 4))
+        h = int(rng.choice([1, 7, 16, 31, 47, 79, 80, 81, 97, 130, 161]))
+        w = int(rng.choice([2, 15, 16, 34, 126, 128, 130, 160, 257, 300]))
+        kind = it % 4
+        mag = float(rng.choice([0.5, 3.0, 8.0]))
+        if kind == 0:
+            flow = synthetic.smooth_flow(B, h, w, mag, seed=it)
+        elif kind == 1:
+            flow = synthetic.random_flow(B, h, w, mag, seed=it)
+        elif kind == 2:       # half-integer steps: many exact cell-border and image-border hits, many collisions
+            flow = torch.from_numpy(rng.integers(-16, 17, size=(B, h, w, 2)).astype(np.float32) * 0.5)
+        else:                 # smooth field with a few far movers: the promise of 8 px is broken
+            flow = synthetic.smooth_flow(B, h, w, 6.0, seed=it)
+            flow[:, h // 2, :: max(w // 5, 1), 0] = 23.0
+        inv = synthetic.inv_depth(B, h, w, seed=100 + it) if it % 3 else None
+        _check_projection(flow, inv, bounds=(8.0, None))
