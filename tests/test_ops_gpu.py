@@ -227,7 +227,7 @@ def test_projection_degenerate_shapes_and_border_hits(shape):
 
 def test_projection_full_size_properties():
     # C3 size (1080p): size-independent properties instead of the slow CPU oracle
-    B, h, w = 1, 1080, 1920
+    B, h, w = 2, 1080, 1920            # 420 tiles: the tile path (a single image's 210 tiles take the general path)
     flow = synthetic.smooth_flow(B, h, w, 8.0, seed=0).to(DEV)
     inv = synthetic.inv_depth(B, h, w, seed=1).to(DEV)
     proj, wsum, count, hole = ops.project_flow(flow, inv, 8.0)
