@@ -66,7 +66,6 @@ struct ProjArgs {
   int* flags;              // [0] promise broken (bounded path), [1 + b] image b has holes, [1 + B] length of holelist
   uint32_t* holelist;      // bounded path: the row words (b * h * ceil(w/32) + word) that contain holes
   int B, h, w;
-  int bound;               // bounded path: ceil(max_disp)
   int gate;                // general path: 1 = run only if flags[0] != 0 (fallback of the bounded path)
 };
 
@@ -156,11 +155,11 @@ __device__ __forceinline__ void role_splat(const float* __restrict__ flow, const
 }
 
 // 2x2 box sum of the cells + normalise + hole mask, and the occupancy bitmaps the fill uses.  One warp task = one
-// 32-wide, 16-tall strip: lane = column, the warp walks the rows.  The cell above is the previous row's own cell (a
+// 32-wide, kStrip-tall strip: lane = column, the warp walks the rows.  The cell above is the previous row's own cell (a
 // register), the cells to the left come from the neighbouring lane by shuffle (lane 0 loads them), so every cell is
 // loaded once; 4 rows of loads are in flight at a time.  The ballot of "has hits" is the row word; each lane collects
-// its own column bits and writes its 16-bit half of the column word -- no shared memory, no block barrier.  Hole
-// pixels get (0,0) here; the fill overwrites them.
+// its own column bits and writes its byte of the column word -- no shared memory, no block barrier.  Hole pixels
+// get (0,0) here; the fill overwrites them.  The row words with holes go on a list for the fill.
 constexpr int kStrip = 8, kBatch = 4;      // 8 rows per warp task: twice the warps of 16-row strips for the same loads in flight
 
 template <bool CG, bool LOOP>
@@ -739,8 +738,6 @@ projection_tiled_kernel(const ProjArgs a) {
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const TilePos t = tile_pos(tile, tiles_x, tiles_xy);
     const int tx0 = t.tx0, ty0 = t.ty0;
-    const float2* flow = flow_all + (int64_t)t.tb * P;
-    const float* depth = a.inv_depth ? a.inv_depth + (int64_t)t.tb * P : nullptr;
     if (prev_tile >= 0) flush_colm(prev_tile);
     prev_tile = tile;
     const int ye = ty0 + kTH - 1 + kBD;          // the extra source row (warp kAccWarps), loaded a tile ahead
@@ -1020,7 +1017,6 @@ extern "C" int vsr_flow_projection_forward_bounded(const float* flow, const floa
   a.B = B;
   a.h = h;
   a.w = w;
-  a.bound = 0;
   a.gate = 0;
   const bool bounded = max_disp >= 0.0f && max_disp <= (float)kMaxBound && w % 2 == 0 &&
                        (int64_t)B * h * ceil_div(w, 32) < ((int64_t)1 << 31);   // NaN / negative / large, or
@@ -1033,7 +1029,6 @@ extern "C" int vsr_flow_projection_forward_bounded(const float* flow, const floa
     if (n_tiles > kNumSMs && n_tiles < kNumSMs * 7 / 4) return run_general(a, st);
   }
 
-  a.bound = kBD;
   static PerDeviceOnce once;
   int dev;
   if (once.needed(&dev)) {
