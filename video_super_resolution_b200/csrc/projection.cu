@@ -262,38 +262,58 @@ __device__ __forceinline__ void fill_word(const uint32_t* rowmask_, const uint32
   const uint32_t hits = rowmask[wd];
   if (x >= w || ((hits >> lane) & 1u)) return;
   const int p = y * w + x;
-  float sx = 0.f, sy = 0.f;
-  int found = 0;
-  auto take = [&](int yy, int xx) {
-    const float2 q = CG ? __ldcg(pin + yy * w + xx) : pin[yy * w + xx];   // the neighbour's normalised value, as written by the normalise pass
-    sx += q.x;
-    sy += q.y;
-    ++found;
-  };
+  // the four searches first (bitmap words only), then the four neighbour values in flight together, summed in the
+  // order left, right, up, down
+  int nx[4], ny[4];
+  bool has[4] = {false, false, false, false};
   {  // left
     int seg = x >> 5;
     uint32_t word = hits & ((1u << (x & 31)) - 1u);
     while (word == 0 && seg > 0) word = rowmask[y * wpr + --seg];
-    if (word) take(y, seg * 32 + 31 - __clz(word));
+    has[0] = word != 0;
+    nx[0] = seg * 32 + 31 - __clz(word);
+    ny[0] = y;
   }
   {  // right
     int seg = x >> 5;
     uint32_t word = hits & ~((2u << (x & 31)) - 1u);
     while (word == 0 && seg + 1 < wpr) word = rowmask[y * wpr + ++seg];
-    if (word) take(y, seg * 32 + __ffs(word) - 1);
+    has[1] = word != 0;
+    nx[1] = seg * 32 + __ffs(word) - 1;
+    ny[1] = y;
   }
+  const uint32_t cword = colmask[(y >> 5) * w + x];
   {  // up
     int sb = y >> 5;
-    uint32_t word = colmask[sb * w + x] & ((1u << (y & 31)) - 1u);
+    uint32_t word = cword & ((1u << (y & 31)) - 1u);
     while (word == 0 && sb > 0) word = colmask[--sb * w + x];
-    if (word) take(sb * 32 + 31 - __clz(word), x);
+    has[2] = word != 0;
+    nx[2] = x;
+    ny[2] = sb * 32 + 31 - __clz(word);
   }
   {  // down
     int sb = y >> 5;
-    uint32_t word = colmask[sb * w + x] & ~((2u << (y & 31)) - 1u);
+    uint32_t word = cword & ~((2u << (y & 31)) - 1u);
     while (word == 0 && sb + 1 < hpr) word = colmask[++sb * w + x];
-    if (word) take(sb * 32 + __ffs(word) - 1, x);
+    has[3] = word != 0;
+    nx[3] = x;
+    ny[3] = sb * 32 + __ffs(word) - 1;
   }
+  float2 q[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {     // the neighbours' normalised values, as written by the normalise pass
+    q[k] = make_float2(0.f, 0.f);
+    if (has[k]) q[k] = CG ? __ldcg(pin + ny[k] * w + nx[k]) : pin[ny[k] * w + nx[k]];
+  }
+  float sx = 0.f, sy = 0.f;
+  int found = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (has[k]) {
+      sx += q[k].x;
+      sy += q[k].y;
+      ++found;
+    }
   if (found > 0) reinterpret_cast<float2*>(proj)[p] = make_float2(__fdiv_rn(sx, (float)found), __fdiv_rn(sy, (float)found));
 }
 
