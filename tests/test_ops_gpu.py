@@ -296,3 +296,23 @@ def test_projection_random_shapes_and_fields_against_oracle():
             flow[:, h // 2, :: max(w // 5, 1), 0] = 23.0
         inv = synthetic.inv_depth(B, h, w, seed=100 + it) if it % 3 else None
         _check_projection(flow, inv, bounds=(8.0, None))
+
+
+def test_projection_tile_path_needs_aligned_pixel_pairs():
+    """The tile path loads two pixels at a time (16-byte flow, 8-byte depth loads): a flow that starts 8 bytes into a
+    16-byte line or a depth map that starts 4 bytes into an 8-byte word takes the general path -- same results."""
+    B, h, w = 2, 90, 140
+    flow = synthetic.smooth_flow(B, h, w, 6.0, seed=3)
+    inv = synthetic.inv_depth(B, h, w, seed=4)
+    want = orc.flow_projection(flow.numpy(), inv.numpy())
+    fbuf = torch.empty(flow.numel() + 2, device=DEV)
+    dbuf = torch.empty(inv.numel() + 1, device=DEV)
+    f_off = fbuf[2:].view(B, h, w, 2)
+    d_off = dbuf[1:].view(B, h, w)
+    f_off.copy_(flow)
+    d_off.copy_(inv)
+    assert f_off.data_ptr() % 16 == 8 and d_off.data_ptr() % 8 == 4
+    for fl, dp in ((f_off, inv.to(DEV)), (flow.to(DEV), d_off), (f_off, d_off)):
+        proj, wsum, count, hole = ops.project_flow(fl, dp, 8.0)
+        assert np.array_equal(_np(count), want[2]) and np.array_equal(_np(hole), want[3])
+        assert np.abs(_np(proj) - want[0]).max() <= TOL and np.abs(_np(wsum) - want[1]).max() <= TOL * max(1.0, float(want[1].max()))

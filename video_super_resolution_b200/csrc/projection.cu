@@ -1039,8 +1039,10 @@ extern "C" int vsr_flow_projection_forward_bounded(const float* flow, const floa
   a.w = w;
   a.gate = 0;
   const bool bounded = max_disp >= 0.0f && max_disp <= (float)kMaxBound && w % 2 == 0 &&
+                       reinterpret_cast<uintptr_t>(flow) % 16 == 0 && reinterpret_cast<uintptr_t>(inv_depth) % 8 == 0 &&
                        (int64_t)B * h * ceil_div(w, 32) < ((int64_t)1 << 31);   // NaN / negative / large, or
-                                                                                       // unaligned pixel pairs: general path
+                                                                                       // unaligned pixel pairs (the tile path
+                                                                                       // loads two pixels at a time): general path
   if (!bounded) return run_general(a, st);
   {
     // one tile per CTA and pass: between one and 1.75 waves of tiles (a single 1080p image: 210 tiles on 148 SMs) the
