@@ -192,9 +192,13 @@ warp_nhwc3_kernel(const float* __restrict__ src, const float* __restrict__ flow,
   // skip >= 0 (window mode): batch item b samples image b of `src` when b < skip, else image b+1 -- the
   // neighbours of a frame window with the centre frame left out, no gathered copy of the frames needed;
   // ref_shared: every batch item is compared with the SAME reference image (the centre frame).
-  __shared__ __align__(16) float stage[kThreads * 3];
+  // two staging buffers, used alternately: one barrier per iteration (the barrier of iteration k+1 separates the
+  // reads of buffer k & 1 from its next writes in iteration k+2)
+  __shared__ __align__(16) float stage2[2][kThreads * 3];
+  int buf = 0;
   const int64_t HW = (int64_t)H * W;
-  for (int64_t base = (int64_t)blockIdx.x * kThreads; base < n_pix; base += (int64_t)gridDim.x * kThreads) {
+  for (int64_t base = (int64_t)blockIdx.x * kThreads; base < n_pix; base += (int64_t)gridDim.x * kThreads, buf ^= 1) {
+    float* stage = stage2[buf];
     int64_t i = base + threadIdx.x;
     float v0 = 0.f, v1 = 0.f, v2 = 0.f;
     if (i < n_pix) {
@@ -245,7 +249,6 @@ warp_nhwc3_kernel(const float* __restrict__ src, const float* __restrict__ flow,
     } else {
       for (int k = threadIdx.x; k < n_here; k += kThreads) out[k] = stage[k];
     }
-    __syncthreads();
   }
 }
 
