@@ -1,4 +1,4 @@
-"""Per-launch device times of one conv-stack forward at the C2 shape, and plain memory-bandwidth
+"""Per-launch device times of one conv-stack forward at the C2 shape (--c4: the C4 shape), and plain memory-bandwidth
 reference points (write-only / read-only / copy) on the same box.
     gpurun -- 'python tools/layer_times.py > gpurun_out/layer_times.log'"""
 import ctypes
@@ -38,9 +38,11 @@ def bw():
 def main():
     if "--no-bw" not in sys.argv:
         bw()
-    M, h, w = 20, 270, 480
+    M, h, w, scale = 20, 270, 480, 4
+    if "--c4" in sys.argv:        # config C4: 2x, 1080p -> 4K, 5-frame window
+        M, h, w, scale = 14, 1080, 1920, 2
     torch.manual_seed(0)
-    sr = SRProjectionModule(num_maps=M)
+    sr = SRProjectionModule(num_maps=M, upscale_factor=scale)
     x = (torch.rand((M, 3, h, w)) * 255).cuda()
     for _ in range(2):
         sr(x)

@@ -37,6 +37,7 @@ enum EpiMode : int {
   EPI_DECONV = 1,      // BN=256 (one half of the 16 sub-positions): HR block layout or plain NHWC HR
   EPI_CONV_OUT = 2,    // BN=32 (27 real = 9 taps x 3): output-shift 3x3 conv, fp32 planar output + skip + mean shifts
   EPI_DECONV2 = 3,     // BN=128 (4 sub-positions x 32): x2 transposed conv k6 s2 p2, plain NHWC HR output
+  EPI_DOWN2 = 4,       // BN=96 (3 column taps x 32): x2 strided conv k6 s2 p2 with the column taps in output-shift form
 };
 
 struct Chunk {
@@ -208,6 +209,30 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "}\n" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// same, accumulate flag as an immediate predicate (unrolled issue loops)
+template <bool kAccumulate>
+__device__ __forceinline__ void umma_bf16_imm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "n"(kAccumulate ? 1 : 0)
+      : "memory");
+}
+// one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -421,9 +446,9 @@ __device__ __forceinline__ void igemm_body(const IgemmParams& p, const int cta, 
   constexpr int kThreadsHere = (MODE == EPI_DECONV || MODE == EPI_DECONV2) ? kDeconvThreads : kIgemmThreads;
   constexpr int kEpiThreads = kThreadsHere - 64;
   static_assert(CK == 32 || CK == 64, "K chunk is 32 (64B swizzle) or 64 (128B swizzle) BF16");
-  static_assert(BN == 16 || BN == 32 || BN == 128 || BN == 256, "supported N tiles");
+  static_assert(BN == 16 || BN == 32 || BN == 96 || BN == 128 || BN == 256, "supported N tiles");
   constexpr int kSwz = CK * 2;
-  constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator stages
+  constexpr int kTmemCols = (2 * BN < 32) ? 32 : (BN == 96 ? 256 : 2 * BN);   // two accumulator stages (a power of two)
   constexpr int kABytes = a_stage_bytes<CK>();
   constexpr int kBBytes = b_chunk_bytes<CK, BN>();
 
@@ -500,6 +525,50 @@ __device__ __forceinline__ void igemm_body(const IgemmParams& p, const int cta, 
           if (++s == p.num_stages) { s = 0; phase ^= 1; }
         }
       }
+    }
+  } else if (warp == 1 && MODE == EPI_DOWN2) {
+    // ===================== MMA issuer, static schedule =====================
+    // Two stages per tile (row parity 0 / 1), three row taps per stage, four K steps per tap: the 24 MMAs of N = 96
+    // take 48 cycles each, so the generic issue loop below (~10 instructions and ~125 cycles per MMA on one thread:
+    // chunk table look-ups, 64-bit descriptor arithmetic, ELECT + R2UR per operand) was the floor of this layer at
+    // 0.21 tensor-pipe activity.  Here the whole warp walks the loop (warp-uniform values live in uniform registers),
+    // every offset is an immediate, and one elected lane issues.
+    constexpr uint32_t idesc = make_idesc(BN);
+    constexpr uint32_t kRowTap = 16 * 128;          // a tap one tile row down: 16 pixel pairs of 128 bytes further in
+    mbar_wait(b_full, 0);
+    tc_fence_after();
+    int s = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t acc_phase = 0;
+    const uint64_t dA = make_smem_desc<kSwz>(smem_u32(smem_a));
+    const uint64_t dB = make_smem_desc<kSwz>(smem_u32(smem_b));
+    for (int tile = cta; tile < total_tiles; tile += ncta) {
+      mbar_wait(&tmem_empty[as], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+#pragma unroll
+      for (int py = 0; py < 2; ++py) {
+        mbar_wait(&full_bar[s], phase);
+        tc_fence_after();
+        const uint64_t a0 = dA + (uint64_t)((uint32_t)(s * p.stage_bytes) >> 4);
+        if (elect_one()) {
+#pragma unroll
+          for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t ad = a0 + (uint64_t)((a * kRowTap) >> 4) + 2 * k;
+              const uint64_t bd = dB + (uint64_t)(((py * 3 + a) * kBBytes) >> 4) + 2 * k;
+              if (py == 0 && a == 0 && k == 0) umma_bf16_imm<false>(d_tmem, ad, bd, idesc);
+              else umma_bf16_imm<true>(d_tmem, ad, bd, idesc);
+            }
+          umma_commit(&empty_bar[s]);
+          if (py == 1) umma_commit(&tmem_full[as]);
+        }
+        __syncwarp();
+        if (++s == p.num_stages) { s = 0; phase ^= 1; }
+      }
+      if (++as == 2) { as = 0; acc_phase ^= 1; }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
@@ -705,6 +774,38 @@ __device__ __forceinline__ void igemm_body(const IgemmParams& p, const int cta, 
 #pragma unroll
             for (int j = 0; j < 4; ++j) d4[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
           }
+        }
+      } else if constexpr (MODE == EPI_DOWN2) {
+        // Conv2d k6 s2 p2 (SRFBN's x2 geometry) with the three column taps b = kx>>1 in output-shift form: row =
+        // pixel-pair column x' = x0 + xi of LR row Y, accumulator columns [b*32, b*32+32) hold
+        // P_b[Y, x'] = sum over (ky, px, c) of HR[2(Y + (ky>>1) - 1) + (ky&1), 2x' + px, c] * W[o, c, ky, 2b + px], and
+        // out[Y, X] = P_0[Y, X-1] + P_1[Y, X] + P_2[Y, X+1]: every HR pixel is loaded once per tile (1.25 x 16/14 with
+        // the row halo and the overlapping columns) instead of once per column tap.  A TMEM lane quarter is two tile
+        // rows of 16 columns, so the neighbours are the adjacent lanes; columns 1..14 of a tile are finished.
+        const int xi = row & 15;
+        const int Y = t.y0 + (row >> 4), X = t.x0 + xi;
+        const bool valid = (xi >= 1) && (xi <= 14) && (Y < p.out_h) && (X < p.out_w);
+        const PreluCfg pc = make_prelu(s_bias[p.bias_n], p.act);
+        uint32_t acc[32], vl[32], vr[32];
+        tmem_ld32(taddr + 32, acc);
+        tmem_ld32(taddr, vl);
+        tmem_ld32(taddr + 64, vr);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive_warp(&tmem_empty[as]);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float l = __shfl_up_sync(0xffffffffu, __uint_as_float(vl[j]), 1);
+          const float r = __shfl_down_sync(0xffffffffu, __uint_as_float(vr[j]), 1);
+          acc[j] = __float_as_uint((__uint_as_float(acc[j]) + l) + r);
+        }
+        if (valid) {
+          uint32_t o[16];
+          convert32(acc, s_bias, pc, o);
+          uint4* d4 = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) +
+                                               (((int64_t)t.b * p.out_h + Y) * p.out_w + X) * p.out_pitch + p.out_off);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) d4[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
         }
       } else {  // EPI_CONV_OUT
         // 3x3 conv in "output-shift" form: row = INPUT pixel (xi, yi) of a 16x8 tile whose origin is

@@ -90,7 +90,7 @@ int make_w_map(CUtensorMap* m, const void* base, int64_t K, int64_t N, int ck, i
 // ------------------------------------------------------------------------------------------------
 // kernel variants
 // ------------------------------------------------------------------------------------------------
-enum Variant : int { V_PW32 = 0, V_PW128, V_DECONV, V_CONVOUT, V_FUSED_TRAN, V_FUSED_PLAIN, V_FINALIZE, V_DECONV2, V_GROUP_TRAN, V_GROUP_PLAIN, V_COUNT };
+enum Variant : int { V_PW32 = 0, V_PW128, V_DECONV, V_CONVOUT, V_FUSED_TRAN, V_FUSED_PLAIN, V_FINALIZE, V_DECONV2, V_GROUP_TRAN, V_GROUP_PLAIN, V_DOWN2, V_COUNT };
 
 // kernel classes for the per-launch accounting bench.py reads (vsr_srfbn_profile_*)
 static_assert(VSR_SRFBN_KERNEL_CLASSES == 11, "header constant");
@@ -211,6 +211,7 @@ int launch_layer(const Layer& L, cudaStream_t st) {
     case V_DECONV: return launch_variant<EPI_DECONV, 32, 256>(L, st);
     case V_CONVOUT: return launch_variant<EPI_CONV_OUT, 32, 32>(L, st);
     case V_DECONV2: return launch_variant<EPI_DECONV2, 32, 128>(L, st);
+    case V_DOWN2: return launch_variant<EPI_DOWN2, 64, 96>(L, st);
     default: return VSR_ERR_INVALID_ARG;
   }
 }
@@ -221,6 +222,7 @@ size_t variant_smem(int variant, int chunks, size_t ring) {
     case V_PW128:
     case V_DECONV2: return igemm_smem_bytes<32, 128>(chunks, ring);
     case V_DECONV: return igemm_smem_bytes<32, 256>(chunks, ring, kDeconvStageBytes);
+    case V_DOWN2: return igemm_smem_bytes<64, 96>(chunks, ring);
     default: return igemm_smem_bytes<32, 32>(chunks, ring, kConvOutStageBytes);
   }
 }
@@ -419,57 +421,57 @@ int build_deconv2(Layer& L, const void* x, int B, int h, int w, const void* w_de
   return VSR_OK;
 }
 
-// Conv2d(32,32,6,2,2) + PReLU: xhr (B,2h,2w,32) NHWC -> out (B,h,w,32).  Input pixel (2Y-2+ky, 2X-2+kx): the
-// row parity ky&1 selects one of two tensor maps over every other HR row (no element strides), the column parity
-// kx&1 the channel-offset half of a 64-element (pixel pair x channel) inner dimension; TMA zero fill is the padding.
+// Conv2d(32,32,6,2,2) + PReLU: xhr (B,2h,2w,32) NHWC -> out (B,h,w,32).  Input pixel (2Y-2+ky, 2X-2+kx) with
+// (ky, kx) = (2a + py, 2b + px): the row parity py selects one of two tensor maps over every other HR row (no element
+// strides); a row of such a map is w pixel pairs of 128 bytes (px, channel) = one K chunk of 64; the three row taps a
+// are one 10-row box read 0 / 1 / 2 tile rows (2048 bytes) in; the three column taps b are NOT loaded as shifted boxes:
+// they are 3 x 32 accumulator columns (N = 96) and the epilogue adds the neighbours' partials (EPI_DOWN2, 16-column
+// tiles that finish their 14 interior columns).  Per 112 output pixels: 2 boxes of 20 KB (1.43 x the HR pixels they
+// cover) and 24 MMAs of N = 96, against 12 boxes of 10 KB (3.75 x) and 72 MMAs of N = 32 with the column taps as
+// input shifts -- that version kept only 60 KB in flight per SM and ran at the latency of its loads (6.6 ms per
+// launch at C4).  TMA zero fill is the padding (column -1 of the first tile included).
 int build_downconv2(Layer& L, const void* xhr, int B, int h, int w, const void* w_dev, const float* bias_dev, void* out) {
   memset(&L, 0, sizeof(L));
-  L.variant = V_PW32;
+  L.variant = V_DOWN2;
   IgemmParams& p = L.p;
   EncodeTiledFn enc = encode_fn();
   if (!enc) return VSR_ERR_STATE;
   for (int py = 0; py < 2; ++py) {
     cuuint64_t dims[4] = {64, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)B};
     cuuint64_t strides[3] = {128, (cuuint64_t)256 * w, (cuuint64_t)256 * w * h};
-    cuuint32_t box[4] = {32, (cuuint32_t)kTW, (cuuint32_t)kTH + 2, 1};
+    cuuint32_t box[4] = {64, (cuuint32_t)kTW, (cuuint32_t)kTH + 2, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     void* base = const_cast<uint8_t*>(reinterpret_cast<const uint8_t*>(xhr)) + (size_t)py * 128 * w;
     CUresult r = enc(&p.a_maps[py], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return VSR_ERR_CUDA_BASE + 999;
   }
-  int rc = make_w_map(&p.b_map, w_dev, 36 * kNF, 32, 32, 32);
+  int rc = make_w_map(&p.b_map, w_dev, 6 * 64, 96, 64, 96);
   if (rc) return rc;
-  // tap (ky, kx) = (2*a + py, 2*b + px): half-resolution offsets dy = a-1, dx = b-1.  For fixed (py, px, dx) the three
-  // dy taps are one 10-row box read 0 / 1 / 2 rows in: 12 boxes per tile instead of 36.  Chunk order (= weight
-  // packing order, pack_downconv2): ((py*2 + px)*3 + b)*3 + a; one pipeline stage = the 18 taps of one row parity.
-  constexpr int kBox = kTW * (kTH + 2) * 64;   // 10240 bytes
+  // chunk = py*3 + a (= weight packing order, pack_downconv2); one pipeline stage = one row parity = one box
+  constexpr int kBox = kTW * (kTH + 2) * 128;   // 20480 bytes
   for (int py = 0; py < 2; ++py)
-    for (int px = 0; px < 2; ++px)
-      for (int b = 0; b < 3; ++b)
-        for (int a = 0; a < 3; ++a) {
-          Chunk& c = p.chunks[((py * 2 + px) * 3 + b) * 3 + a];
-          c.map = (int8_t)py;
-          c.dy = -1;
-          c.dx = (int8_t)(b - 1);
-          c.c0 = px * 32;
-          c.a_off = (px * 3 + b) * kBox + a * (kTW * 64);
-          c.tx = a == 0 ? kBox : 0;
-        }
-  // one pipeline stage = the 18 taps of one row parity (6 boxes, 60 KB), 2 stages.  Measured (C4, per pass, 18 launches):
-  // this 121 ms; one box per stage x 14 stages 179 ms -- every stage hand-over costs the single MMA-issuing thread a
-  // barrier round trip, and 12 of them per 128-pixel tile outweigh the deeper prefetch.
-  p.num_chunks = 36;
-  p.cps = 18;
-  p.stage_bytes = 6 * kBox;
-  p.num_stages = 2;
+    for (int a = 0; a < 3; ++a) {
+      Chunk& c = p.chunks[py * 3 + a];
+      c.map = (int8_t)py;
+      c.dy = -1;
+      c.dx = 0;
+      c.c0 = 0;
+      c.a_off = a * (kTW * 128);
+      c.tx = a == 0 ? kBox : 0;
+    }
+  p.num_chunks = 6;
+  p.cps = 3;
+  p.stage_bytes = kBox;
+  p.num_stages = 6;
   p.n_tiles = 1;
-  p.tiles_x = ceil_div(w, kTW);
+  p.tile_w = kTW - 2;                 // 14 finished columns per 16-column tile
+  p.tile_h = kTH;
+  p.org_x = -1;
+  p.tiles_x = ceil_div(w, kTW - 2);
   p.tiles_y = ceil_div(h, kTH);
   p.batch = B;
-  p.tile_w = kTW;
-  p.tile_h = kTH;
   p.bias = bias_dev;
   p.bias_n = kNF;
   p.act = 1;
@@ -727,16 +729,17 @@ void pack_deconv2(const float* w, uint16_t* dst) {
           dst[(s * 32 + o) * 288 + t * 32 + c] = f2bf(w[((c * 32 + o) * 6 + ky) * 6 + kx]);
         }
 }
-// x2: Conv2d weight (o, c, 6, 6) s2 p2 -> [32 = o][1152 = chunk*32 + c], chunk = ((py*2 + px)*3 + b)*3 + a for tap
-// (ky, kx) = (2a + py, 2b + px) -- the order build_downconv2 issues its taps in
+// x2: Conv2d weight (o, c, 6, 6) s2 p2 -> [96 = b*32 + o][384 = chunk*64 + px*32 + c], chunk = py*3 + a, for tap
+// (ky, kx) = (2a + py, 2b + px) -- the order build_downconv2 issues its K chunks in; the column tap b is an N slice
 void pack_downconv2(const float* w, uint16_t* dst) {
-  for (int o = 0; o < 32; ++o)
-    for (int py = 0; py < 2; ++py)
-      for (int px = 0; px < 2; ++px)
-        for (int b = 0; b < 3; ++b)
-          for (int a = 0; a < 3; ++a) {
-            const int chunk = ((py * 2 + px) * 3 + b) * 3 + a, ky = 2 * a + py, kx = 2 * b + px;
-            for (int c = 0; c < 32; ++c) dst[o * 1152 + chunk * 32 + c] = f2bf(w[((o * 32 + c) * 6 + ky) * 6 + kx]);
+  for (int b = 0; b < 3; ++b)
+    for (int o = 0; o < 32; ++o)
+      for (int py = 0; py < 2; ++py)
+        for (int a = 0; a < 3; ++a)
+          for (int px = 0; px < 2; ++px) {
+            const int chunk = py * 3 + a, ky = 2 * a + py, kx = 2 * b + px;
+            for (int c = 0; c < 32; ++c)
+              dst[(b * 32 + o) * 384 + chunk * 64 + px * 32 + c] = f2bf(w[((o * 32 + c) * 6 + ky) * 6 + kx]);
           }
 }
 // conv_out (3,32,3,3) for the output-shift form -> [32 = (ky*3+kx)*3 + o][32 = c], rows 27..31 zero
@@ -930,7 +933,7 @@ static void layout_weights(vsr_srfbn_plan* pl) {
   const bool x2 = pl->cfg.upscale == 2;   // k6 s2 p2: 3x3 LR taps x 4 sub-positions / 36 taps; else k8 s4 p2
   for (int i = 0; i < 6; ++i) put(W_UP0 + i, x2 ? 128 : 512, x2 ? 288 : 128, 33);
   for (int i = 0; i < 5; ++i) put(W_DOWNTRAN0 + i, 32, 32 * (i + 2), 33);
-  for (int i = 0; i < 6; ++i) put(W_DOWN0 + i, x2 ? 32 : 128, x2 ? 1152 : 512, 33);
+  for (int i = 0; i < 6; ++i) put(W_DOWN0 + i, x2 ? 96 : 128, x2 ? 384 : 512, 33);
   put(W_COMPRESS_OUT, 32, 192, 33);
   put(W_OUT, x2 ? 128 : 512, x2 ? 288 : 128, 33);
   put(W_CONV_OUT, 32, 32, 16 + 7);
