@@ -571,8 +571,11 @@ __device__ __forceinline__ void igemm_body(const IgemmParams& p, const int cta, 
       if (++as == 2) { as = 0; acc_phase ^= 1; }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (the warp walks the loop, one elected lane issues) =====================
+    // With the loop inside `if (lane == 0)` every operand of a tcgen05.mma went through ELECT + R2UR and the chunk
+    // table through per-thread loads: ~10 instructions / ~125 cycles per MMA on the one thread, which is the MMA time
+    // itself for N <= 128.  Walked by the converged warp the loop state is warp-uniform (uniform registers, LDCU).
+    {
       constexpr uint32_t idesc = make_idesc(BN);
       mbar_wait(b_full, 0);
       tc_fence_after();
@@ -590,16 +593,19 @@ __device__ __forceinline__ void igemm_body(const IgemmParams& p, const int cta, 
           const int nk = min(p.cps, p.num_chunks - kc0);
           mbar_wait(&full_bar[s], phase);
           tc_fence_after();
-          for (int j = 0; j < nk; ++j) {
-            const int kc = kc0 + j;
-            const uint64_t a0 = dA + (uint64_t)((s * p.stage_bytes + p.chunks[kc].a_off) >> 4);
-            const uint64_t b0 = dB + (uint64_t)((kc * kBBytes) >> 4);
-            if (!(VSR_DBG(p) & 4))
+          if (elect_one()) {
+            for (int j = 0; j < nk; ++j) {
+              const int kc = kc0 + j;
+              const uint64_t a0 = dA + (uint64_t)((s * p.stage_bytes + p.chunks[kc].a_off) >> 4);
+              const uint64_t b0 = dB + (uint64_t)((kc * kBBytes) >> 4);
+              if (!(VSR_DBG(p) & 4))
 #pragma unroll
-            for (int k = 0; k < CK / 16; ++k) umma_bf16(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, (uint32_t)((kc | k) != 0));
+              for (int k = 0; k < CK / 16; ++k) umma_bf16(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, (uint32_t)((kc | k) != 0));
+            }
+            umma_commit(&empty_bar[s]);                      // frees the stage when these MMAs retire
+            if (kc0 + nk >= p.num_chunks) umma_commit(&tmem_full[as]);
           }
-          umma_commit(&empty_bar[s]);                      // frees the stage when these MMAs retire
-          if (kc0 + nk >= p.num_chunks) umma_commit(&tmem_full[as]);
+          __syncwarp();
           if (++s == p.num_stages) { s = 0; phase ^= 1; }
         }
         if (++as == 2) { as = 0; acc_phase ^= 1; }
