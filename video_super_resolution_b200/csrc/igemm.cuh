@@ -32,6 +32,8 @@ constexpr int kDeconvThreads = 64 + 32 * kDeconvEpiWarps;
 constexpr int kConvOutPitch = 33;                          // floats per row of the tap-partial exchange buffer
 constexpr int kConvOutStageBytes = 2 * 128 * kConvOutPitch * 4;
 
+enum EpiMode : int;
+__host__ __device__ constexpr int igemm_threads(int mode);
 enum EpiMode : int {
   EPI_ROWS = 0,        // BN=32: 64-byte BF16 row per pixel at out + row*pitch + off
   EPI_DECONV = 1,      // BN=256 (one half of the 16 sub-positions): HR block layout or plain NHWC HR
@@ -39,6 +41,13 @@ enum EpiMode : int {
   EPI_DECONV2 = 3,     // BN=128 (4 sub-positions x 32): x2 transposed conv k6 s2 p2, plain NHWC HR output
   EPI_DOWN2 = 4,       // BN=96 (3 column taps x 32): x2 strided conv k6 s2 p2 with the column taps in output-shift form
 };
+
+constexpr int kDown2EpiWarps = 8;    // EPI_DOWN2 / EPI_DECONV2: 2 warps per TMEM lane quarter (16 of the 32 channels / one ry each)
+constexpr int kDeconv2StageBytes = kDown2EpiWarps * 32 * 128;   // EPI_DECONV2: per warp 32 LR pixels x one HR pixel pair
+// threads of an igemm CTA: producer warp + MMA warp + the mode's epilogue warps
+__host__ __device__ constexpr int igemm_threads(int mode) {
+  return (mode == EPI_DECONV) ? kDeconvThreads : (mode == EPI_DOWN2 || mode == EPI_DECONV2) ? 64 + 32 * kDown2EpiWarps : kIgemmThreads;
+}
 
 struct Chunk {
   int8_t map;   // index into a_maps
@@ -317,6 +326,17 @@ __device__ __forceinline__ void convert32(const uint32_t (&v)[32], const float* 
     o[2 * j + 1] = prelu_pack(__uint_as_float(v[4 * j + 2]) + bb.z, __uint_as_float(v[4 * j + 3]) + bb.w, c);
   }
 }
+// 16 accumulator columns -> 8 packed BF16 pairs
+__device__ __forceinline__ void convert16(const uint32_t (&v)[16], const float* bias, const PreluCfg& c,
+                                          uint32_t (&o)[8]) {
+  const float4* b4 = reinterpret_cast<const float4*>(bias);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 bb = b4[j];
+    o[2 * j] = prelu_pack(__uint_as_float(v[4 * j]) + bb.x, __uint_as_float(v[4 * j + 1]) + bb.y, c);
+    o[2 * j + 1] = prelu_pack(__uint_as_float(v[4 * j + 2]) + bb.z, __uint_as_float(v[4 * j + 3]) + bb.w, c);
+  }
+}
 __device__ __forceinline__ void zero16(uint32_t (&o)[16]) {
 #pragma unroll
   for (int j = 0; j < 16; ++j) o[j] = 0u;
@@ -443,12 +463,18 @@ __device__ __forceinline__ void tma_load_4d_hint(void* smem_dst, const CUtensorM
 // the EPI_DECONV instance on CTAs [0, n_deconv) of its grid, with the tile hand-off `gs`.
 template <int MODE, int CK, int BN>
 __device__ __forceinline__ void igemm_body(const IgemmParams& p, const int cta, const int ncta, const GroupSync* gs) {
-  constexpr int kThreadsHere = (MODE == EPI_DECONV || MODE == EPI_DECONV2) ? kDeconvThreads : kIgemmThreads;
+  constexpr int kThreadsHere = igemm_threads(MODE);
   constexpr int kEpiThreads = kThreadsHere - 64;
   static_assert(CK == 32 || CK == 64, "K chunk is 32 (64B swizzle) or 64 (128B swizzle) BF16");
   static_assert(BN == 16 || BN == 32 || BN == 96 || BN == 128 || BN == 256, "supported N tiles");
   constexpr int kSwz = CK * 2;
-  constexpr int kTmemCols = (2 * BN < 32) ? 32 : (BN == 96 ? 256 : 2 * BN);   // two accumulator stages (a power of two)
+  // accumulator stages: two; four for the x2 layers, whose MMA time per tile (~1150 cycles) is of the order of one
+  // commit -> wake -> tcgen05.ld -> arrive -> wake round trip, so with two the issuer and the epilogue took turns
+  // (each waited ~45 % of the time on the other).  Only for kernels that are alone on their SM (512 columns).
+  constexpr int kAccStages = (MODE == EPI_DECONV2 || MODE == EPI_DOWN2) ? 4 : 2;
+  constexpr int kTmemCols = (kAccStages * BN <= 32) ? 32 : (kAccStages * BN <= 64) ? 64 : (kAccStages * BN <= 128) ? 128
+                          : (kAccStages * BN <= 256) ? 256 : 512;
+  static_assert(kAccStages * BN <= 512, "TMEM columns");
   constexpr int kABytes = a_stage_bytes<CK>();
   constexpr int kBBytes = b_chunk_bytes<CK, BN>();
 
@@ -462,8 +488,8 @@ __device__ __forceinline__ void igemm_body(const IgemmParams& p, const int cta, 
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);          // [kMaxStages]
   uint64_t* empty_bar = full_bar + kMaxStages;                     // [kMaxStages]
   uint64_t* tmem_full = empty_bar + kMaxStages;                    // [2]
-  uint64_t* tmem_empty = tmem_full + 2;                            // [2]
-  uint64_t* b_full = tmem_empty + 2;                               // [1]
+  uint64_t* tmem_empty = tmem_full + 4;                            // [4]
+  uint64_t* b_full = tmem_empty + 4;                               // [1]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_full + 1);
   float* s_bias = reinterpret_cast<float*>(tail + 512);            // up to 384 floats
   uint8_t* s_stage = tail + 2048;                                  // EPI_DECONV store staging (64 KB)
@@ -478,7 +504,7 @@ __device__ __forceinline__ void igemm_body(const IgemmParams& p, const int cta, 
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kAccStages; ++s) {
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], kEpiThreads / 32);
     }
@@ -568,7 +594,7 @@ __device__ __forceinline__ void igemm_body(const IgemmParams& p, const int cta, 
         __syncwarp();
         if (++s == p.num_stages) { s = 0; phase ^= 1; }
       }
-      if (++as == 2) { as = 0; acc_phase ^= 1; }
+      if (++as == kAccStages) { as = 0; acc_phase ^= 1; }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (the warp walks the loop, one elected lane issues) =====================
@@ -608,7 +634,7 @@ __device__ __forceinline__ void igemm_body(const IgemmParams& p, const int cta, 
           __syncwarp();
           if (++s == p.num_stages) { s = 0; phase ^= 1; }
         }
-        if (++as == 2) { as = 0; acc_phase ^= 1; }
+        if (++as == kAccStages) { as = 0; acc_phase ^= 1; }
       }
     }
   } else if (warp < 2 + kEpiThreads / 32) {
@@ -757,29 +783,44 @@ __device__ __forceinline__ void igemm_body(const IgemmParams& p, const int cta, 
         }
       } else if constexpr (MODE == EPI_DECONV2) {
         // ConvTranspose2d k6 s2 p2 (SRFBN's x2 geometry): row = LR pixel (Y,X), the 3x3 LR taps are the
-        // K chunks, column group s = ry*2+rx is HR pixel (2Y+ry, 2X+rx): HR rows 2Y and 2Y+1 each get
-        // 128 contiguous bytes from this thread, consecutive lanes write consecutive 128-byte pieces.
-        const int Y = t.y0 + (row >> 4), X = t.x0 + (row & 15);
-        const bool valid = (Y < p.lr_h) && (X < p.lr_w);
+        // K chunks, column group s = ry*2+rx is HR pixel (2Y+ry, 2X+rx).  8 epilogue warps, 2 per TMEM lane quarter:
+        // a warp converts both rx of one ry, i.e. the 128 contiguous bytes (HR pixel pair) of each of its 32 LR
+        // pixels, stages them as a [32 x 128 B] tile in the 128B-swizzle pattern and stores each of its two tile rows
+        // with one TMA bulk tensor store (16 pairs = 2 KB contiguous; clipped at the tensor edge).  The version that
+        // stored from registers (a 16-byte piece per lane at a 128-byte stride: 32 partial sectors per instruction)
+        // spent half of the layer's time in the LSU: 70.6 ms per C4 pass, 36 ms with the stores knocked out.
         const PreluCfg pc = make_prelu(s_bias[p.bias_n], 1);
-        const int64_t W2 = 2 * (int64_t)p.lr_w;
-        uint8_t* base = reinterpret_cast<uint8_t*>(p.out) + (((int64_t)t.b * 2 * p.lr_h + 2 * Y) * W2 + 2 * X) * 64;
-        // 16 epilogue warps, 4 per TMEM lane quarter: each converts ONE of the four sub-positions (with 4 warps doing
-        // all four in turn the layer ran at 30 % of the write bandwidth: the epilogue, not the MMAs, was its floor)
-        {
-          const int cg = (warp - 2) >> 2;
-          uint32_t v[32];
-          tmem_ld32(taddr + cg * 32, v);
-          tmem_ld_wait();
-          tc_fence_before();
-          mbar_arrive_warp(&tmem_empty[as]);
-          if (valid) {
-            uint32_t o[16];
-            convert32(v, s_bias, pc, o);
-            uint4* d4 = reinterpret_cast<uint4*>(base + ((cg >> 1) * W2 + (cg & 1)) * 64);
+        const int ry = (warp - 2) >> 2;
+        uint8_t* stg = s_stage + (warp - 2) * (32 * 128);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) d4[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        for (int rx = 0; rx < 2; ++rx) {
+          uint32_t v[32];
+          tmem_ld32(taddr + (ry * 2 + rx) * 32, v);
+          tmem_ld_wait();
+          if (rx == 1) {
+            tc_fence_before();
+            mbar_arrive_warp(&tmem_empty[as]);
           }
+          uint32_t o[16];
+          convert32(v, s_bias, pc, o);
+          if (rx == 0) {   // the previous tile's stores must have read the staging tile before it is overwritten
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
+          }
+          uint8_t* srow = stg + lane * 128;
+          const int sw = lane & 7;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(srow + (((rx * 4 + j) ^ sw) << 4)) =
+                make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          const int Yq = t.y0 + 2 * q;
+          tma_store_4d(&p.out_map, stg, 0, t.x0, 2 * Yq + ry, t.b);
+          tma_store_4d(&p.out_map, stg + 16 * 128, 0, t.x0, 2 * (Yq + 1) + ry, t.b);
+          tma_store_commit();
         }
       } else if constexpr (MODE == EPI_DOWN2) {
         // Conv2d k6 s2 p2 (SRFBN's x2 geometry) with the three column taps b = kx>>1 in output-shift form: row =
@@ -792,26 +833,30 @@ __device__ __forceinline__ void igemm_body(const IgemmParams& p, const int cta, 
         const int Y = t.y0 + (row >> 4), X = t.x0 + xi;
         const bool valid = (xi >= 1) && (xi <= 14) && (Y < p.out_h) && (X < p.out_w);
         const PreluCfg pc = make_prelu(s_bias[p.bias_n], p.act);
-        uint32_t acc[32], vl[32], vr[32];
-        tmem_ld32(taddr + 32, acc);
-        tmem_ld32(taddr, vl);
-        tmem_ld32(taddr + 64, vr);
+        // 8 epilogue warps, 2 per TMEM lane quarter: each finishes 16 of the 32 channels (with 4 warps doing all 32
+        // the epilogue was busy 79 % of the time and the MMA issuer waited for accumulators)
+        const int half = (warp - 2) >> 2;
+        uint32_t acc[16], vl[16], vr[16];
+        tmem_ld16(taddr + 32 + 16 * half, acc);
+        tmem_ld16(taddr + 16 * half, vl);
+        tmem_ld16(taddr + 64 + 16 * half, vr);
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive_warp(&tmem_empty[as]);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
+        for (int j = 0; j < 16; ++j) {
           const float l = __shfl_up_sync(0xffffffffu, __uint_as_float(vl[j]), 1);
           const float r = __shfl_down_sync(0xffffffffu, __uint_as_float(vr[j]), 1);
           acc[j] = __float_as_uint((__uint_as_float(acc[j]) + l) + r);
         }
         if (valid) {
-          uint32_t o[16];
-          convert32(acc, s_bias, pc, o);
+          uint32_t o[8];
+          convert16(acc, s_bias + 16 * half, pc, o);
           uint4* d4 = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) +
-                                               (((int64_t)t.b * p.out_h + Y) * p.out_w + X) * p.out_pitch + p.out_off);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) d4[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                                               (((int64_t)t.b * p.out_h + Y) * p.out_w + X) * p.out_pitch + p.out_off +
+                                               32 * half);
+          d4[0] = make_uint4(o[0], o[1], o[2], o[3]);
+          d4[1] = make_uint4(o[4], o[5], o[6], o[7]);
         }
       } else {  // EPI_CONV_OUT
         // 3x3 conv in "output-shift" form: row = INPUT pixel (xi, yi) of a 16x8 tile whose origin is
@@ -863,8 +908,9 @@ __device__ __forceinline__ void igemm_body(const IgemmParams& p, const int cta, 
           }
         }
       }
-      if (++as == 2) { as = 0; acc_phase ^= 1; }
+      if (++as == kAccStages) { as = 0; acc_phase ^= 1; }
     }
+    if (MODE == EPI_DECONV2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (MODE == EPI_DECONV && lane == 0) {
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // the last tile's store
       if (gs != nullptr && prev_tile >= 0) {
@@ -883,7 +929,7 @@ __device__ __forceinline__ void igemm_body(const IgemmParams& p, const int cta, 
 }
 
 template <int MODE, int CK, int BN>
-__global__ void __launch_bounds__((MODE == EPI_DECONV || MODE == EPI_DECONV2) ? kDeconvThreads : kIgemmThreads, 1)
+__global__ void __launch_bounds__(igemm_threads(MODE), 1)
 igemm_kernel(const __grid_constant__ IgemmParams p) {
   igemm_body<MODE, CK, BN>(p, (int)blockIdx.x, (int)gridDim.x, nullptr);
 }

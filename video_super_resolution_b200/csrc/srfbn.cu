@@ -144,7 +144,7 @@ int launch_variant(const Layer& L, cudaStream_t st) {
     if (e != cudaSuccess) return cuda_status(e);
     once.mark(dev);
   }
-  cudaError_t e = launch_pdl(igemm_kernel<MODE, CK, BN>, L.grid, (MODE == EPI_DECONV || MODE == EPI_DECONV2) ? kDeconvThreads : kIgemmThreads,
+  cudaError_t e = launch_pdl(igemm_kernel<MODE, CK, BN>, L.grid, igemm_threads(MODE),
                              L.smem, st, L.p);
   if (e != cudaSuccess) return cuda_status(e);
   return after_launch();
@@ -219,8 +219,8 @@ int launch_layer(const Layer& L, cudaStream_t st) {
 size_t variant_smem(int variant, int chunks, size_t ring) {
   switch (variant) {
     case V_PW32: return igemm_smem_bytes<32, 32>(chunks, ring);
-    case V_PW128:
-    case V_DECONV2: return igemm_smem_bytes<32, 128>(chunks, ring);
+    case V_PW128: return igemm_smem_bytes<32, 128>(chunks, ring);
+    case V_DECONV2: return igemm_smem_bytes<32, 128>(chunks, ring, kDeconv2StageBytes);
     case V_DECONV: return igemm_smem_bytes<32, 256>(chunks, ring, kDeconvStageBytes);
     case V_DOWN2: return igemm_smem_bytes<64, 96>(chunks, ring);
     default: return igemm_smem_bytes<32, 32>(chunks, ring, kConvOutStageBytes);
@@ -387,6 +387,18 @@ int build_deconv2(Layer& L, const void* x, int B, int h, int w, const void* w_de
   if (rc) return rc;
   rc = make_w_map(&p.b_map, w_dev, 9 * kNF, 128, 32, 128);
   if (rc) return rc;
+  {   // output: HR rows of w pixel pairs (128 bytes: rx, channel); one store = 16 pairs of one HR row
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return VSR_ERR_STATE;
+    cuuint64_t dims[4] = {64, (cuuint64_t)w, (cuuint64_t)2 * h, (cuuint64_t)B};
+    cuuint64_t strides[3] = {128, (cuuint64_t)128 * w, (cuuint64_t)256 * w * h};
+    cuuint32_t box[4] = {64, (cuuint32_t)kTW, 1, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&p.out_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return VSR_ERR_CUDA_BASE + 999;
+  }
   constexpr int kBox = kTW * (kTH + 2) * 64;   // 10240 bytes
   for (int t = 0; t < 9; ++t) {   // tap at LR (Y+dy, X+dx)
     const int dyi = t / 3, dxi = t % 3;
