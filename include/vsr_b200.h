@@ -349,6 +349,13 @@ int vsr_test_pointwise(const void* x_bf16, int64_t rows, int K, const float* w_h
 int vsr_test_deconv(const void* x_bf16, int B, int h, int w, const float* w_host,
                     const float* b_host, float slope, int block_layout, void* y_bf16,
                     void* workspace, size_t workspace_bytes, vsr_stream_t stream);
+/*   x2_layer : one layer of the x2 geometry (SRFBN's k6 s2 p2; the reference
+ *              hard-wires x4, SRProjectionModule.py:101-103) + PReLU:
+ *              up=1 ConvTranspose2d(32,32,6,2,2): x (B,h,w,32) -> y (B,2h,2w,32), w (32 in,32 out,6,6);
+ *              up=0 Conv2d(32,32,6,2,2): x (B,2h,2w,32) -> y (B,h,w,32), w (32 out,32 in,6,6). */
+int vsr_test_x2_layer(const void* x_bf16, int up, int B, int h, int w, const float* w_host,
+                      const float* b_host, float slope, void* y_bf16, void* workspace,
+                      size_t workspace_bytes, vsr_stream_t stream);
 size_t vsr_test_workspace_bytes(int B, int h, int w);
 /*   fused_down: the kernel the plan uses for the HR half of a feedback group
  *              (SRProjectionModule.py:70-80): PReLU(Conv1x1 over nsrc concatenated HR maps) ->

@@ -63,6 +63,22 @@ def deconv(x_bf16, w, b, slope, block_layout=False):
     return y
 
 
+def x2_layer(x_bf16, w, b, slope, up):
+    """x2 geometry (k6 s2 p2): up: x (B,h,w,32) -> (B,2h,2w,32), w (32 in,32 out,6,6); down: x (B,2h,2w,32) ->
+    (B,h,w,32), w (32 out,32 in,6,6)."""
+    B, H, W, _ = x_bf16.shape
+    h, wd = (H, W) if up else (H // 2, W // 2)
+    shape = (B, 2 * h, 2 * wd, 32) if up else (B, h, wd, 32)
+    y = torch.full(shape, float("nan"), dtype=torch.bfloat16, device=x_bf16.device)
+    ws = _ws(x_bf16.device)
+    w = w.contiguous().float()
+    b = b.contiguous().float()
+    _lib.check(_lib.lib().vsr_test_x2_layer(x_bf16.data_ptr(), int(up), B, h, wd, _fp(w), _fp(b), float(slope),
+                                            y.data_ptr(), ws.data_ptr(), ws.numel(),
+                                            torch.cuda.current_stream().cuda_stream), "test_x2_layer")
+    return y
+
+
 def fused_down(hr_bf16, wt, bt, slope_t, wd, bd, slope_d):
     """hr (nsrc,B,8,h+1,w+1,64) bf16 block layout; wt (32,32*nsrc)|None; wd (32,32,8,8) -> (B,h,w,32) bf16."""
     nsrc, B, _, hb, wb = hr_bf16.shape[:5]

@@ -97,6 +97,34 @@ def test_fused_downtran_downconv(nsrc, B, h, w):
     _close(got, want, f"fused_down nsrc={nsrc} B={B} {h}x{w}")
 
 
+@pytest.mark.parametrize("B,h,w", [(1, 8, 16), (2, 5, 7), (1, 19, 33), (1, 9, 14), (1, 17, 29), (3, 40, 61)])
+def test_x2_transposed_conv_layer(B, h, w):
+    """ConvTranspose2d k6 s2 p2 (x2 geometry): staged TMA stores, ragged tiles on both axes."""
+    g = torch.Generator().manual_seed(B * 100 + h * 10 + w)
+    x = _bf(torch.randn((B, h, w, 32), generator=g))
+    wt = _bf(torch.randn((32, 32, 6, 6), generator=g) / 12).float()
+    b = torch.randn(32, generator=g) * 0.1
+    got = hk.x2_layer(x.to(DEV), wt, b, 0.25, up=True)
+    want = F.prelu(F.conv_transpose2d(x.float().permute(0, 3, 1, 2), wt, b, stride=2, padding=2),
+                   torch.tensor([0.25])).permute(0, 2, 3, 1)
+    _close(got, want, f"deconv2 B={B} {h}x{w}")
+
+
+@pytest.mark.parametrize("B,h,w", [(1, 8, 16), (2, 5, 7), (1, 19, 33), (1, 9, 14), (1, 9, 15), (1, 17, 28), (1, 17, 29),
+                                   (3, 40, 61)])
+def test_x2_strided_conv_layer(B, h, w):
+    """Conv2d k6 s2 p2 with the column taps in output-shift form (16-column tiles finish 14): widths on both
+    sides of the 14-column tile stride, zero padding through TMA fill at every border."""
+    g = torch.Generator().manual_seed(B * 100 + h * 10 + w + 1)
+    x = _bf(torch.randn((B, 2 * h, 2 * w, 32), generator=g))
+    wd = _bf(torch.randn((32, 32, 6, 6), generator=g) / 34).float()
+    b = torch.randn(32, generator=g) * 0.1
+    got = hk.x2_layer(x.to(DEV), wd, b, 0.15, up=False)
+    want = F.prelu(F.conv2d(x.float().permute(0, 3, 1, 2), wd, b, stride=2, padding=2),
+                   torch.tensor([0.15])).permute(0, 2, 3, 1)
+    _close(got, want, f"downconv2 B={B} {h}x{w}")
+
+
 def _psnr(a, b):
     mse = ((a - b) ** 2).mean().item()
     return 10 * math.log10(255.0 ** 2 / max(mse, 1e-20))

@@ -1474,6 +1474,35 @@ extern "C" int vsr_test_deconv(const void* x_bf16, int B, int h, int w, const fl
   return cuda_status(cudaStreamSynchronize(st));
 }
 
+// x2 geometry (SRFBN's k6 s2 p2, config C4), one layer each through the kernels the plan uses:
+//   up = 1: ConvTranspose2d(32,32,6,2,2) + PReLU, x (B,h,w,32) -> y (B,2h,2w,32), w_host (32 in, 32 out, 6, 6)
+//   up = 0: Conv2d(32,32,6,2,2) + PReLU, x (B,2h,2w,32) -> y (B,h,w,32), w_host (32 out, 32 in, 6, 6)
+extern "C" int vsr_test_x2_layer(const void* x_bf16, int up, int B, int h, int w, const float* w_host,
+                                 const float* b_host, float slope, void* y_bf16, void* workspace,
+                                 size_t workspace_bytes, vsr_stream_t stream) {
+  if (!x_bf16 || !w_host || !b_host || !y_bf16 || !workspace || B <= 0 || h <= 0 || w <= 0) return VSR_ERR_INVALID_ARG;
+  if (workspace_bytes < vsr_test_workspace_bytes(B, h, w)) return VSR_ERR_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  std::vector<uint16_t> wp((size_t)36 * 32 * 32);
+  if (up) pack_deconv2(w_host, wp.data());
+  else pack_downconv2(w_host, wp.data());
+  float bias[33];
+  memcpy(bias, b_host, 32 * 4);
+  bias[32] = slope;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  int rc = upload(ws, wp.data(), wp.size() * 2, st);
+  if (rc) return rc;
+  rc = upload(ws + 256 * 1024, bias, sizeof(bias), st);
+  if (rc) return rc;
+  Layer L;
+  const float* bdev = reinterpret_cast<const float*>(ws + 256 * 1024);
+  rc = up ? build_deconv2(L, x_bf16, B, h, w, ws, bdev, y_bf16) : build_downconv2(L, x_bf16, B, h, w, ws, bdev, y_bf16);
+  if (rc) return rc;
+  rc = launch_layer(L, st);
+  if (rc) return rc;
+  return cuda_status(cudaStreamSynchronize(st));
+}
+
 // downtran (nsrc >= 2; wt (32, 32*nsrc) fp32 host, bt (32), slope_t) + PReLU + Conv2d(32,32,8,4,2) (wd (32,32,8,8),
 // bd (32), slope_d) + PReLU through the fused kernel and finalize_lr_kernel.  hr: nsrc maps in block layout,
 // contiguous (nsrc, B, h+1, w+1, 16, 32) BF16.  y (B,h,w,32) BF16.  workspace additionally holds the fp32
