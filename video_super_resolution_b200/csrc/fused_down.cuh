@@ -269,10 +269,11 @@ __device__ __forceinline__ void fused_body(const FusedDownParams& p, const int c
     }
   } else if (warp == 1 || (HAS_TRAN && warp == kFusedBWarp)) {
     // ===================== MMA issuers =====================
-    // One thread runs the whole role (no warp-wide waits / __syncwarp per box): timing experiments
-    // showed this thread's instruction stream to be co-critical with HBM (each box costs it a barrier
-    // wait, four MMA issues and a commit), so descriptors are pre-built and only offsets are added.
-    if (lane == 0) {
+    // Timing experiments showed this role's instruction stream to be co-critical with HBM (each box costs it a
+    // barrier wait, four MMA issues and a commit), so descriptors are pre-built and only offsets are added -- and the
+    // loop is walked by the converged warp (its state lives in uniform registers, no ELECT + R2UR per operand as
+    // inside `if (lane == 0)`), one elected lane issues.
+    {
     constexpr uint32_t idesc_a = make_idesc(32);
     constexpr uint32_t idesc_b = make_idesc(128);
     if (HAS_TRAN && warp == 1) mbar_wait(w_full, 0);
@@ -300,17 +301,20 @@ __device__ __forceinline__ void fused_body(const FusedDownParams& p, const int c
           const uint64_t a0 = dA + (uint64_t)((s * kStageBytes) >> 4);
           const uint64_t b0 = dWt + (uint64_t)((j * kWtChunkBytes) >> 4);
           const uint32_t d0 = tmem_base + (uint32_t)(buf * 128 + pair * 64);
-          if (!(VSR_DBG(p) & 1)) {
-            const uint32_t acc = (uint32_t)(j != 0);
-            umma_bf16(d0, a0, b0, idesc_a, acc);
-            umma_bf16(d0, a0 + 2, b0 + 2, idesc_a, 1u);
-            umma_bf16(d0 + 32, a0 + 4, b0, idesc_a, acc);
-            umma_bf16(d0 + 32, a0 + 6, b0 + 2, idesc_a, 1u);
+          if (elect_one()) {
+            if (!(VSR_DBG(p) & 1)) {
+              const uint32_t acc = (uint32_t)(j != 0);
+              umma_bf16(d0, a0, b0, idesc_a, acc);
+              umma_bf16(d0, a0 + 2, b0 + 2, idesc_a, 1u);
+              umma_bf16(d0 + 32, a0 + 4, b0, idesc_a, acc);
+              umma_bf16(d0 + 32, a0 + 6, b0 + 2, idesc_a, 1u);
+            }
+            umma_commit(&empty_bar[s]);
+            if (pair == 1 && j == p.nsrc - 1) umma_commit(&da_full[buf]);
           }
-          umma_commit(&empty_bar[s]);
+          __syncwarp();
           if (++s == p.num_stages) { s = 0; phase ^= 1; }
         }
-      umma_commit(&da_full[buf]);
       ++n_a[buf];
     };
     // phase B of group g: D_B[tb] += H_g * Wd_g^T
@@ -330,18 +334,21 @@ __device__ __forceinline__ void fused_body(const FusedDownParams& p, const int c
       tc_fence_after();
       const uint32_t d = tmem_base + kDB + (uint32_t)(tb * 128);
       const uint64_t b0 = dWd + (uint64_t)((wslot * kWdGroupBytes) >> 4);
-      if (!(VSR_DBG(p) & 8)) {
+      if (elect_one()) {
+        if (!(VSR_DBG(p) & 8)) {
 #pragma unroll
-        for (int kc = 0; kc < 2; ++kc)
+          for (int kc = 0; kc < 2; ++kc)
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(d, a0 + (uint64_t)(kc * 1024 + k * 2), b0 + (uint64_t)(kc * 1024 + k * 2), idesc_b,
-                      (uint32_t)((g | kc | k) != 0));
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(d, a0 + (uint64_t)(kc * 1024 + k * 2), b0 + (uint64_t)(kc * 1024 + k * 2), idesc_b,
+                        (uint32_t)((g | kc | k) != 0));
+        }
+        if (!p.wd_resident) umma_commit(&wd_empty[wslot]);
+        if (HAS_TRAN) umma_commit(h_empty);
+        else umma_commit(&empty_bar[s]);
+        if (g == 3) umma_commit(&db_full[tb]);
       }
-      if (!p.wd_resident) umma_commit(&wd_empty[wslot]);
-      if (HAS_TRAN) umma_commit(h_empty);
-      else umma_commit(&empty_bar[s]);
-      if (g == 3) umma_commit(&db_full[tb]);
+      __syncwarp();
       ++n_wd;
       if (HAS_TRAN) ++n_h;
       else if (++s == p.num_stages) { s = 0; phase ^= 1; }
