@@ -185,11 +185,14 @@ __device__ __forceinline__ void fused_body(const FusedDownParams& p, const int c
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      if (HAS_TRAN) {
+    // walked by the converged warp, one elected lane issues (as the MMA roles: the loop state stays in uniform
+    // registers; "box count, not bytes, limits a single-thread producer")
+    {
+      if (HAS_TRAN && elect_one()) {
         mbar_expect_tx(w_full, (uint32_t)(p.nsrc * kWtChunkBytes));
         for (int j = 0; j < p.nsrc; ++j) tma_load_2d(s_wt + j * kWtChunkBytes, &p.wt_map, w_full, j * 32, 0);
       }
+      __syncwarp();
       griddep_wait();   // weights are static; the HR maps only after the previous layers have completed
       int s = 0;
       uint32_t phase = 0;
@@ -200,12 +203,15 @@ __device__ __forceinline__ void fused_body(const FusedDownParams& p, const int c
         if (tile >= total_tiles) return;
         int px0, py0, pb;
         tile_coord(tile, px0, py0, pb);
-        if (HAS_TRAN) {
-          for (int sp = half * 8; sp < half * 8 + 8; sp += 2)
-            for (int j = 0; j < p.nsrc; ++j) tma_prefetch_4d(&p.hr_maps[j], 0, px0, py0, pb * 8 + (sp >> 1));
-        } else {
-          for (int pr = half * 4; pr < half * 4 + 4; ++pr) tma_prefetch_4d(&p.h0_map, 0, px0, py0, pb * 8 + pr);
+        if (elect_one()) {
+          if (HAS_TRAN) {
+            for (int sp = half * 8; sp < half * 8 + 8; sp += 2)
+              for (int j = 0; j < p.nsrc; ++j) tma_prefetch_4d(&p.hr_maps[j], 0, px0, py0, pb * 8 + (sp >> 1));
+          } else {
+            for (int pr = half * 4; pr < half * 4 + 4; ++pr) tma_prefetch_4d(&p.h0_map, 0, px0, py0, pb * 8 + pr);
+          }
         }
+        __syncwarp();
       };
       {
         int t = cta, hf = 0;
@@ -232,20 +238,22 @@ __device__ __forceinline__ void fused_body(const FusedDownParams& p, const int c
             for (int sp = half * 8; sp < half * 8 + 8; sp += 2) {
               for (int j = 0; j < p.nsrc; ++j) {
                 mbar_wait(&empty_bar[s], phase ^ 1);
-                mbar_expect_tx(&full_bar[s], kStageBytes);
-                if (gs != nullptr) {
-                  // group launch: the newest map's tile comes from the deconv role of this launch (L2); the older
-                  // maps stream from HBM and are marked evict-first so that they do not push it out
-                  if (j == p.nsrc - 1 && !newest_ready) {
-                    spin_until_ge(gs->tile_flags + tile, 32 * gs->epoch, gs->error);
-                    fence_proxy_async_all();
-                    newest_ready = true;
-                  }
-                  tma_load_4d_hint(s_a + s * kStageBytes, &p.hr_maps[j], &full_bar[s], 0, x0, y0, b * 8 + (sp >> 1),
-                                   kL2EvictFirst);
-                } else {
-                  tma_load_4d(s_a + s * kStageBytes, &p.hr_maps[j], &full_bar[s], 0, x0, y0, b * 8 + (sp >> 1));
+                // group launch: the newest map's tile comes from the deconv role of this launch (L2); the older
+                // maps stream from HBM and are marked evict-first so that they do not push it out
+                if (gs != nullptr && j == p.nsrc - 1 && !newest_ready) {
+                  spin_until_ge(gs->tile_flags + tile, 32 * gs->epoch, gs->error);
+                  fence_proxy_async_all();
+                  newest_ready = true;
                 }
+                if (elect_one()) {
+                  mbar_expect_tx(&full_bar[s], kStageBytes);
+                  if (gs != nullptr)
+                    tma_load_4d_hint(s_a + s * kStageBytes, &p.hr_maps[j], &full_bar[s], 0, x0, y0, b * 8 + (sp >> 1),
+                                     kL2EvictFirst);
+                  else
+                    tma_load_4d(s_a + s * kStageBytes, &p.hr_maps[j], &full_bar[s], 0, x0, y0, b * 8 + (sp >> 1));
+                }
+                __syncwarp();
                 if (++s == p.num_stages) { s = 0; phase ^= 1; }
               }
             }
@@ -258,9 +266,12 @@ __device__ __forceinline__ void fused_body(const FusedDownParams& p, const int c
                 fence_proxy_async_all();
                 newest_ready = true;
               }
-              mbar_expect_tx(&full_bar[s], kStageBytes);
-              tma_load_4d(s_a + s * kStageBytes, &p.h0_map, &full_bar[s], 0, x0, y0, b * 8 + 2 * g);
-              tma_load_4d(s_a + s * kStageBytes + 16384, &p.h0_map, &full_bar[s], 0, x0, y0, b * 8 + 2 * g + 1);
+              if (elect_one()) {
+                mbar_expect_tx(&full_bar[s], kStageBytes);
+                tma_load_4d(s_a + s * kStageBytes, &p.h0_map, &full_bar[s], 0, x0, y0, b * 8 + 2 * g);
+                tma_load_4d(s_a + s * kStageBytes + 16384, &p.h0_map, &full_bar[s], 0, x0, y0, b * 8 + 2 * g + 1);
+              }
+              __syncwarp();
               if (++s == p.num_stages) { s = 0; phase ^= 1; }
             }
           }

@@ -520,13 +520,16 @@ __device__ __forceinline__ void igemm_body(const IgemmParams& p, const int cta, 
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (the warp walks the loop, one elected lane issues) =====================
+    {
       // resident weights: every K chunk of this CTA's N tile, once
       const int n_tile0 = cta % p.n_tiles;
-      mbar_expect_tx(b_full, (uint32_t)(p.num_chunks * kBBytes));
-      for (int kc = 0; kc < p.num_chunks; ++kc)
-        tma_load_2d(smem_b + kc * kBBytes, &p.b_map, b_full, kc * CK, n_tile0 * BN);
+      if (elect_one()) {
+        mbar_expect_tx(b_full, (uint32_t)(p.num_chunks * kBBytes));
+        for (int kc = 0; kc < p.num_chunks; ++kc)
+          tma_load_2d(smem_b + kc * kBBytes, &p.b_map, b_full, kc * CK, n_tile0 * BN);
+      }
+      __syncwarp();
       griddep_wait();   // weights are static; activations only after the previous layers have completed
       int s = 0;
       uint32_t phase = 0;
@@ -539,15 +542,18 @@ __device__ __forceinline__ void igemm_body(const IgemmParams& p, const int cta, 
         for (int kc0 = 0; kc0 < p.num_chunks; kc0 += p.cps) {
           const int nk = min(p.cps, p.num_chunks - kc0);
           mbar_wait(&empty_bar[s], phase ^ 1);
-          uint32_t tx = 0;
-          for (int j = 0; j < nk; ++j) tx += (uint32_t)p.chunks[kc0 + j].tx;
-          mbar_expect_tx(&full_bar[s], tx);
-          for (int j = 0; j < nk; ++j) {
-            const Chunk c = p.chunks[kc0 + j];
-            if (c.tx)
-              tma_load_4d(smem_a + s * p.stage_bytes + c.a_off, &p.a_maps[c.map], &full_bar[s], c.c0, t.x0 + c.dx,
-                          t.y0 + c.dy, t.b);
+          if (elect_one()) {
+            uint32_t tx = 0;
+            for (int j = 0; j < nk; ++j) tx += (uint32_t)p.chunks[kc0 + j].tx;
+            mbar_expect_tx(&full_bar[s], tx);
+            for (int j = 0; j < nk; ++j) {
+              const Chunk c = p.chunks[kc0 + j];
+              if (c.tx)
+                tma_load_4d(smem_a + s * p.stage_bytes + c.a_off, &p.a_maps[c.map], &full_bar[s], c.c0, t.x0 + c.dx,
+                            t.y0 + c.dy, t.b);
+            }
           }
+          __syncwarp();
           if (++s == p.num_stages) { s = 0; phase ^= 1; }
         }
       }
