@@ -388,18 +388,23 @@ __device__ __forceinline__ void fused_body(const FusedDownParams& p, const int c
     // every tile needs the 128 KB of 8x8-s4 weights once, 32 KB per sub-position group; all SMs
     // stream the same bytes, so these are L2 hits.  A 2-deep ring instead of a resident copy frees
     // 64 KB of shared memory for the activation pipeline (HBM latency hiding).
-    if (lane == 0 && p.wd_resident) {
-      mbar_expect_tx(&wd_full[0], 4 * kWdGroupBytes);
-      for (int kc = 0; kc < 8; ++kc) tma_load_2d(s_wd + kc * 16384, &p.wd_map, &wd_full[0], kc * 64, 0);
-    } else if (lane == 0) {
+    if (p.wd_resident) {
+      if (elect_one()) {
+        mbar_expect_tx(&wd_full[0], 4 * kWdGroupBytes);
+        for (int kc = 0; kc < 8; ++kc) tma_load_2d(s_wd + kc * 16384, &p.wd_map, &wd_full[0], kc * 64, 0);
+      }
+    } else {
       uint32_t n_wd = 0;
       for (int tile = cta; tile < total_tiles; tile += ncta)
         for (int g = 0; g < 4; ++g) {
           const int slot = n_wd & 1;
           mbar_wait(&wd_empty[slot], ((n_wd >> 1) & 1) ^ 1);
-          mbar_expect_tx(&wd_full[slot], kWdGroupBytes);
-          tma_load_2d(s_wd + slot * kWdGroupBytes, &p.wd_map, &wd_full[slot], (2 * g) * 64, 0);
-          tma_load_2d(s_wd + slot * kWdGroupBytes + 16384, &p.wd_map, &wd_full[slot], (2 * g + 1) * 64, 0);
+          if (elect_one()) {
+            mbar_expect_tx(&wd_full[slot], kWdGroupBytes);
+            tma_load_2d(s_wd + slot * kWdGroupBytes, &p.wd_map, &wd_full[slot], (2 * g) * 64, 0);
+            tma_load_2d(s_wd + slot * kWdGroupBytes + 16384, &p.wd_map, &wd_full[slot], (2 * g + 1) * 64, 0);
+          }
+          __syncwarp();
           ++n_wd;
         }
     }

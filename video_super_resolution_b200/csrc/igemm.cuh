@@ -756,7 +756,7 @@ __device__ __forceinline__ void igemm_body(const IgemmParams& p, const int cta, 
             convert32(v, s_bias, pc, o);
             if (__builtin_expect(!inside, 0)) zero16(o);   // ring positions (tile border only) stay zero
             if (c2 == 0) {   // the previous tile's store must have read the staging tile before it is overwritten
-              if (lane == 0) {                        // (waited for here, after the TMEM read + conversion, not before)
+              if (elect_one()) {                      // (waited for here, after the TMEM read + conversion, not before)
                 if (gs != nullptr && prev_tile >= 0) {   // group launch: the store must have COMPLETED; publish the tile
                   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
                   fence_proxy_async_all();
@@ -776,7 +776,7 @@ __device__ __forceinline__ void igemm_body(const IgemmParams& p, const int cta, 
           }
           fence_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (elect_one()) {   // (the same lane every time: bulk groups are per thread)
             // one box = this warp's 2 block rows x 16 blocks of one sub-position-pair plane; rows or
             // columns beyond the tensor edge are clipped by the TMA unit
             if (VSR_DBG(p) & 8)   // timing experiment: every tile stores to the first tile's place (L2-resident, no DRAM)
@@ -810,7 +810,7 @@ __device__ __forceinline__ void igemm_body(const IgemmParams& p, const int cta, 
           uint32_t o[16];
           convert32(v, s_bias, pc, o);
           if (rx == 0) {   // the previous tile's stores must have read the staging tile before it is overwritten
-            if (lane == 0) tma_store_wait_read();
+            if (elect_one()) tma_store_wait_read();
             __syncwarp();
           }
           uint8_t* srow = stg + lane * 128;
@@ -822,7 +822,7 @@ __device__ __forceinline__ void igemm_body(const IgemmParams& p, const int cta, 
         }
         fence_async_smem();
         __syncwarp();
-        if (lane == 0) {
+        if (elect_one()) {
           const int Yq = t.y0 + 2 * q;
           tma_store_4d(&p.out_map, stg, 0, t.x0, 2 * Yq + ry, t.b);
           tma_store_4d(&p.out_map, stg + 16 * 128, 0, t.x0, 2 * (Yq + 1) + ry, t.b);
@@ -916,8 +916,9 @@ __device__ __forceinline__ void igemm_body(const IgemmParams& p, const int cta, 
       }
       if (++as == kAccStages) { as = 0; acc_phase ^= 1; }
     }
-    if (MODE == EPI_DECONV2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    if (MODE == EPI_DECONV && lane == 0) {
+    __syncwarp();
+    if (MODE == EPI_DECONV2 && elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (MODE == EPI_DECONV && elect_one()) {
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // the last tile's store
       if (gs != nullptr && prev_tile >= 0) {
         fence_proxy_async_all();
