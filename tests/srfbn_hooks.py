@@ -65,18 +65,24 @@ def deconv(x_bf16, w, b, slope, block_layout=False):
 
 def x2_layer(x_bf16, w, b, slope, up):
     """x2 geometry (k6 s2 p2): up: x (B,h,w,32) -> (B,2h,2w,32), w (32 in,32 out,6,6); down: x (B,2h,2w,32) ->
-    (B,h,w,32), w (32 out,32 in,6,6)."""
+    (B,h,w,32), w (32 out,32 in,6,6).  The output sits between two guard bands that must come back untouched
+    (the kernels store through clipped TMA boxes / predicated register stores)."""
     B, H, W, _ = x_bf16.shape
     h, wd = (H, W) if up else (H // 2, W // 2)
     shape = (B, 2 * h, 2 * wd, 32) if up else (B, h, wd, 32)
-    y = torch.full(shape, float("nan"), dtype=torch.bfloat16, device=x_bf16.device)
+    n = shape[0] * shape[1] * shape[2] * shape[3]
+    G = 1 << 16                                   # guard elements on each side (128 KB: more than a tile row)
+    buf = torch.full((n + 2 * G,), 12345.0, dtype=torch.bfloat16, device=x_bf16.device)
+    y = buf[G:G + n].view(shape)
+    y.fill_(float("nan"))
     ws = _ws(x_bf16.device)
     w = w.contiguous().float()
     b = b.contiguous().float()
     _lib.check(_lib.lib().vsr_test_x2_layer(x_bf16.data_ptr(), int(up), B, h, wd, _fp(w), _fp(b), float(slope),
                                             y.data_ptr(), ws.data_ptr(), ws.numel(),
                                             torch.cuda.current_stream().cuda_stream), "test_x2_layer")
-    return y
+    assert bool((buf[:G] == 12345.0).all()) and bool((buf[G + n:] == 12345.0).all()), "x2 layer wrote outside its output"
+    return y.clone()
 
 
 def fused_down(hr_bf16, wt, bt, slope_t, wd, bd, slope_d):
