@@ -595,7 +595,7 @@ def run_b200(args, rank, world, local_rank):
                "pointwise_lr": "igemm_kernel<0, 32, 32>", "finalize_lr": "finalize_lr_kernel",
                "conv_out3x3": "igemm_kernel<2, 32, 32>", "conv_in_gemm": "igemm_kernel<0, 32, 128>",
                "fc_fuse": "fc_fuse_kernel", "im2col": "im2col_kernel"}[dom]
-        tfile = next(f for f in ("traffic_r02.json", "traffic_r01h.json", "traffic_r01f.json")
+        tfile = next(f for f in ("traffic_r02h.json", "traffic_r02.json", "traffic_r01h.json", "traffic_r01f.json")
                      if os.path.exists(os.path.join(ROOT, "profiles", f)))
         tr = [t["dram_read_bytes"] + t["dram_write_bytes"]
               for t in json.load(open(os.path.join(ROOT, "profiles", tfile))) if pat in t["kernel"]]
